@@ -1,0 +1,440 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a.
+//
+//   D[m,n] = act( sum_k A(m,k) * B(n,k) + bias[n] ) + residual[m,n]       (bf16 in, fp32 accumulate)
+//
+// One persistent CTA per SM, 192 threads:
+//   warp 0 (lane 0) : TMA producer   — cp.async.bulk.tensor 2-D boxes into a 128B-swizzled smem ring
+//   warp 1 (lane 0) : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction,
+//                                      accumulators double-buffered in TMEM (2 x BLOCK_N columns)
+//   warps 2..5      : epilogue       — tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
+//                                      bias / ReLU / residual fused, fp32 or bf16 stores
+// Both operands may be K-major ([MN,K] row-major) or MN-major ([K,MN] row-major), selected in the UMMA
+// instruction/smem descriptors, so the forward (X W^T), input-gradient (dY W) and weight-gradient
+// (dY^T X) products of a Linear layer all run here without transposed copies.
+//
+// Replaces (through cuBLAS) nn.Linear / MHA projections / 1x1 conv of lib/sttran.py:336-348,370-372 and
+// lib/transformer.py:9-13,38-42.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace nlv {
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
+constexpr int ATOM_BYTES = 64 * BLOCK_K * 2;          // one [64 mn x 64 k] MN-major box, 8 KiB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512, power of two
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU — trap after ~4 s instead.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout, SWIZZLE_128B, version 1).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);            // start address  [0,14)
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // leading byte offset [16,30)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;       // stride byte offset  [32,46)
+  d |= (uint64_t)1 << 46;                                 // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                                 // layout type: SWIZZLE_128B
+  return d;
+}
+
+struct Params {
+  void* d;
+  const float* bias;
+  const void* residual;
+  int m, n, k;
+  int ldd, ldr;
+  int d_dtype, r_dtype;
+  int relu;
+  int num_m_blocks, num_n_blocks;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Kernel
+// ---------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr int STAGES = C::STAGES;
+  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + C::B_STAGE_BYTES;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_b + STAGES * C::B_STAGE_BYTES;
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tmem_full_bar(s), 1);
+      mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
+  }
+  if (warp == 1) {  // whole warp: allocate TMEM columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+
+  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
+  const int num_k_blocks = (p.k + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== TMA producer =====================
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
+        const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
+          const int k0 = kb * BLOCK_K;
+          const uint32_t sa = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b + stage * C::B_STAGE_BYTES;
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * ATOM_BYTES, &tmap_a, full_bar(stage), m0 + 64 * i, k0);
+          } else {
+            tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(sb + i * ATOM_BYTES, &tmap_b, full_bar(stage), n0 + 64 * i, k0);
+          } else {
+            tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer =====================
+      // instruction descriptor: D=f32, A=B=bf16, majors, N>>3 at [17,23), M>>4 at [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      // K-major  : 8-row groups 1024 B apart (SBO); 16 k-elements = +32 B on the start address
+      // MN-major : 64-mn atoms 8 KiB apart (LBO), 8-k groups 1024 B apart (SBO); 16 k-elements = +2048 B
+      constexpr uint32_t A_LBO = A_MN ? ATOM_BYTES : 16, A_KSTEP = A_MN ? 2048 : 32;
+      constexpr uint32_t B_LBO = B_MN ? ATOM_BYTES : 16, B_KSTEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1;
+        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_a + stage * A_STAGE_BYTES;
+          const uint32_t sb = smem_b + stage * C::B_STAGE_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
+            const uint64_t bdesc = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          if (kb == num_k_blocks - 1) tc_commit(tmem_full_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    int iter = 0;
+    const bool d_bf16 = p.d_dtype == NLV_BF16;
+    const bool vec_ok = d_bf16 ? ((p.ldd & 7) == 0 && ((uintptr_t)p.d & 15) == 0)
+                               : ((p.ldd & 3) == 0 && ((uintptr_t)p.d & 15) == 0);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
+      const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1;
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
+      const int row = m0 + quarter * 32 + lane;
+      const bool row_ok = row < p.m;
+      const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        if (n0 + c0 >= p.n) break;  // warp-uniform
+        uint32_t v[32];
+        tmem_ld32(taddr_row + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N || n0 + c0 + 32 >= p.n) {
+          // last chunk of this tile: the accumulator stage can be handed back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        }
+        if (!row_ok) continue;
+        const int ncol = min(32, p.n - (n0 + c0));
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) f[j] += __ldg(p.bias + n0 + c0 + j);
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.residual != nullptr) {
+          const size_t roff = (size_t)row * p.ldr + n0 + c0;
+          if (p.r_dtype == NLV_BF16) {
+            const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) f[j] += __bfloat162float(r[j]);
+          } else {
+            const float* r = reinterpret_cast<const float*>(p.residual) + roff;
+            if (ncol == 32 && (p.ldr & 3) == 0 && ((uintptr_t)p.residual & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(r + j);
+                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol) f[j] += r[j];
+            }
+          }
+        }
+        const size_t doff = (size_t)row * p.ldd + n0 + c0;
+        if (d_bf16) {
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
+          if (ncol == 32 && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 t;
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+              t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + j) = t;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) o[j] = __float2bfloat16_rn(f[j]);
+          }
+        } else {
+          float* o = reinterpret_cast<float*>(p.d) + doff;
+          if (ncol == 32 && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) o[j] = f[j];
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// Tensor map over a bf16 row-major matrix [rows, cols] (cols contiguous, row stride ld elements).
+int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_cols, int box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return NLV_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box=%dx%d ptr=%p", (int)r, rows, cols, ld,
+              box_cols, box_rows, ptr);
+    return NLV_ERR_CUDA;
+  }
+  return NLV_OK;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const nlv_gemm_args& g, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  CUtensorMap ta, tb;
+  int rc;
+  if (A_MN) rc = make_tmap(&ta, g.a, g.k, g.m, g.lda, 64, BLOCK_K);
+  else      rc = make_tmap(&ta, g.a, g.m, g.k, g.lda, BLOCK_K, BLOCK_M);
+  if (rc != NLV_OK) return rc;
+  if (B_MN) rc = make_tmap(&tb, g.b, g.k, g.n, g.ldb, 64, BLOCK_K);
+  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N);
+  if (rc != NLV_OK) return rc;
+  Params p;
+  p.d = g.d; p.bias = g.bias; p.residual = g.residual;
+  p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.ldr = g.ldr;
+  p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
+  p.num_m_blocks = cdiv(g.m, BLOCK_M);
+  p.num_n_blocks = cdiv(g.n, BLOCK_N);
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+template <int BLOCK_N>
+int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false>(g, s);
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_MN) return launch<BLOCK_N, false, true>(g, s);
+  if (g.a_major == NLV_MAJOR_MN && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, true, false>(g, s);
+  return launch<BLOCK_N, true, true>(g, s);
+}
+
+}  // namespace
+
+int gemm_tc(const nlv_gemm_args& g, cudaStream_t stream) {
+  NLV_CHECK_ARG(((uintptr_t)g.a & 15) == 0 && ((uintptr_t)g.b & 15) == 0, "gemm(bf16): a and b must be 16-byte aligned");
+  NLV_CHECK_ARG((g.lda & 7) == 0 && (g.ldb & 7) == 0, "gemm(bf16): lda=%d and ldb=%d must be multiples of 8", g.lda, g.ldb);
+  if (g.n > 128) return dispatch_major<256>(g, stream);
+  return dispatch_major<128>(g, stream);
+}
+
+}  // namespace nlv

@@ -1,0 +1,104 @@
+"""The oracle restatement against the golden vectors produced by the reference itself
+(oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import cref, model as omodel
+from nlvsgg_b200 import synth
+from tests import golden_util as G
+
+
+def test_state_dict_template_matches_reference_names():
+    # the golden train case lists every parameter that received a gradient in the reference
+    case = G.load_case("sttran_sgdet_train")
+    tmpl = G.sttran_template()
+    params = {k for k in tmpl if "running_" not in k and "num_batches" not in k}
+    assert set(case["grads"].keys()) | set(case["no_grad_params"]) == params
+    assert sum(tmpl[k].numel() for k in params) == 103660503
+
+
+def test_native_draw_union_boxes_golden():
+    z = np.load(G.GOLDEN + "/native_draw_union_boxes.npz")
+    assert np.array_equal(cref.draw_union_boxes(z["box_pairs"], 27), z["out"])
+
+
+def test_native_bbox_overlaps_golden():
+    z = np.load(G.GOLDEN + "/native_bbox_overlaps.npz")
+    out = cref.bbox_overlaps(z["boxes"], z["query"])
+    assert np.array_equal(out, z["out"])
+    assert out[0, 0] == 1.0 and abs(out[1, 1] - 1.0 / 3.0) < 1e-15 and out[2, 2] == 0.0
+
+
+def test_nms_cpu_vs_cuda_threshold_semantics():
+    # two boxes with IoU exactly 0.5 under the +1 convention: kept by the CUDA rule (>), dropped by the CPU rule (>=)
+    d = np.array([[0, 0, 9, 9], [0, 0, 9, 4], [100, 100, 120, 120]], dtype=np.float32)
+    s = np.array([0.9, 0.8, 0.7], dtype=np.float32)
+    assert cref.nms(d, s, 0.5, strict=False).tolist() == [0, 2]
+    assert cref.nms(d, s, 0.5, strict=True).tolist() == [0, 1, 2]
+    assert cref.nms(np.zeros((0, 4), np.float32), np.zeros(0, np.float32), 0.5).tolist() == []
+
+
+def test_roi_align_matches_torchvision():
+    import torchvision
+    rng = np.random.default_rng(0)
+    inp = rng.standard_normal((2, 5, 38, 67)).astype(np.float32)
+    rois = np.array([[0, 10, 20, 300, 200], [1, 0, 0, 1071, 607], [0, 5, 5, 6, 6], [1, -50, -50, 2000, 900]], np.float32)
+    tv = torchvision.ops.roi_align(torch.from_numpy(inp), torch.from_numpy(rois), (7, 7), 1 / 16., 0, aligned=False).numpy()
+    assert np.array_equal(cref.roi_align_forward(inp, rois, 1 / 16., 7, 7, 0), tv)
+
+
+@pytest.mark.parametrize("name", G.model_cases("sttran_"))
+def test_oracle_sttran_matches_reference_golden(name):
+    case = G.load_case(name)
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    sd = synth.make_state_dict(G.sttran_template(), case["seed"])
+    if case["training"]:
+        for k, v in sd.items():
+            if v.is_floating_point() and "running_" not in k:
+                v.requires_grad_(True)
+        pred = omodel.sttran_forward(sd, entry, case["mode"], training=True)
+        loss = omodel.training_loss(pred, entry, case["mode"])
+        loss.backward()
+        assert abs(loss.item() - case["loss"]) <= 1e-5 * abs(case["loss"])
+        for k, dg in case["grads"].items():
+            g = sd[k].grad.double().flatten()
+            assert abs(g.sum().item() - dg["sum"]) <= 2e-4 * dg["abs_sum"] + 1e-7, k
+            assert abs(g.abs().sum().item() - dg["abs_sum"]) <= 2e-4 * dg["abs_sum"] + 1e-7, k
+        for k, v in case["running"].items():
+            assert G.rel_err(sd[k].detach(), v) < 1e-5, k
+    else:
+        with torch.no_grad():
+            pred = omodel.sttran_forward(sd, entry, case["mode"], training=False)
+    for k, want in case["outputs"].items():
+        assert G.rel_err(pred[k].detach(), want) < 2e-5, k
+
+
+def test_oracle_dsg_matches_reference_golden():
+    case = G.load_case("dsg_sgdet_eval")
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    # template = sttran's shared part + dsg-specific transformer names, taken from the fixture-free builder below
+    sd = synth.make_state_dict(dsg_template(), case["seed"])
+    with torch.no_grad():
+        pred = omodel.dsg_forward(sd, entry, case["mode"], training=False)
+    for k, want in case["outputs"].items():
+        assert G.rel_err(pred[k], want) < 2e-5, k
+
+
+def dsg_template():
+    """Names/shapes of lib/dsg_detr.py:STTran (incl. the unused-in-sgdet object-track encoder)."""
+    t = {k: v for k, v in G.sttran_template().items() if not k.startswith("glocal_transformer")}
+    def enc(p, d, ff):
+        t[p + ".self_attn.in_proj_weight"] = torch.empty(3 * d, d); t[p + ".self_attn.in_proj_bias"] = torch.empty(3 * d)
+        t[p + ".self_attn.out_proj.weight"] = torch.empty(d, d); t[p + ".self_attn.out_proj.bias"] = torch.empty(d)
+        t[p + ".linear1.weight"] = torch.empty(ff, d); t[p + ".linear1.bias"] = torch.empty(ff)
+        t[p + ".linear2.weight"] = torch.empty(d, ff); t[p + ".linear2.bias"] = torch.empty(d)
+        for n in ("norm1", "norm2"):
+            t[f"{p}.{n}.weight"] = torch.empty(d); t[f"{p}.{n}.bias"] = torch.empty(d)
+    for i in range(3):
+        enc(f"object_classifier.encoder_tran.layers.{i}", 2376, 1024)
+        enc(f"global_transformer.layers.{i}", 1936, 2048)
+    enc("local_transformer.layers.0", 1936, 2048)
+    t["object_classifier.positional_encoder.pe"] = torch.empty(1, 600, 2376)
+    t["positional_encoder.pe"] = omodel.sinusoidal_pe(400, 1936).unsqueeze(0)
+    return t

@@ -1,0 +1,96 @@
+"""tcgen05 GEMM (and the exact-fp32 SIMT GEMM) against torch fp32 matmul, through the C-ABI."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_major, b_major, bias, residual, relu):
+    A = a.float() if a_major == 0 else a.float().t()
+    B = b.float() if b_major == 0 else b.float().t()
+    y = A.double() @ B.double().t()
+    if bias is not None:
+        y = y + bias.double()
+    if relu:
+        y = torch.relu(y)
+    if residual is not None:
+        y = y + residual.double()
+    return y
+
+
+def _mk(m, k, major, dtype, ld_pad=0):
+    shape = (m, k) if major == 0 else (k, m)
+    cols = shape[1] + ld_pad
+    full = torch.randn(shape[0], cols, device="cuda", dtype=torch.float32).to(dtype)
+    return full[:, :shape[1]]
+
+
+SHAPES = [
+    (128, 256, 64), (128, 128, 128), (200, 1936, 1936), (98, 5808, 1936), (1000, 2048, 1936), (777, 1936, 2048),
+    (64, 512, 12544), (300, 256, 2048), (4321, 1936, 1936), (130, 37, 1024), (50, 26, 1936), (257, 264, 72),
+    (5000, 1024, 2376), (128, 3872, 5808),
+]
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", SHAPES)
+def test_gemm_tc_matches_fp32(cuda_lib, m, n, k, a_major, b_major):
+    from nlvsgg_b200 import ops
+    torch.manual_seed(m * 7 + n * 3 + k)
+    # MN-major operands need their leading dimension (m or n) to be a multiple of 8 (16-byte rows)
+    pad_a = (-m) % 8 if a_major == 1 else (-k) % 8
+    pad_b = (-n) % 8 if b_major == 1 else (-k) % 8
+    a = _mk(m, k, a_major, torch.bfloat16, pad_a)
+    b = _mk(n, k, b_major, torch.bfloat16, pad_b)
+    out = torch.full((m, n), float("nan"), device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out, a_major=a_major, b_major=b_major)
+    ref = _ref(a, b, a_major, b_major, None, None, False)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= 2e-5 * scale + 1e-4, f"err {err} scale {scale}"  # bf16 products are exact in fp32; only summation order differs
+
+
+@pytest.mark.parametrize("d_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,n,k", [(300, 1936, 2048), (1000, 2048, 1936), (70, 40, 200)])
+def test_gemm_tc_epilogue(cuda_lib, m, n, k, d_dtype):
+    from nlvsgg_b200 import ops
+    torch.manual_seed(1)
+    a = _mk(m, k, 0, torch.bfloat16)
+    b = _mk(n, k, 0, torch.bfloat16)
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda")
+    out = torch.empty(m, n, device="cuda", dtype=d_dtype)
+    ops.gemm(a, b, out, bias=bias, residual=res, relu=True)
+    ref = _ref(a, b, 0, 0, bias, res, True)
+    tol = 1e-2 if d_dtype == torch.bfloat16 else 2e-5
+    err = (out.double() - ref).abs().max().item()
+    assert err <= tol * ref.abs().max().item() + 1e-4
+    # output written into a column slice of a wider buffer (token assembly writes [R,1936] in place)
+    wide = torch.zeros(m, n + 24, device="cuda", dtype=d_dtype)
+    ops.gemm(a, b, wide[:, 8:8 + n], bias=bias)
+    ref2 = _ref(a, b, 0, 0, bias, None, False)
+    assert (wide[:, 8:8 + n].double() - ref2).abs().max().item() <= tol * ref2.abs().max().item() + 1e-4
+    assert wide[:, :8].abs().max().item() == 0 and wide[:, 8 + n:].abs().max().item() == 0
+
+
+@pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("m,n,k", [(130, 37, 1024), (50, 26, 1936), (33, 65, 17), (200, 300, 129)])
+def test_gemm_simt_fp32(cuda_lib, m, n, k, a_major, b_major):
+    from nlvsgg_b200 import ops
+    torch.manual_seed(5)
+    a = _mk(m, k, a_major, torch.float32)
+    b = _mk(n, k, b_major, torch.float32)
+    bias = torch.randn(n, device="cuda")
+    out = torch.empty(m, n, device="cuda")
+    ops.gemm(a, b, out, a_major=a_major, b_major=b_major, bias=bias)
+    ref = _ref(a, b, a_major, b_major, bias, None, False)
+    assert (out.double() - ref).abs().max().item() <= 1e-5 * ref.abs().max().item() + 1e-5
+
+
+def test_gemm_rejects_bad_args(cuda_lib):
+    from nlvsgg_b200 import ops
+    a = torch.randn(16, 12, device="cuda").bfloat16()  # ld 12 is not a multiple of 8
+    b = torch.randn(16, 12, device="cuda").bfloat16()
+    out = torch.empty(16, 16, device="cuda")
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, b, out)
