@@ -78,6 +78,93 @@ int nlv_union_mask_pairs(const float* boxes, const int64_t* pair_idx, int r, int
 /* lib/fpn/box_intersections_cpu/bbox.pyx:15-61 bbox_overlaps (float64, +1 convention) -> f64[n,k] */
 int nlv_bbox_overlaps_f64(const double* boxes, int n, const double* query, int k, double* out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Layout / conversion / gather kernels (pair-token construction, lib/sttran.py:381-399)
+ * ------------------------------------------------------------------------------------------ */
+/* 2-D strided dtype conversion (f32 <-> bf16) */
+int nlv_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows, int cols,
+                void* stream);
+/* bf16x3 operand split of an fp32 matrix (parity mode): dst gets 3 blocks along block_dim (0 rows, 1 cols);
+ * pattern 0 = (hi,hi,lo) for A operands, 1 = (hi,lo,hi) for B operands */
+int nlv_split3(const float* src, int lds, long long rows, int cols, void* dst_bf16, int ldd, int block_dim, int pattern,
+               void* stream);
+/* union_feat f32[r,c,7,7] (NCHW, as the reference producer hands it) -> [r*49, c] rows (operand of the
+ * union_func1 1x1 conv, lib/sttran.py:336,386) */
+int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_dtype, void* stream);
+/* im2col of the 2x27x27 spatial masks for Conv2d(2,128,k7,s2,p3) (lib/sttran.py:338): -> [r*196, ldd], 98 cols */
+int nlv_im2col_mask(const float* masks, int r, void* dst, int dst_dtype, int ldd, void* stream);
+/* im2col / col2im of the 3x3 s1 p1 conv (lib/sttran.py:342) over NHWC [r,h,w,c]; column = c*9+ky*3+kx */
+int nlv_im2col_3x3(const void* x, int x_dtype, int r, int h, int w, int c, void* dst, int dst_dtype, void* stream);
+int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, float* dx, void* stream);
+/* MaxPool2d(3,2,1) (lib/sttran.py:341) on NHWC [r,14,14,c] -> [r,7,7,c]; argmax u8 per output */
+int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dtype, uint8_t* argmax, void* stream);
+int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, float* dx, void* stream);
+/* dst[i,:] = src[idx[i],:] (+ add[add_idx[i],:]); idx null = identity, idx<0 = zero row; optional 2nd output.
+ * Builds the sliding-window token stream + frame position embedding (lib/transformer_wk.py:163-171) and the
+ * DSG-DETR class sequences + sinusoidal encoding (lib/dsg_detr.py:545-559). */
+int nlv_gather_rows(const void* src, int src_dtype, int lds, const int* idx, const float* add, const int* add_idx,
+                    int ld_add, long long n_out, int cols, void* dst, int dst_dtype, int ldd, void* dst2,
+                    int dst2_dtype, int ldd2, void* stream);
+/* dst[i,:] (+)= sum_j src[idx[i*fan+j],:] (idx<0 skipped): adjoint of a bounded-fan-out gather */
+int nlv_gather_sum_rows(const float* src, int lds, const int* idx, int fan, long long n_out, int cols, float* dst,
+                        int ldd, int accumulate, void* stream);
+int nlv_scatter_add_rows(const float* src, int lds, const long long* idx, int idx_stride, long long n, int cols,
+                         float* dst, int ldd, void* stream);
+/* rel[r, 0:512|512:1024|1536:1736|1736:1936] from fo[N,1024], pair_idx i64[r,2], labels i64[N], tables [37,200] */
+int nlv_assemble_tokens(const float* fo, const long long* pair_idx, const long long* labels, const float* e1,
+                        const float* e2, long long r, float* rel, void* stream);
+int nlv_assemble_tokens_bwd(const float* drel, const long long* pair_idx, const long long* labels, long long r,
+                            float* dfo, float* de1, float* de2, void* stream);
+/* lib/fpn/box_utils.py:51-63 center_size on boxes[:,1:5] -> f32[n,4] */
+int nlv_center_size(const float* boxes, long long n, float* out, void* stream);
+/* out[cls,c] += sum over rows of class cls of x[row,c] (bias / position-embedding gradients) */
+int nlv_colsum(const void* x, int x_dtype, int ld, long long rows, int cols, const int* row_class, int n_class,
+               float* out, void* stream);
+int nlv_relu_mask(const void* x, int x_dtype, int ldx, const void* gate, int gate_dtype, int ldg, long long rows,
+                  int cols, void* y, int y_dtype, int ldy, void* stream);
+int nlv_add(const float* a, const float* b, long long n, float* y, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Normalisation (lib/transformer.py:15-16,45; lib/sttran.py:43,49,340,344)
+ * ------------------------------------------------------------------------------------------ */
+int nlv_layernorm_fwd(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y,
+                      void* y2, int y2_dtype, float* mean, float* rstd, void* stream);
+int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                      long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, void* stream);
+int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, long long rows, int c, float momentum,
+                 double* sums_ws, float* mean, float* var, float* running_mean, float* running_var, void* stream);
+int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const float* mean, const float* var,
+                 const float* w, const float* b, float eps, int relu, long long rows, int c, void* y, int y_dtype, int ldy,
+                 void* y2, int y2_dtype, int ldy2, void* stream);
+int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
+               const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
+               int use_batch_stats, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
+               float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused variable-length attention over contiguous segments (nn.MultiheadAttention core of
+ * lib/transformer.py:22,51 and nn.TransformerEncoderLayer of lib/dsg_detr.py:502-506)
+ * ------------------------------------------------------------------------------------------ */
+int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                 float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, void* stream);
+int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                 float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
+                 int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                 int dqkv_dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Heads, losses, optimiser (lib/sttran.py:404-409; tools/train_STTran.py:169-195; lib/AdamW.py:52-114)
+ * ------------------------------------------------------------------------------------------ */
+int nlv_heads_activation(const float* logits, long long r, float* att, float* spa, float* con, void* stream);
+int nlv_ce_loss(const float* logits, int ld, int c, const long long* labels, const float* row_weight, long long rows,
+                float* loss, float* dlogits, int ldd, void* stream);
+int nlv_bce_sigmoid_loss(const float* logits, int ld, int c, const unsigned* label_bits, const float* row_weight,
+                         long long rows, float* loss, float* dlogits, int ldd, void* stream);
+int nlv_sumsq(const float* x, long long n, float* out, void* stream);
+int nlv_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, const float* total_sq, float max_norm, void* p_bf16, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

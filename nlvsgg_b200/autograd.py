@@ -1,0 +1,85 @@
+"""torch.autograd glue: one Function per whole model, so the reference training scripts
+(loss.backward(); clip_grad_norm_; optimizer.step()) drive the hand-written backward unchanged."""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+
+from . import engine as E
+from . import model as M
+from . import ops
+
+
+def module_tensors(module: torch.nn.Module) -> Dict[str, torch.Tensor]:
+    P = dict(module.named_parameters())
+    P.update(dict(module.named_buffers()))
+    return P
+
+
+class _WholeModelFn(torch.autograd.Function):
+    """outputs: (object logits [N,37] or empty, attention logits [R,3], spatial probs [R,6], contacting probs [R,17])"""
+
+    @staticmethod
+    def forward(ctx, runner, names: List[str], *params):
+        P = runner.P
+        want_ctx = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        out, saved = runner.fwd(want_ctx)
+        att, spa, con = ops.heads_activation(out["logits26"])
+        obj = out.get("distribution")
+        if obj is None:
+            obj = torch.empty(0, device=att.device)
+        ctx.runner, ctx.saved, ctx.names = runner, saved, names
+        ctx.spa, ctx.con = spa, con
+        ctx.has_obj = "distribution" in out
+        return obj, att, spa, con
+
+    @staticmethod
+    def backward(ctx, dobj, datt, dspa, dcon):
+        spa, con = ctx.spa, ctx.con
+        R = spa.shape[0]
+        d26 = torch.zeros(R, 26, device=spa.device, dtype=torch.float32)
+        if datt is not None:
+            d26[:, 0:3] = datt
+        if dspa is not None:
+            d26[:, 3:9] = dspa * spa * (1.0 - spa)
+        if dcon is not None:
+            d26[:, 9:26] = dcon * con * (1.0 - con)
+        dobj_l = dobj.contiguous() if (ctx.has_obj and dobj is not None) else None
+        grads = ctx.runner.bwd(ctx.saved, d26, dobj_l)
+        ctx.saved = None
+        return (None, None) + tuple(grads.get(n) for n in ctx.names)
+
+
+class Runner:
+    """Binds a parameter dict, a batch and a plan to the engine's forward/backward."""
+
+    def __init__(self, kernels: E.Kernels, P, batch, plan, mode: str, training: bool, arch: str = "sttran"):
+        self.k, self.P, self.batch, self.plan, self.mode, self.training, self.arch = kernels, P, batch, plan, mode, training, arch
+
+    def fwd(self, want_ctx: bool):
+        f = M.sttran_forward if self.arch == "sttran" else M.dsg_forward
+        return f(self.k, self.P, self.batch, self.plan, self.mode, self.training, want_ctx)
+
+    def bwd(self, saved, d26, dobj):
+        f = M.sttran_backward if self.arch == "sttran" else M.dsg_backward
+        return f(self.k, self.P, self.batch, self.plan, self.mode, saved, d26, dobj)
+
+
+def run_module(module: torch.nn.Module, kernels: E.Kernels, entries, mode: str, arch: str):
+    """Shared forward of the drop-in modules: returns (obj_logits|None, att, spa, con, batch)."""
+    dev = next(module.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("nlvsgg_b200 models run on CUDA only (sm_100a kernels); there is no CPU fallback")
+    batch, plan = M.make_batch(entries, dev, mode, dsg=(arch == "dsg"))
+    P = {k: v for k, v in module_tensors(module).items()}
+    runner = Runner(kernels, P, batch, plan, mode, module.training, arch)
+    names = [n for n, p in module.named_parameters()]
+    params = [p for n, p in module.named_parameters()]
+    obj, att, spa, con = _WholeModelFn.apply(runner, names, *params)
+    if module.training:   # BatchNorm bookkeeping the kernels do not touch
+        for n, buf in module.named_buffers():
+            if n.endswith("num_batches_tracked") and "encoder_tran" not in n:
+                if not (mode == "predcls" and n.startswith("object_classifier.")):
+                    buf += len(entries)
+    return (obj if obj.numel() or mode != "predcls" else None), att, spa, con, batch

@@ -1,0 +1,195 @@
+"""Whole-model forward / backward / fused training step on top of engine.py.
+
+A *batch* is a list of per-video ``entry`` dicts (the reference contract, lib/assign_pseudo_label.py:1368-1382):
+the videos are concatenated into one set of device tensors and one Plan; BatchNorm statistics stay per video
+and the batch loss is the mean over videos of the reference's per-video loss (tools/train_STTran.py:169-189).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import engine as E
+from . import ops
+
+F32 = torch.float32
+
+
+class Batch:
+    pass
+
+
+def make_batch(entries: List[dict], device, mode: str, dsg: bool = False):
+    """Concatenate per-video entries; returns (Batch, Plan).  Tensors may live on the host or the device."""
+    dev = torch.device(device)
+    b = Batch()
+    n_boxes = [int(e["boxes"].shape[0]) for e in entries]
+    frame_ids = [e["im_idx"].detach().cpu().numpy() for e in entries]
+    off = np.concatenate(([0], np.cumsum(n_boxes)))[:-1]
+
+    def cat(key, dtype=None):
+        ts = [e[key] for e in entries]
+        t = ts[0] if len(ts) == 1 else torch.cat(ts, 0)
+        t = t.to(dev, non_blocking=True)
+        return t.to(dtype) if dtype is not None and t.dtype != dtype else t
+
+    b.features = cat("features", F32).contiguous()
+    b.boxes = cat("boxes", F32).contiguous()
+    b.labels = cat("labels", torch.int64).contiguous()
+    b.scores = cat("scores", F32)
+    b.distribution = cat("distribution", F32).contiguous() if mode != "predcls" else None
+    b.union_feat = cat("union_feat", F32).contiguous()
+    if len(entries) == 1:
+        b.pair_idx = entries[0]["pair_idx"].to(dev, non_blocking=True).to(torch.int64).contiguous()
+    else:
+        b.pair_idx = torch.cat([e["pair_idx"].to(torch.int64) + int(o) for e, o in zip(entries, off)], 0).to(dev).contiguous()
+    if all("spatial_masks" in e for e in entries):
+        b.spatial_masks = cat("spatial_masks", F32).contiguous()
+    else:  # rasterise on device from the boxes (fused pair gather + draw_union_boxes - 0.5)
+        b.spatial_masks = ops.union_mask_pairs(b.boxes, b.pair_idx, 27, -0.5)
+    b.n_boxes, b.n_pairs = n_boxes, [len(f) for f in frame_ids]
+    obj_class = subj_box = None
+    if dsg:
+        lab = torch.cat([e["labels"] for e in entries]).cpu().numpy()
+        pi = b.pair_idx.cpu().numpy()
+        obj_class, subj_box = lab[pi[:, 1]], pi[:, 0]
+    plan = E.Plan(n_boxes, frame_ids, dev, obj_class=obj_class, subj_box=subj_box, dsg=dsg, dsg_pos_by_rank=(mode == "sgdet"))
+    return b, plan
+
+
+# ================================================================================================
+# STTran
+# ================================================================================================
+def sttran_forward(k: E.Kernels, P: Dict[str, torch.Tensor], batch: Batch, plan: E.Plan, mode: str, training: bool,
+                   want_ctx: bool):
+    """lib/sttran.py:375-411.  Returns (outputs dict, ctx)."""
+    ctx = {}
+    out = {}
+    if mode == "predcls":
+        feat_op = k.opnd(batch.features)
+        ctx["oc"] = None
+    else:
+        logits, objfeat, ctx["oc"] = E.object_classifier_fwd(k, P, plan, batch.features, batch.distribution, batch.boxes,
+                                                            training, want_ctx)
+        out["distribution"] = logits
+        feat_op = objfeat[:, :2048]
+    rel, ctx["pt"] = E.pair_tokens_fwd(k, P, plan, feat_op, batch.union_feat, batch.spatial_masks, batch.pair_idx,
+                                       batch.labels, training, want_ctx)
+    glob, ctx["tr"] = E.sttran_transformer_fwd(k, P, plan, rel, want_ctx)
+    logits26 = E.heads_fwd(k, P, glob)
+    ctx["glob"], ctx["logits26"] = glob, logits26
+    out["logits26"] = logits26
+    return out, (ctx if want_ctx else None)
+
+
+def sttran_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits):
+    grads: Dict[str, torch.Tensor] = {}
+    dglob = E.heads_bwd(k, P, ctx["glob"], dlogits26, grads)
+    drel = E.sttran_transformer_bwd(k, P, plan, ctx["tr"], dglob, grads)
+    E.pair_tokens_bwd(k, P, plan, ctx["pt"], drel, grads)
+    if mode != "predcls" and dobj_logits is not None:
+        E.object_classifier_bwd(k, P, plan, ctx["oc"], dobj_logits, grads)
+    return grads
+
+
+# ================================================================================================
+# DSG-DETR (sgdet): lib/dsg_detr.py:514-572
+# ================================================================================================
+def dsg_forward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, training: bool, want_ctx: bool):
+    ctx = {}
+    out = {}
+    if mode == "predcls":
+        feat_op = k.opnd(batch.features)
+        ctx["oc"] = None
+    else:
+        logits, objfeat, ctx["oc"] = E.object_classifier_fwd(k, P, plan, batch.features, batch.distribution, batch.boxes,
+                                                            training, want_ctx)
+        out["distribution"] = logits
+        feat_op = objfeat[:, :2048]
+    rel, ctx["pt"] = E.pair_tokens_fwd(k, P, plan, feat_op, batch.union_feat, batch.spatial_masks, batch.pair_idx,
+                                       batch.labels, training, want_ctx)
+    x, _, ctx["loc"] = E.encoder_fwd(k, P, "local_transformer.layers.0.", "self_attn", rel, k.opnd(rel), plan.local_work,
+                                     plan.n_local_work, want_ctx, out_op=False)
+    pe = P["positional_encoder.pe"].reshape(-1, E.D_MODEL)
+    # class-sorted stream + sinusoidal encoding of the frame rank (dsg_detr.py:545-559)
+    g, gop = ops.gather_rows(x, plan.cls_perm, plan.R, out_dtype=F32, add=pe, add_idx=plan.cls_pos,
+                             out2_dtype=torch.bfloat16 if k.AD == torch.bfloat16 else None)
+    if gop is None:
+        gop = g
+    ctx["glob"] = []
+    for i in range(3):
+        g, gop, c = E.encoder_fwd(k, P, f"global_transformer.layers.{i}.", "self_attn", g, gop, plan.cls_work,
+                                  plan.n_cls_work, want_ctx, out_op=(i < 2))
+        ctx["glob"].append(c)
+    glob, _ = ops.gather_rows(g, plan.cls_iperm, plan.R, out_dtype=F32)
+    logits26 = E.heads_fwd(k, P, glob)
+    ctx["globout"], ctx["logits26"] = glob, logits26
+    out["logits26"] = logits26
+    return out, (ctx if want_ctx else None)
+
+
+def dsg_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits):
+    grads: Dict[str, torch.Tensor] = {}
+    dglob = E.heads_bwd(k, P, ctx["globout"], dlogits26, grads)
+    dg, _ = ops.gather_rows(dglob, plan.cls_perm, plan.R, out_dtype=F32)
+    for i in reversed(range(3)):
+        dg = E.encoder_bwd(k, P, f"global_transformer.layers.{i}.", "self_attn", ctx["glob"][i], dg, plan.cls_work,
+                           plan.n_cls_work, grads)
+    dx, _ = ops.gather_rows(dg, plan.cls_iperm, plan.R, out_dtype=F32)   # the encoding is a constant buffer
+    drel = E.encoder_bwd(k, P, "local_transformer.layers.0.", "self_attn", ctx["loc"], dx, plan.local_work,
+                         plan.n_local_work, grads)
+    E.pair_tokens_bwd(k, P, plan, ctx["pt"], drel, grads)
+    if mode != "predcls" and dobj_logits is not None:
+        E.object_classifier_bwd(k, P, plan, ctx["oc"], dobj_logits, grads)
+    return grads
+
+
+# ================================================================================================
+# fused loss (tools/train_STTran.py:143-189 with bce_loss=True), batch = mean over videos
+# ================================================================================================
+class Labels:
+    pass
+
+
+def make_labels(entries: List[dict], batch: Batch, device, mode: str) -> Labels:
+    nv = len(entries)
+    L = Labels()
+    att, w_att, spa_bits, w_spa, con_bits, w_con, w_obj = [], [], [], [], [], [], []
+    for e, nb in zip(entries, batch.n_boxes):
+        a_gt, s_gt, c_gt = e["attention_gt"], e["spatial_gt"], e["contacting_gt"]
+        n = len(a_gt)
+        a = np.array([int(x[0]) if len(x) else -1 for x in a_gt], dtype=np.int64).reshape(n)
+        na = int((a >= 0).sum())
+        att.append(a)
+        w_att.append(np.where(a >= 0, 1.0 / (max(na, 1) * nv), 0.0).astype(np.float32))
+        sb = np.array([sum(1 << int(j) for j in set(x)) for x in s_gt], dtype=np.uint32).reshape(n)
+        cb = np.array([sum(1 << int(j) for j in set(x)) for x in c_gt], dtype=np.uint32).reshape(n)
+        ns, nc = int((sb != 0).sum()), int((cb != 0).sum())
+        spa_bits.append(sb); con_bits.append(cb)
+        w_spa.append(np.where(sb != 0, 1.0 / (max(ns, 1) * 6 * nv), 0.0).astype(np.float32))
+        w_con.append(np.where(cb != 0, 1.0 / (max(nc, 1) * 17 * nv), 0.0).astype(np.float32))
+        w_obj.append(np.full(nb, 1.0 / (max(nb, 1) * nv), dtype=np.float32))
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.concatenate(a))).to(device, non_blocking=True)
+    L.att, L.w_att = t(att), t(w_att)
+    L.spa_bits, L.w_spa = t([x.view(np.int32) for x in spa_bits]), t(w_spa)
+    L.con_bits, L.w_con = t([x.view(np.int32) for x in con_bits]), t(w_con)
+    L.w_obj = t(w_obj)
+    return L
+
+
+def fused_loss(out: dict, batch: Batch, labels: Labels, mode: str, want_grad: bool = True):
+    """Returns (loss scalar tensor on device, dlogits26, dobj_logits)."""
+    logits26 = out["logits26"]
+    dev = logits26.device
+    loss = torch.zeros(1, device=dev, dtype=F32)
+    d26 = torch.empty_like(logits26) if want_grad else None
+    dobj = None
+    if mode != "predcls":
+        dobj = torch.empty_like(out["distribution"]) if want_grad else None
+        ops.ce_loss(out["distribution"], 37, batch.labels, labels.w_obj, loss, dobj)
+    ops.ce_loss(logits26[:, 0:3], 3, labels.att, labels.w_att, loss, d26[:, 0:3] if want_grad else None)
+    ops.bce_sigmoid_loss(logits26[:, 3:9], 6, labels.spa_bits, labels.w_spa, loss, d26[:, 3:9] if want_grad else None)
+    ops.bce_sigmoid_loss(logits26[:, 9:26], 17, labels.con_bits, labels.w_con, loss, d26[:, 9:26] if want_grad else None)
+    return loss, d26, dobj

@@ -97,3 +97,239 @@ def bbox_overlaps(boxes: torch.Tensor, query: torch.Tensor) -> torch.Tensor:
     _C.check(_C.lib().nlv_bbox_overlaps_f64(_ptr(b), b.shape[0], _ptr(q), q.shape[0], _ptr(out), _stream()),
              "bbox_overlaps")
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# thin wrappers for the remaining entry points (one C call each)
+# ----------------------------------------------------------------------------------------------
+_F = ctypes.c_float
+_LL = ctypes.c_longlong
+
+
+def _call(name, *args):
+    _C.check(getattr(_C.lib(), name)(*args, _stream()), name)
+
+
+def convert(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None) -> torch.Tensor:
+    assert src.dim() == 2 and src.stride(1) == 1
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=dtype)
+    _call("nlv_convert", _ptr(src), _dt(src), src.stride(0), _ptr(out), _dt(out), out.stride(0), _LL(src.shape[0]),
+          src.shape[1])
+    return out
+
+
+def split3(src: torch.Tensor, block_dim: int, pattern: int) -> torch.Tensor:
+    """fp32 [r,c] -> bf16 [r,3c] (block_dim=1) or [3r,c] (block_dim=0); row stride padded to a multiple of 8."""
+    assert src.dtype == torch.float32 and src.dim() == 2 and src.stride(1) == 1
+    r, c = src.shape
+    if block_dim == 1:
+        ld = (3 * c + 7) // 8 * 8
+        out = torch.empty(r, ld, device=src.device, dtype=torch.bfloat16)[:, :3 * c]
+    else:
+        ld = (c + 7) // 8 * 8
+        out = torch.empty(3 * r, ld, device=src.device, dtype=torch.bfloat16)[:, :c]
+    _call("nlv_split3", _ptr(src), src.stride(0), _LL(r), c, _ptr(out), out.stride(0), block_dim, pattern)
+    return out
+
+
+def nchw_to_rows(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    r, c, h, w = x.shape
+    x = x.contiguous()
+    out = torch.empty(r * h * w, c, device=x.device, dtype=dtype)
+    step = 32768
+    for s in range(0, r, step):  # grid.y limit
+        n = min(step, r - s)
+        _call("nlv_nchw_to_rows", _ptr(x[s:s + n]), n, c, h * w, _ptr(out[s * h * w:(s + n) * h * w]), _dt(out))
+    return out
+
+
+def im2col_mask(masks: torch.Tensor, dtype: torch.dtype, ld: int = 104) -> torch.Tensor:
+    r = masks.shape[0]
+    out = torch.empty(r * 196, ld, device=masks.device, dtype=dtype)
+    _call("nlv_im2col_mask", _ptr(masks.contiguous()), r, _ptr(out), _dt(out), ld)
+    return out
+
+
+def im2col_3x3(x: torch.Tensor, r: int, h: int, w: int, c: int, dtype: torch.dtype) -> torch.Tensor:
+    out = torch.empty(r * h * w, c * 9, device=x.device, dtype=dtype)
+    _call("nlv_im2col_3x3", _ptr(x), _dt(x), r, h, w, c, _ptr(out), _dt(out))
+    return out
+
+
+def col2im_3x3(dcol: torch.Tensor, r: int, h: int, w: int, c: int) -> torch.Tensor:
+    out = torch.empty(r * h * w, c, device=dcol.device, dtype=torch.float32)
+    _call("nlv_col2im_3x3", _ptr(dcol), _dt(dcol), r, h, w, c, _ptr(out))
+    return out
+
+
+def maxpool_fwd(x: torch.Tensor, r: int, c: int, dtype: torch.dtype):
+    y = torch.empty(r * 49, c, device=x.device, dtype=dtype)
+    arg = torch.empty(r * 49, c, device=x.device, dtype=torch.uint8)
+    _call("nlv_maxpool_fwd", _ptr(x), _dt(x), r, c, _ptr(y), _dt(y), _ptr(arg))
+    return y, arg
+
+
+def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, r: int, c: int) -> torch.Tensor:
+    dx = torch.empty(r * 196, c, device=dy.device, dtype=torch.float32)
+    _call("nlv_maxpool_bwd", _ptr(dy), _ptr(arg), r, c, _ptr(dx))
+    return dx
+
+
+def gather_rows(src, idx, n_out, out_dtype=None, add=None, add_idx=None, out2_dtype=None, want_out=True):
+    cols = src.shape[1]
+    out = torch.empty(n_out, cols, device=src.device, dtype=out_dtype or src.dtype) if want_out else None
+    out2 = torch.empty(n_out, cols, device=src.device, dtype=out2_dtype) if out2_dtype is not None else None
+    _call("nlv_gather_rows", _ptr(src), _dt(src), src.stride(0), _ptr(idx), _ptr(add), _ptr(add_idx),
+          add.stride(0) if add is not None else 0, _LL(n_out), cols,
+          _ptr(out), _dt(out) if out is not None else 0, cols, _ptr(out2), _dt(out2) if out2 is not None else 0, cols)
+    return out, out2
+
+
+def gather_sum_rows(src, idx, fan, n_out, out=None, accumulate=False):
+    cols = src.shape[1]
+    if out is None:
+        out = torch.empty(n_out, cols, device=src.device, dtype=torch.float32)
+    _call("nlv_gather_sum_rows", _ptr(src), src.stride(0), _ptr(idx), fan, _LL(n_out), cols, _ptr(out), out.stride(0),
+          1 if accumulate else 0)
+    return out
+
+
+def assemble_tokens(fo, pair_idx, labels, e1, e2, rel):
+    _call("nlv_assemble_tokens", _ptr(fo), _ptr(pair_idx), _ptr(labels), _ptr(e1), _ptr(e2), _LL(pair_idx.shape[0]), _ptr(rel))
+
+
+def assemble_tokens_bwd(drel, pair_idx, labels, dfo, de1, de2):
+    _call("nlv_assemble_tokens_bwd", _ptr(drel), _ptr(pair_idx), _ptr(labels), _LL(pair_idx.shape[0]), _ptr(dfo),
+          _ptr(de1), _ptr(de2))
+
+
+def center_size(boxes: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(boxes.shape[0], 4, device=boxes.device, dtype=torch.float32)
+    _call("nlv_center_size", _ptr(boxes), _LL(boxes.shape[0]), _ptr(out))
+    return out
+
+
+def colsum(x: torch.Tensor, row_class=None, n_class: int = 1, out=None) -> torch.Tensor:
+    rows, cols = x.shape
+    if out is None:
+        out = torch.zeros(n_class, cols, device=x.device, dtype=torch.float32)
+    _call("nlv_colsum", _ptr(x), _dt(x), x.stride(0), _LL(rows), cols, _ptr(row_class), n_class, _ptr(out))
+    return out
+
+
+def relu_mask(x: torch.Tensor, gate: torch.Tensor, out_dtype: torch.dtype) -> torch.Tensor:
+    rows, cols = x.shape
+    y = torch.empty(rows, cols, device=x.device, dtype=out_dtype)
+    _call("nlv_relu_mask", _ptr(x), _dt(x), x.stride(0), _ptr(gate), _dt(gate), gate.stride(0), _LL(rows), cols,
+          _ptr(y), _dt(y), cols)
+    return y
+
+
+def add(a: torch.Tensor, b: torch.Tensor, out=None) -> torch.Tensor:
+    if out is None:
+        out = torch.empty_like(a)
+    _call("nlv_add", _ptr(a), _ptr(b), _LL(a.numel()), _ptr(out))
+    return out
+
+
+def layernorm_fwd(x, w, b, eps=1e-5, y2_dtype=None, want_y=True):
+    rows, cols = x.shape
+    y = torch.empty_like(x) if want_y else None
+    y2 = torch.empty(rows, cols, device=x.device, dtype=y2_dtype) if y2_dtype is not None else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    _call("nlv_layernorm_fwd", _ptr(x), _LL(rows), cols, _ptr(w), _ptr(b), _F(eps), _ptr(y), _ptr(y2),
+          _dt(y2) if y2 is not None else 0, _ptr(mean), _ptr(rstd))
+    return y, y2, mean, rstd
+
+
+def layernorm_bwd(dy, x, mean, rstd, w, dx2_dtype=None):
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    dx2 = torch.empty(rows, cols, device=x.device, dtype=dx2_dtype) if dx2_dtype is not None else None
+    dw = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    db = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    _call("nlv_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _LL(rows), cols, _ptr(dx), _ptr(dx2),
+          _dt(dx2) if dx2 is not None else 0, _ptr(dw), _ptr(db))
+    return dx, dx2, dw, db
+
+
+def bn_stats(x, seg, nseg, c, momentum, running_mean, running_var):
+    rows = x.shape[0]
+    ws = torch.empty(nseg * 2 * c, device=x.device, dtype=torch.float64)
+    mean = torch.empty(nseg, c, device=x.device, dtype=torch.float32)
+    var = torch.empty(nseg, c, device=x.device, dtype=torch.float32)
+    _call("nlv_bn_stats", _ptr(x), _dt(x), x.stride(0), _ptr(seg), nseg, _LL(rows), c, _F(momentum), _ptr(ws), _ptr(mean),
+          _ptr(var), _ptr(running_mean), _ptr(running_var))
+    return mean, var
+
+
+def bn_apply(x, row_seg, mean, var, w, b, relu, out=None, out_dtype=None, out2_dtype=None, eps=1e-5):
+    rows, c = x.shape
+    if out is None:
+        out = torch.empty(rows, c, device=x.device, dtype=out_dtype or torch.float32)
+    out2 = torch.empty(rows, c, device=x.device, dtype=out2_dtype) if out2_dtype is not None else None
+    _call("nlv_bn_apply", _ptr(x), _dt(x), x.stride(0), _ptr(row_seg), _ptr(mean), _ptr(var), _ptr(w), _ptr(b), _F(eps),
+          1 if relu else 0, _LL(rows), c, _ptr(out), _dt(out), out.stride(0), _ptr(out2),
+          _dt(out2) if out2 is not None else 0, c)
+    return out, out2
+
+
+def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dtype=torch.float32, eps=1e-5):
+    rows, c = x.shape
+    ws = torch.empty(nseg * 2 * c, device=x.device, dtype=torch.float64)
+    dx = torch.empty(rows, c, device=x.device, dtype=dx_dtype)
+    dw = torch.zeros(c, device=x.device, dtype=torch.float32)
+    db = torch.zeros(c, device=x.device, dtype=torch.float32)
+    _call("nlv_bn_bwd", _ptr(dy), dy.stride(0), _ptr(x), _dt(x), x.stride(0), _ptr(yout),
+          _dt(yout) if yout is not None else 0, yout.stride(0) if yout is not None else 0, _ptr(seg), _ptr(row_seg), nseg,
+          _ptr(mean), _ptr(var), _ptr(w), _F(eps), 1 if use_batch_stats else 0, _LL(rows), c, _ptr(ws), _ptr(dx), _dt(dx), c,
+          _ptr(dw), _ptr(db))
+    return dx, dw, db
+
+
+def attn_fwd(q, k, v, hd, heads, work, n_work, out_dtype, want_lse=True):
+    rows = q.shape[0]
+    o = torch.empty(rows, hd * heads, device=q.device, dtype=out_dtype)
+    lse = torch.empty(rows * heads, device=q.device, dtype=torch.float32) if want_lse else None
+    _call("nlv_attn_fwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
+          _F(1.0 / (hd ** 0.5)), _ptr(work), n_work, _ptr(o), o.stride(0), _dt(o), _ptr(lse))
+    return o, lse
+
+
+def attn_bwd(q, k, v, o, dout, lse, hd, heads, work, n_work, dq, dk, dv):
+    rows = q.shape[0]
+    delta = torch.empty(rows * heads, device=q.device, dtype=torch.float32)
+    assert dq.dtype == dk.dtype == dv.dtype
+    _call("nlv_attn_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
+          _F(1.0 / (hd ** 0.5)), _ptr(work), n_work, _ptr(o), o.stride(0), _dt(o), _ptr(dout), dout.stride(0), _dt(dout),
+          _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _dt(dq))
+
+
+def heads_activation(logits):
+    r = logits.shape[0]
+    att = torch.empty(r, 3, device=logits.device, dtype=torch.float32)
+    spa = torch.empty(r, 6, device=logits.device, dtype=torch.float32)
+    con = torch.empty(r, 17, device=logits.device, dtype=torch.float32)
+    _call("nlv_heads_activation", _ptr(logits), _LL(r), _ptr(att), _ptr(spa), _ptr(con))
+    return att, spa, con
+
+
+def ce_loss(logits, c, labels, row_weight, loss, dlogits):
+    _call("nlv_ce_loss", _ptr(logits), logits.stride(0), c, _ptr(labels), _ptr(row_weight), _LL(logits.shape[0]), _ptr(loss),
+          _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0)
+
+
+def bce_sigmoid_loss(logits, c, bits, row_weight, loss, dlogits):
+    _call("nlv_bce_sigmoid_loss", _ptr(logits), logits.stride(0), c, _ptr(bits), _ptr(row_weight), _LL(logits.shape[0]),
+          _ptr(loss), _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0)
+
+
+def sumsq(x, out):
+    _call("nlv_sumsq", _ptr(x), _LL(x.numel()), _ptr(out))
+
+
+def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, total_sq=None, max_norm=0.0, p_bf16=None):
+    _call("nlv_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _LL(p.numel()), _F(lr), _F(beta1), _F(beta2), _F(eps), _F(wd),
+          int(step), _ptr(total_sq), _F(max_norm), _ptr(p_bf16))

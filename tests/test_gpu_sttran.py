@@ -1,0 +1,146 @@
+"""STTran forward / backward through the drop-in module on CUDA vs (a) golden vectors produced by the reference
+itself and (b) the CPU oracle, on identical seeded inputs and weights.
+
+Tolerances (relative to the max |reference| of each tensor):
+  fp32 / bf16x3 modes : 1e-3  (north-star bound for fp32-accumulated logits)
+  bf16 mode           : 6e-2  (bf16 operand rounding through 7 transformer layers; reported, not a parity claim)
+"""
+import copy
+
+import pytest
+import torch
+
+from nlvsgg_b200 import synth
+from tests import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": 1e-3, "bf16x3": 1e-3, "bf16": 6e-2}
+OUT_KEYS = ("attention_distribution", "spatial_distribution", "contacting_distribution", "distribution")
+
+
+def _build(case, precision, training):
+    from nlvsgg_b200.lib.sttran import STTran
+    m = STTran(case["mode"], 3, 6, 17, synth.AG_OBJECT_CLASSES, 1, 3, "wk", True, 2048, precision=precision)
+    sd = synth.make_state_dict(G.sttran_template(), case["seed"])
+    m.load_state_dict(sd)          # same names/shapes as the reference: drop-in checkpoint compatibility
+    m = m.cuda()
+    m.train(training)
+    return m
+
+
+def _entry_cuda(entry):
+    return {k: (v.cuda() if torch.is_tensor(v) else copy.deepcopy(v)) for k, v in entry.items()}
+
+
+def _reference_style_loss(pred):
+    """tools/train_STTran.py:143-189 (bce_loss=True) with torch ops, as the unchanged training script would run it."""
+    import torch.nn as nn
+    ce, bce = nn.CrossEntropyLoss(), nn.BCELoss()
+    dev = pred["attention_distribution"].device
+    att_mask = torch.tensor([len(i) > 0 for i in pred["attention_gt"]], device=dev)
+    att_label = torch.tensor([int(i[0]) for i in pred["attention_gt"] if len(i) >= 1], dtype=torch.int64, device=dev)
+    R = len(pred["spatial_gt"])
+    spa = torch.zeros(R, 6, device=dev)
+    con = torch.zeros(R, 17, device=dev)
+    for i in range(R):
+        spa[i, pred["spatial_gt"][i]] = 1.0
+        con[i, pred["contacting_gt"][i]] = 1.0
+    loss = ce(pred["distribution"], pred["labels"]) + ce(pred["attention_distribution"][att_mask], att_label)
+    sm, cm = (spa > 0).sum(-1) != 0, (con > 0).sum(-1) != 0
+    loss = loss + bce(pred["spatial_distribution"][sm], spa[sm]) + bce(pred["contacting_distribution"][cm], con[cm])
+    return loss
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", [n for n in G.model_cases("sttran_") if "train" not in n])
+def test_sttran_eval_matches_reference(cuda_lib, name, precision):
+    from oracle import cref
+    case = G.load_case(name)
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    m = _build(case, precision, False)
+    with torch.no_grad():
+        pred = m(_entry_cuda(entry))
+    for k, want in case["outputs"].items():
+        err = G.rel_err(pred[k].cpu(), want)
+        assert err < TOL[precision], f"{k}: rel err {err:.3e}"
+    assert pred["pred_labels"].cpu().equal(entry["labels"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+@pytest.mark.parametrize("name", [n for n in G.model_cases("sttran_") if "train" in n])
+def test_sttran_train_step_matches_reference(cuda_lib, name, precision):
+    from oracle import cref
+    case = G.load_case(name)
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    m = _build(case, precision, True)
+    pred = m(_entry_cuda(entry))
+    loss = _reference_style_loss(pred)
+    loss.backward()
+    tol = TOL[precision]
+    assert abs(loss.item() - case["loss"]) <= tol * abs(case["loss"]), f"loss {loss.item()} vs {case['loss']}"
+    for k, want in case["outputs"].items():
+        assert G.rel_err(pred[k].detach().cpu(), want) < tol, k
+    sd = m.state_dict()
+    for k, want in case["running"].items():
+        assert G.rel_err(sd[k].cpu(), want) < tol, k
+    gtol = 5 * tol
+    bad = []
+    for n, p in m.named_parameters():
+        assert p.grad is not None, f"{n} received no gradient"
+        dg = case["grads"][n]
+        g = p.grad.detach().double().flatten().cpu()
+        scale = (dg["sq_sum"] / max(g.numel(), 1)) ** 0.5 + 1e-12       # rms of the reference gradient
+        if "full" in dg:
+            err = (g - dg["full"].double()).abs().max().item() / (dg["full"].double().abs().max().item() + 1e-12)
+        else:
+            err = (g[:64] - dg["head"].double()).abs().max().item() / (10 * scale)
+            err = max(err, abs(g.abs().sum().item() - dg["abs_sum"]) / (dg["abs_sum"] + 1e-12))
+        if err > gtol:
+            bad.append((n, err))
+    assert not bad, f"gradient mismatches (rel): {bad[:12]}"
+
+
+def test_sttran_matches_oracle_intermediates(cuda_lib):
+    """fp32 mode vs the CPU oracle on a fresh seed with empty frames: pair tokens, transformer output, logits."""
+    from oracle import cref, model as omodel
+    from nlvsgg_b200 import engine as E, model as M
+    seed = 21
+    entry, _ = synth.synth_video(seed, 10, 5, "sgdet", draw_fn=cref.draw_union_boxes, empty_frame_prob=0.25)
+    sd = synth.make_state_dict(G.sttran_template(), seed)
+    with torch.no_grad():
+        want = omodel.sttran_forward(sd, entry, "sgdet", training=False, return_tokens=True)
+    P = {k: v.cuda() for k, v in sd.items()}
+    k = E.Kernels("fp32")
+    batch, plan = M.make_batch([_entry_cuda(entry)], "cuda", "sgdet")
+    logits, objfeat, _ = E.object_classifier_fwd(k, P, plan, batch.features, batch.distribution, batch.boxes, False, False)
+    assert G.rel_err(logits.cpu(), want["distribution"]) < 1e-4
+    rel, _ = E.pair_tokens_fwd(k, P, plan, objfeat[:, :2048], batch.union_feat, batch.spatial_masks, batch.pair_idx,
+                               batch.labels, False, False)
+    assert G.rel_err(rel.cpu(), want["rel_features"]) < 1e-4
+    glob, _ = E.sttran_transformer_fwd(k, P, plan, rel, False)
+    assert G.rel_err(glob.cpu(), want["global_output"]) < 1e-4
+
+
+def test_batched_videos_equal_single_videos(cuda_lib):
+    """A 3-video batch (per-video BatchNorm statistics, per-video windows) reproduces the 3 single-video results."""
+    from oracle import cref
+    from nlvsgg_b200 import engine as E, model as M
+    sd = synth.make_state_dict(G.sttran_template(), 3)
+    P = {k: v.cuda() for k, v in sd.items()}
+    k = E.Kernels("fp32")
+    entries = [_entry_cuda(synth.synth_video(s, f, 5, "sgdet", draw_fn=cref.draw_union_boxes, empty_frame_prob=p)[0])
+               for s, f, p in ((31, 6, 0.0), (32, 1, 0.0), (33, 7, 0.3))]
+    singles = []
+    for e in entries:
+        Pi = {n: t.clone() for n, t in P.items()}
+        b, pl = M.make_batch([e], "cuda", "sgdet")
+        out, _ = M.sttran_forward(k, Pi, b, pl, "sgdet", True, False)
+        singles.append(out)
+    Pb = {n: t.clone() for n, t in P.items()}
+    b, pl = M.make_batch(entries, "cuda", "sgdet")
+    out, _ = M.sttran_forward(k, Pb, b, pl, "sgdet", True, False)
+    want26 = torch.cat([s["logits26"] for s in singles])
+    wantobj = torch.cat([s["distribution"] for s in singles])
+    assert G.rel_err(out["logits26"].cpu(), want26.cpu()) < 1e-5
+    assert G.rel_err(out["distribution"].cpu(), wantobj.cpu()) < 1e-5
