@@ -23,7 +23,7 @@ class _WholeModelFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, runner, names: List[str], *params):
         P = runner.P
-        want_ctx = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        want_ctx = runner.want_ctx   # decided by the caller: grad mode is always off inside Function.forward
         out, saved = runner.fwd(want_ctx)
         att, spa, con = ops.heads_activation(out["logits26"])
         obj = out.get("distribution")
@@ -56,6 +56,7 @@ class Runner:
 
     def __init__(self, kernels: E.Kernels, P, batch, plan, mode: str, training: bool, arch: str = "sttran"):
         self.k, self.P, self.batch, self.plan, self.mode, self.training, self.arch = kernels, P, batch, plan, mode, training, arch
+        self.want_ctx = False
 
     def fwd(self, want_ctx: bool):
         f = M.sttran_forward if self.arch == "sttran" else M.dsg_forward
@@ -76,6 +77,7 @@ def run_module(module: torch.nn.Module, kernels: E.Kernels, entries, mode: str, 
     runner = Runner(kernels, P, batch, plan, mode, module.training, arch)
     names = [n for n, p in module.named_parameters()]
     params = [p for n, p in module.named_parameters()]
+    runner.want_ctx = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     obj, att, spa, con = _WholeModelFn.apply(runner, names, *params)
     if module.training:   # BatchNorm bookkeeping the kernels do not touch
         for n, buf in module.named_buffers():

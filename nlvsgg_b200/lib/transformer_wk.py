@@ -41,8 +41,7 @@ class _Stack(nn.Module):
 
 class _TransformerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kernels, plan, P, names, features, *params):
-        want = torch.is_grad_enabled()
+    def forward(ctx, kernels, plan, P, names, want, features, *params):
         Pg = {"glocal_transformer." + n: t for n, t in P.items()}
         out, saved = E.sttran_transformer_fwd(kernels, Pg, plan, features.contiguous().float(), want)
         ctx.k, ctx.plan, ctx.Pg, ctx.saved, ctx.names = kernels, plan, Pg, saved, names
@@ -53,7 +52,7 @@ class _TransformerFn(torch.autograd.Function):
         grads = {}
         dx = E.sttran_transformer_bwd(ctx.k, ctx.Pg, ctx.plan, ctx.saved, dout.contiguous(), grads)
         ctx.saved = None
-        return (None, None, None, None, dx) + tuple(grads.get("glocal_transformer." + n) for n in ctx.names)
+        return (None, None, None, None, None, dx) + tuple(grads.get("glocal_transformer." + n) for n in ctx.names)
 
 
 class transformer_wk(nn.Module):
@@ -83,7 +82,8 @@ class transformer_wk(nn.Module):
         plan = E.Plan([0], [fid], features.device)
         P = dict(self.named_parameters())
         names = list(P.keys())
-        out = _TransformerFn.apply(self._kernels, plan, P, names, features, *P.values())
+        want = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in P.values()))
+        out = _TransformerFn.apply(self._kernels, plan, P, names, want, features, *P.values())
         return out, None, None
 
 

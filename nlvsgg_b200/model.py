@@ -21,42 +21,71 @@ class Batch:
     pass
 
 
-def make_batch(entries: List[dict], device, mode: str, dsg: bool = False):
-    """Concatenate per-video entries; returns (Batch, Plan).  Tensors may live on the host or the device."""
-    dev = torch.device(device)
-    b = Batch()
-    n_boxes = [int(e["boxes"].shape[0]) for e in entries]
-    frame_ids = [e["im_idx"].detach().cpu().numpy() for e in entries]
-    off = np.concatenate(([0], np.cumsum(n_boxes)))[:-1]
+TENSOR_KEYS = ("features", "boxes", "labels", "scores", "distribution", "union_feat", "pair_idx", "spatial_masks")
 
-    def cat(key, dtype=None):
+
+def collate(entries: List[dict], mode: str, pin: bool = False) -> Batch:
+    """Concatenate per-video entries (wherever their tensors live) into one Batch of the same residency.
+    Host-side metadata (frame ids, per-video counts, label lists) is extracted once here."""
+    b = Batch()
+    b.n_boxes = [int(e["boxes"].shape[0]) for e in entries]
+    b.frame_ids = [e["im_idx"].detach().cpu().numpy() for e in entries]
+    b.n_pairs = [len(f) for f in b.frame_ids]
+    b.gt_lists = [(e.get("attention_gt"), e.get("spatial_gt"), e.get("contacting_gt")) for e in entries]
+    off = np.concatenate(([0], np.cumsum(b.n_boxes)))[:-1]
+
+    def cat(key, dtype):
         ts = [e[key] for e in entries]
         t = ts[0] if len(ts) == 1 else torch.cat(ts, 0)
-        t = t.to(dev, non_blocking=True)
-        return t.to(dtype) if dtype is not None and t.dtype != dtype else t
+        t = t.to(dtype).contiguous() if t.dtype != dtype else t.contiguous()
+        return t.pin_memory() if (pin and not t.is_cuda) else t
 
-    b.features = cat("features", F32).contiguous()
-    b.boxes = cat("boxes", F32).contiguous()
-    b.labels = cat("labels", torch.int64).contiguous()
-    b.scores = cat("scores", F32)
-    b.distribution = cat("distribution", F32).contiguous() if mode != "predcls" else None
-    b.union_feat = cat("union_feat", F32).contiguous()
-    if len(entries) == 1:
-        b.pair_idx = entries[0]["pair_idx"].to(dev, non_blocking=True).to(torch.int64).contiguous()
-    else:
-        b.pair_idx = torch.cat([e["pair_idx"].to(torch.int64) + int(o) for e, o in zip(entries, off)], 0).to(dev).contiguous()
-    if all("spatial_masks" in e for e in entries):
-        b.spatial_masks = cat("spatial_masks", F32).contiguous()
-    else:  # rasterise on device from the boxes (fused pair gather + draw_union_boxes - 0.5)
+    b.features, b.boxes = cat("features", F32), cat("boxes", F32)
+    b.labels, b.scores = cat("labels", torch.int64), cat("scores", F32)
+    b.distribution = cat("distribution", F32) if mode != "predcls" else None
+    b.union_feat = cat("union_feat", F32)
+    pi = [e["pair_idx"].to(torch.int64) + int(o) for e, o in zip(entries, off)]
+    b.pair_idx = (pi[0] if len(pi) == 1 else torch.cat(pi, 0)).contiguous()
+    if pin and not b.pair_idx.is_cuda:
+        b.pair_idx = b.pair_idx.pin_memory()
+    b.spatial_masks = cat("spatial_masks", F32) if all("spatial_masks" in e for e in entries) else None
+    return b
+
+
+def upload(hb: Batch, device) -> Batch:
+    """Device copy of a collated batch (async copies on the current stream); rasterises the spatial masks on
+    device when the producer did not supply them (fused pair gather + draw_union_boxes - 0.5)."""
+    dev = torch.device(device)
+    b = Batch()
+    b.__dict__.update(hb.__dict__)
+    for key in TENSOR_KEYS:
+        t = getattr(hb, key)
+        if t is not None:
+            setattr(b, key, t.to(dev, non_blocking=True))
+    if b.spatial_masks is None:
         b.spatial_masks = ops.union_mask_pairs(b.boxes, b.pair_idx, 27, -0.5)
-    b.n_boxes, b.n_pairs = n_boxes, [len(f) for f in frame_ids]
+    return b
+
+
+def input_bytes(hb: Batch) -> int:
+    return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in TENSOR_KEYS if getattr(hb, k) is not None))
+
+
+def make_plan(b: Batch, device, mode: str, dsg: bool = False) -> "E.Plan":
     obj_class = subj_box = None
     if dsg:
-        lab = torch.cat([e["labels"] for e in entries]).cpu().numpy()
+        lab = b.labels.cpu().numpy()
         pi = b.pair_idx.cpu().numpy()
         obj_class, subj_box = lab[pi[:, 1]], pi[:, 0]
-    plan = E.Plan(n_boxes, frame_ids, dev, obj_class=obj_class, subj_box=subj_box, dsg=dsg, dsg_pos_by_rank=(mode == "sgdet"))
-    return b, plan
+    return E.Plan(b.n_boxes, b.frame_ids, torch.device(device), obj_class=obj_class, subj_box=subj_box, dsg=dsg,
+                  dsg_pos_by_rank=(mode == "sgdet"))
+
+
+def make_batch(entries: List[dict], device, mode: str, dsg: bool = False):
+    """collate + upload + plan; returns (Batch on device, Plan)."""
+    hb = collate(entries, mode)
+    plan = make_plan(hb, device, mode, dsg)
+    return upload(hb, device), plan
 
 
 # ================================================================================================
@@ -84,8 +113,9 @@ def sttran_forward(k: E.Kernels, P: Dict[str, torch.Tensor], batch: Batch, plan:
     return out, (ctx if want_ctx else None)
 
 
-def sttran_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits):
-    grads: Dict[str, torch.Tensor] = {}
+def sttran_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits, grads=None):
+    """`grads`: any mapping that accepts grads[name] = tensor (a dict, or the trainer's flat-buffer sink)."""
+    grads = {} if grads is None else grads
     dglob = E.heads_bwd(k, P, ctx["glob"], dlogits26, grads)
     drel = E.sttran_transformer_bwd(k, P, plan, ctx["tr"], dglob, grads)
     E.pair_tokens_bwd(k, P, plan, ctx["pt"], drel, grads)
@@ -130,8 +160,8 @@ def dsg_forward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, training
     return out, (ctx if want_ctx else None)
 
 
-def dsg_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits):
-    grads: Dict[str, torch.Tensor] = {}
+def dsg_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits, grads=None):
+    grads = {} if grads is None else grads
     dglob = E.heads_bwd(k, P, ctx["globout"], dlogits26, grads)
     dg, _ = ops.gather_rows(dglob, plan.cls_perm, plan.R, out_dtype=F32)
     for i in reversed(range(3)):
@@ -153,12 +183,12 @@ class Labels:
     pass
 
 
-def make_labels(entries: List[dict], batch: Batch, device, mode: str) -> Labels:
-    nv = len(entries)
+def make_labels(batch: Batch, device, mode: str) -> Labels:
+    """Label tensors + per-row loss weights from the python label lists of the entries (train_STTran.py:143-167)."""
+    nv = len(batch.n_boxes)
     L = Labels()
     att, w_att, spa_bits, w_spa, con_bits, w_con, w_obj = [], [], [], [], [], [], []
-    for e, nb in zip(entries, batch.n_boxes):
-        a_gt, s_gt, c_gt = e["attention_gt"], e["spatial_gt"], e["contacting_gt"]
+    for (a_gt, s_gt, c_gt), nb in zip(batch.gt_lists, batch.n_boxes):
         n = len(a_gt)
         a = np.array([int(x[0]) if len(x) else -1 for x in a_gt], dtype=np.int64).reshape(n)
         na = int((a >= 0).sum())

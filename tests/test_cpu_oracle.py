@@ -78,27 +78,8 @@ def test_oracle_dsg_matches_reference_golden():
     case = G.load_case("dsg_sgdet_eval")
     entry, _ = G.case_inputs(case, cref.draw_union_boxes)
     # template = sttran's shared part + dsg-specific transformer names, taken from the fixture-free builder below
-    sd = synth.make_state_dict(dsg_template(), case["seed"])
+    sd = synth.make_state_dict(G.dsg_template(), case["seed"])
     with torch.no_grad():
         pred = omodel.dsg_forward(sd, entry, case["mode"], training=False)
     for k, want in case["outputs"].items():
         assert G.rel_err(pred[k], want) < 2e-5, k
-
-
-def dsg_template():
-    """Names/shapes of lib/dsg_detr.py:STTran (incl. the unused-in-sgdet object-track encoder)."""
-    t = {k: v for k, v in G.sttran_template().items() if not k.startswith("glocal_transformer")}
-    def enc(p, d, ff):
-        t[p + ".self_attn.in_proj_weight"] = torch.empty(3 * d, d); t[p + ".self_attn.in_proj_bias"] = torch.empty(3 * d)
-        t[p + ".self_attn.out_proj.weight"] = torch.empty(d, d); t[p + ".self_attn.out_proj.bias"] = torch.empty(d)
-        t[p + ".linear1.weight"] = torch.empty(ff, d); t[p + ".linear1.bias"] = torch.empty(ff)
-        t[p + ".linear2.weight"] = torch.empty(d, ff); t[p + ".linear2.bias"] = torch.empty(d)
-        for n in ("norm1", "norm2"):
-            t[f"{p}.{n}.weight"] = torch.empty(d); t[f"{p}.{n}.bias"] = torch.empty(d)
-    for i in range(3):
-        enc(f"object_classifier.encoder_tran.layers.{i}", 2376, 1024)
-        enc(f"global_transformer.layers.{i}", 1936, 2048)
-    enc("local_transformer.layers.0", 1936, 2048)
-    t["object_classifier.positional_encoder.pe"] = torch.empty(1, 600, 2376)
-    t["positional_encoder.pe"] = omodel.sinusoidal_pe(400, 1936).unsqueeze(0)
-    return t

@@ -84,21 +84,26 @@ def test_sttran_train_step_matches_reference(cuda_lib, name, precision):
     sd = m.state_dict()
     for k, want in case["running"].items():
         assert G.rel_err(sd[k].cpu(), want) < tol, k
-    gtol = 5 * tol
+    # gradient check: relative L2 error per tensor (digest: first 64 entries + |g| sum for the large ones).
+    # bf16x3 is looser than its forward error because ReLU masks of near-zero activations flip on these tiny
+    # (27-pair) batches; structurally-zero gradients (bias in front of a BatchNorm) are checked absolutely.
+    gtol = {"fp32": 2e-3, "bf16x3": 3e-2, "bf16": 0.35}[precision]
     bad = []
     for n, p in m.named_parameters():
         assert p.grad is not None, f"{n} received no gradient"
         dg = case["grads"][n]
         g = p.grad.detach().double().flatten().cpu()
-        scale = (dg["sq_sum"] / max(g.numel(), 1)) ** 0.5 + 1e-12       # rms of the reference gradient
-        if "full" in dg:
-            err = (g - dg["full"].double()).abs().max().item() / (dg["full"].double().abs().max().item() + 1e-12)
+        ref = dg["full"].double() if "full" in dg else dg["head"].double()
+        got = g if "full" in dg else g[:64]
+        if ref.abs().max().item() < 1e-6:
+            err = 0.0 if got.abs().max().item() < 1e-4 else float("inf")
         else:
-            err = (g[:64] - dg["head"].double()).abs().max().item() / (10 * scale)
-            err = max(err, abs(g.abs().sum().item() - dg["abs_sum"]) / (dg["abs_sum"] + 1e-12))
+            err = (got - ref).norm().item() / (ref.norm().item() + 1e-30)
+            if "full" not in dg:
+                err = max(err, abs(g.abs().sum().item() - dg["abs_sum"]) / (dg["abs_sum"] + 1e-30))
         if err > gtol:
             bad.append((n, err))
-    assert not bad, f"gradient mismatches (rel): {bad[:12]}"
+    assert not bad, f"gradient mismatches (rel L2): {bad[:12]}"
 
 
 def test_sttran_matches_oracle_intermediates(cuda_lib):
