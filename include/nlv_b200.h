@@ -165,6 +165,21 @@ int nlv_sumsq(const float* x, long long n, float* out, void* stream);
 int nlv_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, const float* total_sq, float max_norm, void* p_bf16, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Recall@K triplet matching (lib/evaluation_recall.py:397-467, :209-353, :630-773; bbox.pyx:21-61)
+ * One launch over n_frames frames (any number of videos).  Per frame f:
+ *   pairs  [pair_off[f], pair_off[f+1])   : pair_sub/pair_obj index the pred_* arrays; att (softmaxed) / spa / con scores
+ *   gt rels [gtrel_off[f], gtrel_off[f+1]): (sub, obj, predicate) with sub/obj local to the frame's gt boxes
+ *   gt boxes [gtbox_off[f], gtbox_off[f+1]): class + box (rounded to f32 as evaluation_recall.py:765 does)
+ * out: u32[n_frames, 3 protocols (with, no, semi constraint), 3 K (10,20,50), 8] = 256-bit sets of matched gt relations.
+ * Limits per frame (nlv_recall_limits): 40 pairs, 256 gt relations, 64 gt boxes.
+ * ------------------------------------------------------------------------------------------ */
+int nlv_recall_match(int n_frames, const int* pair_off, const int* gtrel_off, const int* gtbox_off, const int* pair_sub,
+                     const int* pair_obj, const float* att, const float* spa, const float* con, const float* obj_scores,
+                     const int* pred_cls, const float* pred_boxes, const int* gt_rel, const int* gt_cls,
+                     const float* gt_boxes, unsigned* out, void* stream);
+int nlv_recall_limits(int* p_max, int* g_max, int* gb_max);
+
 #ifdef __cplusplus
 }
 #endif

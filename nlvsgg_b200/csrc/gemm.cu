@@ -17,21 +17,25 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D, const float* __restrict__ bias,
                  const void* residual, int M, int N, int K, int lda, int ldb, int ldd, int ldr, int ab_dtype,
-                 int d_dtype, int r_dtype, int relu) {
+                 int d_dtype, int r_dtype, int relu, int k_per_split) {
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4 (strided by 16)
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  // split-K: blockIdx.z owns k in [kz0, kz1); partial sums are atomically added into a zeroed fp32 D
+  const int kz0 = blockIdx.z * k_per_split;
+  const int kz1 = min(K, kz0 + k_per_split);
+  const bool split = gridDim.z > 1;
+  for (int k0 = kz0; k0 < kz1; k0 += TK) {
     // load A tile: TM x TK
     for (int i = tid; i < TM * TK; i += 256) {
       int mm, kk;
       if (A_MN) { mm = i % TM; kk = i / TM; } else { kk = i % TK; mm = i / TK; }
       const int gm = m0 + mm, gk = k0 + kk;
       float v = 0.f;
-      if (gm < M && gk < K) v = A_MN ? ld_elem(A, ab_dtype, (size_t)gk * lda + gm) : ld_elem(A, ab_dtype, (size_t)gm * lda + gk);
+      if (gm < M && gk < kz1) v = A_MN ? ld_elem(A, ab_dtype, (size_t)gk * lda + gm) : ld_elem(A, ab_dtype, (size_t)gm * lda + gk);
       As[kk][mm] = v;
     }
     for (int i = tid; i < TN * TK; i += 256) {
@@ -39,7 +43,7 @@ gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D
       if (B_MN) { nn = i % TN; kk = i / TN; } else { kk = i % TK; nn = i / TK; }
       const int gn = n0 + nn, gk = k0 + kk;
       float v = 0.f;
-      if (gn < N && gk < K) v = B_MN ? ld_elem(B, ab_dtype, (size_t)gk * ldb + gn) : ld_elem(B, ab_dtype, (size_t)gn * ldb + gk);
+      if (gn < N && gk < kz1) v = B_MN ? ld_elem(B, ab_dtype, (size_t)gk * ldb + gn) : ld_elem(B, ab_dtype, (size_t)gn * ldb + gk);
       Bs[kk][nn] = v;
     }
     __syncthreads();
@@ -66,6 +70,7 @@ gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D
       const int gn = n0 + tx + 16 * j;
       if (gn >= N) continue;
       float v = acc[i][j];
+      if (split) { atomicAdd(reinterpret_cast<float*>(D) + (size_t)gm * ldd + gn, v); continue; }
       if (bias != nullptr) v += bias[gn];
       if (relu) v = fmaxf(v, 0.f);
       if (residual != nullptr) v += ld_as_float(residual, r_dtype, (size_t)gm * ldr + gn);
@@ -75,11 +80,22 @@ gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D
 }
 
 int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
-  dim3 grid(cdiv(g.n, TN), cdiv(g.m, TM));
+  dim3 grid(cdiv(g.n, TN), cdiv(g.m, TM), 1);
   NLV_CHECK_ARG(grid.y <= 65535, "gemm(simt): m=%d too large", g.m);
+  int k_per_split = g.k;
+  const int tiles = (int)(grid.x * grid.y);
+  if (tiles < 2 * sm_count() && g.k >= 2048 && g.d_dtype == NLV_F32 && !g.bias && !g.residual && !g.relu) {
+    int want = cdiv(4 * sm_count(), tiles);
+    if (want > g.k / 256) want = g.k / 256;
+    if (want > 1) {
+      k_per_split = cdiv(cdiv(g.k, want), TK) * TK;
+      grid.z = cdiv(g.k, k_per_split);
+      NLV_CHECK_CUDA(cudaMemset2DAsync(g.d, (size_t)g.ldd * 4, 0, (size_t)g.n * 4, g.m, s));
+    }
+  }
 #define LAUNCH(AM, BM)                                                                                          \
   gemm_simt_kernel<AM, BM><<<grid, 256, 0, s>>>(g.a, g.b, g.d, g.bias, g.residual, g.m, g.n, g.k, g.lda, g.ldb, \
-                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu)
+                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu, k_per_split)
   if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) LAUNCH(false, false);
   else if (g.a_major == NLV_MAJOR_K) LAUNCH(false, true);
   else if (g.b_major == NLV_MAJOR_K) LAUNCH(true, false);

@@ -122,6 +122,7 @@ struct Params {
   int d_dtype, r_dtype;
   int relu;
   int num_m_blocks, num_n_blocks;
+  int k_splits, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to a zeroed fp32 D
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -172,18 +173,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
-  const int num_tiles = p.num_m_blocks * p.num_n_blocks;
   const int num_k_blocks = (p.k + BLOCK_K - 1) / BLOCK_K;
+  const int num_work = p.num_m_blocks * p.num_n_blocks * p.k_splits;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int tile = work / p.k_splits;
+        const int kb0 = (work % p.k_splits) * p.kb_per_split;
+        const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
         const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
         const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
           const int k0 = kb * BLOCK_K;
@@ -218,13 +222,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++iter) {
+        const int kb0 = (work % p.k_splits) * p.kb_per_split;
+        const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
         const int acc = iter & 1;
         const uint32_t acc_phase = (iter >> 1) & 1;
         mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = smem_a + stage * A_STAGE_BYTES;
@@ -233,10 +239,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
           tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
-          if (kb == num_k_blocks - 1) tc_commit(tmem_full_bar(acc));
+          if (kb == kb1 - 1) tc_commit(tmem_full_bar(acc));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -248,7 +254,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool d_bf16 = p.d_dtype == NLV_BF16;
     const bool vec_ok = d_bf16 ? ((p.ldd & 7) == 0 && ((uintptr_t)p.d & 15) == 0)
                                : ((p.ldd & 3) == 0 && ((uintptr_t)p.d & 15) == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+    const bool split = p.k_splits > 1;
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++iter) {
+      const int tile = work / p.k_splits;
       const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
       const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
       const int acc = iter & 1;
@@ -275,6 +283,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         float f[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        if (split) {  // partial sum of one k range: accumulate into the zero-initialised fp32 output
+          float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + n0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < ncol) atomicAdd(o + j, f[j]);
+          continue;
+        }
         if (p.bias != nullptr) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -407,13 +422,28 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
   p.num_m_blocks = cdiv(g.m, BLOCK_M);
   p.num_n_blocks = cdiv(g.n, BLOCK_N);
+  // split-K when the output has too few tiles to fill the GPU and the reduction is long (weight gradients of the
+  // conv / union layers reduce over R*49..R*196 rows into one or a handful of tiles)
+  const int nkb = cdiv(g.k, BLOCK_K);
+  const int tiles0 = p.num_m_blocks * p.num_n_blocks;
+  p.k_splits = 1;
+  p.kb_per_split = nkb;
+  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu) {
+    int want = sm_count() / tiles0;
+    if (want > nkb / 8) want = nkb / 8;
+    if (want > 1) {
+      p.kb_per_split = cdiv(nkb, want);
+      p.k_splits = cdiv(nkb, p.kb_per_split);
+      NLV_CHECK_CUDA(cudaMemset2DAsync(g.d, (size_t)g.ldd * 4, 0, (size_t)g.n * 4, g.m, stream));
+    }
+  }
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
     NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks;
+  const int tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
   NLV_CHECK_LAUNCH();

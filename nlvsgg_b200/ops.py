@@ -61,7 +61,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_major: int = 
     g.d_dtype = _dt(out)
     g.r_dtype = _dt(residual) if residual is not None else NLV_F32
     g.relu = 1 if relu else 0
+    if PROFILE is None:
+        _C.check(_C.lib().nlv_gemm(ctypes.byref(g), _stream()), "gemm")
+        return out
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     _C.check(_C.lib().nlv_gemm(ctypes.byref(g), _stream()), "gemm")
+    e.record()
+    tag = "nlv_gemm[%s %s%s m=%d n=%d k=%d]" % ("tc" if (a.dtype == torch.bfloat16 and not force_simt) else "simt",
+                                                 "KM"[a_major == MAJOR_MN], "KM"[b_major == MAJOR_MN], m, n, k)
+    PROFILE.setdefault(tag, []).append((s, e))
     return out
 
 
@@ -106,8 +115,24 @@ _F = ctypes.c_float
 _LL = ctypes.c_longlong
 
 
+PROFILE = None  # set to {} to collect (start, end) CUDA events per entry point; see profile_summary()
+
+
 def _call(name, *args):
+    if PROFILE is None:
+        _C.check(getattr(_C.lib(), name)(*args, _stream()), name)
+        return
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
     _C.check(getattr(_C.lib(), name)(*args, _stream()), name)
+    e.record()
+    PROFILE.setdefault(name, []).append((s, e))
+
+
+def profile_summary():
+    """{entry point: (calls, total ms)} from the events collected while PROFILE was a dict (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in (PROFILE or {}).items()}
 
 
 def convert(src: torch.Tensor, dtype: torch.dtype, out: torch.Tensor | None = None) -> torch.Tensor:

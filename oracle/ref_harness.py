@@ -182,3 +182,15 @@ def build_reference_sttran(ref, mode: str):
 def build_reference_dsg(ref, mode: str):
     return ref.dsg_detr.STTran(mode=mode, attention_class_num=3, spatial_class_num=6, contact_class_num=17,
                                obj_classes=ref.obj_classes)
+
+
+def load_stable_evaluator(ref):
+    """Scratch copy of lib/evaluation_recall.py with the two one-word stable-sort patches of SURVEY.md Appendix A.10
+    (argsort(kind='stable') at :670-672 and a stable argsort_desc).  Nothing is written into the repository."""
+    src = os.path.join(SCRATCH, "lib", "evaluation_recall.py")
+    dst = os.path.join(SCRATCH, "lib", "evaluation_recall_stable.py")
+    txt = open(src).read().replace("sorted_scores.argsort()[::-1]", 'sorted_scores.argsort(kind="stable")[::-1]')
+    open(dst, "w").write(txt)
+    mod = importlib.import_module("lib.evaluation_recall_stable")
+    mod.argsort_desc = lambda s: np.column_stack(np.unravel_index(np.argsort(-s.ravel(), kind="stable"), s.shape))
+    return mod

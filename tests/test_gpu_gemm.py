@@ -94,3 +94,18 @@ def test_gemm_rejects_bad_args(cuda_lib):
     out = torch.empty(16, 16, device="cuda")
     with pytest.raises(RuntimeError):
         ops.gemm(a, b, out)
+
+
+@pytest.mark.parametrize("m,n,k,dtype", [(128, 104, 300000, torch.bfloat16), (256, 1152, 70001, torch.bfloat16),
+                                         (26, 1936, 12000, torch.float32), (128, 4, 14000, torch.float32)])
+def test_gemm_split_k_weight_gradient_shapes(cuda_lib, m, n, k, dtype):
+    """dW = dY^T X with a long token reduction and one / a few output tiles (split-K + atomics path)."""
+    from nlvsgg_b200 import ops
+    torch.manual_seed(9)
+    pad_a, pad_b = (-m) % 8, (-n) % 8
+    a = (_mk(m, k, 1, torch.float32, pad_a) * 0.05).to(dtype)
+    b = (_mk(n, k, 1, torch.float32, pad_b) * 0.05).to(dtype)
+    out = torch.full((m, n), float("nan"), device="cuda")
+    ops.gemm(a, b, out, a_major=1, b_major=1)
+    ref = _ref(a, b, 1, 1, None, None, False)
+    assert (out.double() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item() + 1e-5
