@@ -18,6 +18,22 @@ void set_error(const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+__global__ void zero_fill_kernel(float* p, long long rows, int cols, int ld) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  p[r * ld + (i - r * cols)] = 0.f;
+}
+
+// Zero a strided fp32 matrix with a kernel (cudaMemset*Async may be routed to a copy engine, where it would queue
+// behind a multi-GB host-to-device prefetch running on another stream).
+int zero_fill(float* p, long long rows, int cols, int ld, cudaStream_t s) {
+  if (rows * cols == 0) return NLV_OK;
+  zero_fill_kernel<<<cdiv(rows * cols, 256), 256, 0, s>>>(p, rows, cols, ld);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {

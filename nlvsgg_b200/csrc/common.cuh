@@ -40,6 +40,7 @@ void count_launch(int n);
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();
+int zero_fill(float* p, long long rows, int cols, int ld, cudaStream_t s);
 
 // dtype-tagged load/store used by the elementwise kernels (dtype: NLV_F32 / NLV_BF16)
 __device__ __forceinline__ float ld_as_float(const void* p, int dtype, size_t i) {

@@ -90,7 +90,7 @@ int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
     if (want > 1) {
       k_per_split = cdiv(cdiv(g.k, want), TK) * TK;
       grid.z = cdiv(g.k, k_per_split);
-      NLV_CHECK_CUDA(cudaMemset2DAsync(g.d, (size_t)g.ldd * 4, 0, (size_t)g.n * 4, g.m, s));
+      { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, s); if (zrc != NLV_OK) return zrc; }
     }
   }
 #define LAUNCH(AM, BM)                                                                                          \

@@ -434,7 +434,7 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
     if (want > 1) {
       p.kb_per_split = cdiv(nkb, want);
       p.k_splits = cdiv(nkb, p.kb_per_split);
-      NLV_CHECK_CUDA(cudaMemset2DAsync(g.d, (size_t)g.ldd * 4, 0, (size_t)g.n * 4, g.m, stream));
+      { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, stream); if (zrc != NLV_OK) return zrc; }
     }
   }
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;

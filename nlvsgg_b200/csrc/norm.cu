@@ -313,7 +313,7 @@ int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, l
                  double* sums_ws, float* mean, float* var, float* running_mean, float* running_var, void* stream) {
   NLV_CHECK_ARG(nseg >= 1 && c > 0 && rows >= 0, "bn_stats: bad sizes");
   NLV_CHECK_ARG(x && seg && sums_ws && mean && var, "bn_stats: null pointer");
-  NLV_CHECK_CUDA(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (size_t)nseg * 2 * c, STREAM));
+  { int zrc = zero_fill(reinterpret_cast<float*>(sums_ws), 1, 4 * nseg * c, 4 * nseg * c, STREAM); if (zrc != NLV_OK) return zrc; }
   if (rows > 0) {
     NLV_CHECK_ARG(nseg <= 65535, "bn_stats: too many segments");
     dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
@@ -345,7 +345,7 @@ int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, c
                float* db, void* stream) {
   NLV_CHECK_ARG(nseg >= 1 && c > 0 && rows >= 0, "bn_bwd: bad sizes");
   NLV_CHECK_ARG(dy && x && seg && mean && var && w && sums_ws && dx && dw && db, "bn_bwd: null pointer");
-  NLV_CHECK_CUDA(cudaMemsetAsync(sums_ws, 0, sizeof(double) * (size_t)nseg * 2 * c, STREAM));
+  { int zrc = zero_fill(reinterpret_cast<float*>(sums_ws), 1, 4 * nseg * c, 4 * nseg * c, STREAM); if (zrc != NLV_OK) return zrc; }
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(nseg <= 65535, "bn_bwd: too many segments");
   dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);

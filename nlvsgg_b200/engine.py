@@ -36,6 +36,7 @@ class Kernels:
         self.precision = precision
         self.AD = BF16 if precision == "bf16" else F32   # dtype of GEMM-operand activations
         self._wcache: Dict[tuple, tuple] = {}
+        self.mirror: Dict[str, torch.Tensor] = {}
 
     # ---- activations -------------------------------------------------------------------------
     def opnd(self, x: torch.Tensor) -> torch.Tensor:
@@ -48,6 +49,9 @@ class Kernels:
     def weight(self, key: str, srcs, make=None, f32: bool = False) -> torch.Tensor:
         """Cached operand form of one or several parameters (re-made when any of them is updated in place).
         `make(*tensors)` builds the matrix (concatenation / permutation / reshape); f32 keeps it in fp32."""
+        m = self.mirror.get(key)
+        if m is not None:      # operand copy kept current by the optimiser kernel (trainer.py)
+            return m
         if torch.is_tensor(srcs):
             srcs = (srcs,)
         ver = tuple((t.data_ptr(), t._version) for t in srcs)
@@ -102,118 +106,7 @@ class Kernels:
         return x
 
 
-# ================================================================================================
-# host-side descriptors
-# ================================================================================================
-def _work_items(seg_start: np.ndarray, seg_len: np.ndarray) -> np.ndarray:
-    """int4 work list for the attention kernels: 16 rows of one segment per item."""
-    items = []
-    for s, l in zip(seg_start.tolist(), seg_len.tolist()):
-        for q0 in range(0, l, 16):
-            items.append((s, l, q0, 0))
-    return np.asarray(items, dtype=np.int32).reshape(-1, 4)
-
-
-class Plan:
-    """Everything the kernels need to know about the batch structure (built on the host from the frame ids)."""
-
-    def __init__(self, n_boxes: List[int], frame_ids: List[np.ndarray], device, obj_class: Optional[np.ndarray] = None,
-                 subj_box: Optional[np.ndarray] = None, dsg: bool = False, dsg_pos_by_rank: bool = True):
-        nv = len(n_boxes)
-        self.nv = nv
-        n_pairs = [len(f) for f in frame_ids]
-        self.N, self.R = int(sum(n_boxes)), int(sum(n_pairs))
-        box_seg = np.concatenate(([0], np.cumsum(n_boxes))).astype(np.int32)
-        pair_seg = np.concatenate(([0], np.cumsum(n_pairs))).astype(np.int32)
-        box_row = np.repeat(np.arange(nv, dtype=np.int32), n_boxes)
-        pair_row = np.repeat(np.arange(nv, dtype=np.int32), n_pairs)
-
-        # ---- frames (spatial encoder segments) ----
-        f_start, f_len = [], []
-        # ---- window stream (temporal decoder) ----
-        stream_src, stream_slot, w_start, w_len = [], [], [], []
-        out_src = np.full(self.R, -1, dtype=np.int32)        # stream row giving token r's output
-        passthrough = np.full(self.R, -1, dtype=np.int32)    # tokens of single-frame videos: output = local output
-        row0 = 0
-        for v in range(nv):
-            fid = np.asarray(frame_ids[v]).astype(np.int64)
-            if len(fid) == 0:
-                continue
-            assert np.all(np.diff(fid) >= 0), "im_idx must be sorted"
-            b = int(fid[-1]) + 1
-            cnt = np.bincount(fid, minlength=b)
-            start = np.concatenate(([0], np.cumsum(cnt)))
-            for f in range(b):
-                if cnt[f]:
-                    f_start.append(row0 + start[f]); f_len.append(cnt[f])
-            wins = [j for j in range(b - 1) if cnt[j] + cnt[j + 1] > 0]
-            if not wins:
-                passthrough[row0:row0 + len(fid)] = np.arange(row0, row0 + len(fid))
-            for j in wins:
-                base = len(stream_src)
-                n0, n1 = int(cnt[j]), int(cnt[j + 1])
-                rows = np.arange(row0 + start[j], row0 + start[j + 2])
-                stream_src.extend(rows.tolist())
-                stream_slot.extend([0] * n0 + [1] * n1)
-                w_start.append(base); w_len.append(n0 + n1)
-                if j == 0 and n0:
-                    out_src[rows[:n0]] = base + np.arange(n0)
-                if n1:
-                    out_src[rows[n0:]] = base + n0 + np.arange(n1)
-            row0 += len(fid)
-        self.Mg = len(stream_src)
-        stream_src = np.asarray(stream_src, dtype=np.int32)
-        inv = np.full((self.R, 2), -1, dtype=np.int32)       # stream rows holding a copy of token r
-        fill = np.zeros(self.R, dtype=np.int32)
-        for srow, r in enumerate(stream_src.tolist()):
-            inv[r, fill[r]] = srow; fill[r] += 1
-        out_inv = np.full(max(self.Mg, 1), -1, dtype=np.int32)  # token whose output comes from this stream row
-        ok = out_src >= 0
-        out_inv[out_src[ok]] = np.nonzero(ok)[0]
-        self.has_passthrough = bool((passthrough >= 0).any())
-
-        dev = device
-        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev, non_blocking=True)
-        self.box_seg, self.pair_seg = t(box_seg), t(pair_seg)
-        self.box_row, self.pair_row = t(box_row), t(pair_row)
-        self.seg196, self.seg49 = t(pair_seg * 196), t(pair_seg * 49)
-        self.row196 = t(np.repeat(pair_row, 196)) if nv > 1 else None
-        self.row49 = t(np.repeat(pair_row, 49)) if nv > 1 else None
-        if nv == 1:
-            self.box_row = self.pair_row = None
-        lw = _work_items(np.asarray(f_start, dtype=np.int64), np.asarray(f_len, dtype=np.int64))
-        self.local_work, self.n_local_work = t(lw), len(lw)
-        gw = _work_items(np.asarray(w_start, dtype=np.int64), np.asarray(w_len, dtype=np.int64))
-        self.glob_work, self.n_glob_work = t(gw), len(gw)
-        self.stream_src, self.stream_slot = t(stream_src), t(np.asarray(stream_slot, dtype=np.int32))
-        self.inv, self.out_src, self.out_inv = t(inv), t(out_src), t(out_inv[:self.Mg] if self.Mg else out_inv[:0])
-        self.passthrough = t(passthrough)
-
-        # ---- DSG-DETR class sequences ----
-        self.dsg = dsg
-        if dsg:
-            assert nv == 1 or True
-            perm, s_start, s_len, pos = [], [], [], []
-            row0 = 0
-            for v in range(nv):
-                r0, r1 = int(pair_seg[v]), int(pair_seg[v + 1])
-                oc = obj_class[r0:r1]
-                for c in np.unique(oc):
-                    rows = np.nonzero(oc == c)[0]
-                    s_start.append(len(perm)); s_len.append(len(rows))
-                    perm.extend((rows + r0).tolist())
-                    if dsg_pos_by_rank:
-                        _, inv_s, counts = np.unique(subj_box[rows + r0], return_inverse=True, return_counts=True)
-                        pos.extend(np.repeat(np.arange(len(counts)), counts).tolist())
-                    else:
-                        pos.extend(range(len(rows)))
-            perm = np.asarray(perm, dtype=np.int32)
-            self.cls_perm = t(perm)
-            iperm = np.empty_like(perm); iperm[perm] = np.arange(len(perm), dtype=np.int32)
-            self.cls_iperm = t(iperm)
-            self.cls_pos = t(np.asarray(pos, dtype=np.int32))
-            cw = _work_items(np.asarray(s_start, dtype=np.int64), np.asarray(s_len, dtype=np.int64))
-            self.cls_work, self.n_cls_work = t(cw), len(cw)
+from .plan import Plan  # noqa: E402,F401  (host-side descriptors live in plan.py)
 
 
 # ================================================================================================

@@ -52,16 +52,26 @@ def collate(entries: List[dict], mode: str, pin: bool = False) -> Batch:
     return b
 
 
-def upload(hb: Batch, device) -> Batch:
+def upload(hb: Batch, device, rasterise: bool = True, consumer_stream=None) -> Batch:
     """Device copy of a collated batch (async copies on the current stream); rasterises the spatial masks on
-    device when the producer did not supply them (fused pair gather + draw_union_boxes - 0.5)."""
+    device when the producer did not supply them (fused pair gather + draw_union_boxes - 0.5).
+    consumer_stream: the stream that will read the tensors when the copies are issued on a side stream."""
     dev = torch.device(device)
     b = Batch()
     b.__dict__.update(hb.__dict__)
     for key in TENSOR_KEYS:
         t = getattr(hb, key)
         if t is not None:
-            setattr(b, key, t.to(dev, non_blocking=True))
+            d = t.to(dev, non_blocking=True)
+            if consumer_stream is not None and d is not t:
+                d.record_stream(consumer_stream)
+            setattr(b, key, d)
+    if rasterise:
+        ensure_masks(b)
+    return b
+
+
+def ensure_masks(b: Batch) -> Batch:
     if b.spatial_masks is None:
         b.spatial_masks = ops.union_mask_pairs(b.boxes, b.pair_idx, 27, -0.5)
     return b
@@ -71,14 +81,22 @@ def input_bytes(hb: Batch) -> int:
     return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in TENSOR_KEYS if getattr(hb, k) is not None))
 
 
-def make_plan(b: Batch, device, mode: str, dsg: bool = False) -> "E.Plan":
+def make_plan(b: Batch, device, mode: str, dsg: bool = False, with_labels: bool = False, consumer_stream=None) -> "E.Plan":
+    """Descriptors (+ optionally the loss labels) -> one pinned async upload.  plan.labels is set when with_labels."""
     obj_class = subj_box = None
     if dsg:
         lab = b.labels.cpu().numpy()
         pi = b.pair_idx.cpu().numpy()
         obj_class, subj_box = lab[pi[:, 1]], pi[:, 0]
-    return E.Plan(b.n_boxes, b.frame_ids, torch.device(device), obj_class=obj_class, subj_box=subj_box, dsg=dsg,
-                  dsg_pos_by_rank=(mode == "sgdet"))
+    extra = label_arrays(b) if with_labels else None
+    plan = E.Plan(b.n_boxes, b.frame_ids, torch.device(device), obj_class=obj_class, subj_box=subj_box, dsg=dsg,
+                  dsg_pos_by_rank=(mode == "sgdet"), extra=extra, consumer_stream=consumer_stream)
+    if with_labels:
+        L = Labels()
+        L.att, L.w_att, L.spa_bits, L.w_spa = plan.lab_att, plan.lab_w_att, plan.lab_spa_bits, plan.lab_w_spa
+        L.con_bits, L.w_con, L.w_obj = plan.lab_con_bits, plan.lab_w_con, plan.lab_w_obj
+        plan.labels = L
+    return plan
 
 
 def make_batch(entries: List[dict], device, mode: str, dsg: bool = False):
@@ -183,29 +201,48 @@ class Labels:
     pass
 
 
-def make_labels(batch: Batch, device, mode: str) -> Labels:
-    """Label tensors + per-row loss weights from the python label lists of the entries (train_STTran.py:143-167)."""
+def _bits_of(lists) -> np.ndarray:
+    """uint32 multi-hot mask per row from a list of index lists (vectorised)."""
+    n = len(lists)
+    lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=n)
+    out = np.zeros(n, dtype=np.uint32)
+    if lens.sum() == 0:
+        return out
+    flat = np.fromiter((int(j) for x in lists for j in x), dtype=np.int64, count=int(lens.sum()))
+    rows = np.repeat(np.arange(n), lens)
+    np.bitwise_or.at(out, rows, (np.uint32(1) << flat.astype(np.uint32)))
+    return out
+
+
+def label_arrays(batch: Batch) -> dict:
+    """Label tensors + per-row loss weights from the python label lists of the entries (train_STTran.py:143-167).
+    Weight = 1 / (rows of that video entering the mean) / (classes, for BCE) / videos."""
     nv = len(batch.n_boxes)
-    L = Labels()
     att, w_att, spa_bits, w_spa, con_bits, w_con, w_obj = [], [], [], [], [], [], []
     for (a_gt, s_gt, c_gt), nb in zip(batch.gt_lists, batch.n_boxes):
         n = len(a_gt)
-        a = np.array([int(x[0]) if len(x) else -1 for x in a_gt], dtype=np.int64).reshape(n)
+        a = np.fromiter((int(x[0]) if len(x) else -1 for x in a_gt), dtype=np.int64, count=n)
         na = int((a >= 0).sum())
         att.append(a)
         w_att.append(np.where(a >= 0, 1.0 / (max(na, 1) * nv), 0.0).astype(np.float32))
-        sb = np.array([sum(1 << int(j) for j in set(x)) for x in s_gt], dtype=np.uint32).reshape(n)
-        cb = np.array([sum(1 << int(j) for j in set(x)) for x in c_gt], dtype=np.uint32).reshape(n)
+        sb, cb = _bits_of(s_gt), _bits_of(c_gt)
         ns, nc = int((sb != 0).sum()), int((cb != 0).sum())
         spa_bits.append(sb); con_bits.append(cb)
         w_spa.append(np.where(sb != 0, 1.0 / (max(ns, 1) * 6 * nv), 0.0).astype(np.float32))
         w_con.append(np.where(cb != 0, 1.0 / (max(nc, 1) * 17 * nv), 0.0).astype(np.float32))
         w_obj.append(np.full(nb, 1.0 / (max(nb, 1) * nv), dtype=np.float32))
-    t = lambda a: torch.from_numpy(np.ascontiguousarray(np.concatenate(a))).to(device, non_blocking=True)
-    L.att, L.w_att = t(att), t(w_att)
-    L.spa_bits, L.w_spa = t([x.view(np.int32) for x in spa_bits]), t(w_spa)
-    L.con_bits, L.w_con = t([x.view(np.int32) for x in con_bits]), t(w_con)
-    L.w_obj = t(w_obj)
+    c = np.concatenate
+    return {"lab_att": c(att), "lab_w_att": c(w_att), "lab_spa_bits": c(spa_bits), "lab_w_spa": c(w_spa),
+            "lab_con_bits": c(con_bits), "lab_w_con": c(w_con), "lab_w_obj": c(w_obj)}
+
+
+def make_labels(batch: Batch, device, mode: str) -> Labels:
+    from .plan import pack_upload
+    d = pack_upload(label_arrays(batch), device)
+    L = Labels()
+    L._keep = d.pop("_pinned_keepalive")
+    L.att, L.w_att, L.spa_bits, L.w_spa = d["lab_att"], d["lab_w_att"], d["lab_spa_bits"], d["lab_w_spa"]
+    L.con_bits, L.w_con, L.w_obj = d["lab_con_bits"], d["lab_w_con"], d["lab_w_obj"]
     return L
 
 
