@@ -180,6 +180,26 @@ int nlv_recall_match(int n_frames, const int* pair_off, const int* gtrel_off, co
                      const float* gt_boxes, unsigned* out, void* stream);
 int nlv_recall_limits(int* p_max, int* g_max, int* gb_max);
 
+/* ------------------------------------------------------------------------------------------
+ * Native surface 1 of the reference: fasterRCNN/lib/model/csrc/vision.cpp:7-13 (pybind11 `_C`)
+ * ------------------------------------------------------------------------------------------ */
+/* _C.roi_align_forward(input[b,c,h,w], rois[r,5], spatial_scale, ph, pw, sampling_ratio) -> [r,c,ph,pw]
+ * (ROIAlign.h:11-27, ROIAlign_cuda.cu:65-122); bit-identical to the reference CPU kernel */
+int nlv_roi_align_fwd(const float* input, int b, int c, int h, int w, const float* rois, int r, float spatial_scale, int ph,
+                      int pw, int sampling_ratio, float* out, void* stream);
+/* _C.roi_align_backward(grad, rois, scale, ph, pw, b, c, h, w, sampling_ratio) -> [b,c,h,w] (ROIAlign.h:29-45);
+ * dinput must be zeroed by the caller */
+int nlv_roi_align_bwd(const float* grad, const float* rois, int r, float spatial_scale, int ph, int pw, int b, int c, int h, int w,
+                      int sampling_ratio, float* dinput, void* stream);
+/* _C.nms(dets[n,4], scores[n], thr) (nms.h:10-28, nms.cu:23-131): `order` = argsort(scores, descending);
+ * keep_flags u8[n] (zeroed by the caller) marks kept ORIGINAL indices; mask_ws u64[n*ceil(n/64)] */
+int nlv_nms(const float* dets, const long long* order, int n, float thr, int strict, unsigned long long* mask_ws,
+            unsigned char* keep_flags, void* stream);
+/* lib/matcher.py:102-150 HungarianMatcher cost matrix for one frame (detections x live tracks) */
+int nlv_track_cost(const float* det_box_xywh, const float* trk_box_xywh, const float* det_feat, const float* trk_feat, int feat_dim,
+                   const float* det_dist, const float* trk_dist, int dist_dim, int n_det, int n_trk, float w_class, float w_feat,
+                   float w_bbox, float w_giou, float* cost, float* cost_dist, float* cost_feat, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
