@@ -60,6 +60,9 @@ typedef struct nlv_gemm_args {
   int a_major, b_major;
   int ab_dtype, d_dtype, r_dtype;
   int relu;             /* applied after bias, before residual */
+  const void* gate;     /* optional [m,n] (row stride ldg, dtype gate_dtype): value kept where gate > 0, else 0 —
+                           the ReLU backward fused into an input-gradient GEMM; applied before residual */
+  int ldg, gate_dtype;
 } nlv_gemm_args;
 
 int nlv_gemm(const nlv_gemm_args* args, void* stream);
@@ -94,7 +97,8 @@ int nlv_split3(const float* src, int lds, long long rows, int cols, void* dst_bf
 int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_dtype, void* stream);
 /* im2col of the 2x27x27 spatial masks for Conv2d(2,128,k7,s2,p3) (lib/sttran.py:338): -> [r*196, ldd], 98 cols */
 int nlv_im2col_mask(const float* masks, int r, void* dst, int dst_dtype, int ldd, void* stream);
-/* im2col / col2im of the 3x3 s1 p1 conv (lib/sttran.py:342) over NHWC [r,h,w,c]; column = c*9+ky*3+kx */
+/* im2col / col2im of the 3x3 s1 p1 conv (lib/sttran.py:342) over NHWC [r,h,w,c]; column = (ky*3+kx)*c_total + c
+ * (channels innermost: both sides move whole 16-byte channel groups; the conv weight is permuted to match) */
 int nlv_im2col_3x3(const void* x, int x_dtype, int r, int h, int w, int c, void* dst, int dst_dtype, void* stream);
 int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, float* dx, void* stream);
 /* MaxPool2d(3,2,1) (lib/sttran.py:341) on NHWC [r,14,14,c] -> [r,7,7,c]; argmax u8 per output */
@@ -139,8 +143,8 @@ int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const 
                  void* y2, int y2_dtype, int ldy2, void* stream);
 int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
                const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
-               int use_batch_stats, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
-               float* db, void* stream);
+               int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx,
+               float* dw, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused variable-length attention over contiguous segments (nn.MultiheadAttention core of

@@ -62,7 +62,7 @@ class GemmArgs(ctypes.Structure):
                 ("lda", ctypes.c_int), ("ldb", ctypes.c_int), ("ldd", ctypes.c_int), ("ldr", ctypes.c_int),
                 ("a_major", ctypes.c_int), ("b_major", ctypes.c_int),
                 ("ab_dtype", ctypes.c_int), ("d_dtype", ctypes.c_int), ("r_dtype", ctypes.c_int),
-                ("relu", ctypes.c_int)]
+                ("relu", ctypes.c_int), ("gate", ctypes.c_void_p), ("ldg", ctypes.c_int), ("gate_dtype", ctypes.c_int)]
 
 
 _lib = None

@@ -3,6 +3,19 @@
 #include "common.cuh"
 
 namespace nlv {
+// 16-byte vectorised variants (elem_vec.cu)
+int launch_convert8(const void* src, int sdt, void* dst, int ddt, long long n, cudaStream_t s);
+int launch_im2col_3x3_v8(const void* x, int xdt, int r, int h, int w, int c, void* dst, int ddt, cudaStream_t s);
+int launch_col2im_3x3_v8(const void* dcol, int cdt, int r, int h, int w, int c, float* dx, cudaStream_t s);
+int launch_maxpool_fwd_v8(const void* x, int xdt, int r, int c, void* y, int ydt, uint8_t* arg, cudaStream_t s);
+int launch_maxpool_bwd_v8(const float* dy, const uint8_t* arg, int r, int c, float* dx, cudaStream_t s);
+int launch_im2col_mask_v8(const float* m, int r, void* dst, int ddt, int ld, cudaStream_t s);
+int launch_colsum_v8(const void* x, int xdt, int ld, long long rows, int cols, const int* row_class, int n_class, float* out,
+                     cudaStream_t s);
+int launch_gather_rows_v4(const float* src, int lds, const int* idx, const float* add, const int* add_idx, int ld_add,
+                          long long n_out, int cols, float* dst, int ldd, void* dst2, int d2dt, int ldd2, cudaStream_t s);
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 namespace {
 
 constexpr int TPB = 256;
@@ -80,7 +93,7 @@ __global__ void im2col_mask_kernel(const float* __restrict__ m, long long total,
   st_from_float(dst, ddt, (size_t)i, v);
 }
 
-// im2col for a 3x3/s1/p1 conv over NHWC [R,H,W,C] -> [R*H*W, C*9], column = c*9 + ky*3 + kx
+// im2col for a 3x3/s1/p1 conv over NHWC [R,H,W,C] -> [R*H*W, 9*C], column = (ky*3 + kx)*C + c
 __global__ void im2col_3x3_kernel(const void* __restrict__ x, int xdt, int H, int W, int C, long long total,
                                   void* __restrict__ dst, int ddt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -88,7 +101,7 @@ __global__ void im2col_3x3_kernel(const void* __restrict__ x, int xdt, int H, in
   const int K = C * 9;
   const int col = (int)(i % K);
   const long long row = i / K;
-  const int c = col / 9, ky = (col % 9) / 3, kx = col % 3;
+  const int c = col % C, ky = (col / C) / 3, kx = (col / C) % 3;
   const int ox = (int)(row % W), oy = (int)((row / W) % H);
   const long long r = row / ((long long)H * W);
   const int iy = oy - 1 + ky, ix = ox - 1 + kx;
@@ -97,7 +110,7 @@ __global__ void im2col_3x3_kernel(const void* __restrict__ x, int xdt, int H, in
   st_from_float(dst, ddt, (size_t)i, v);
 }
 
-// transpose of the above (gather form, no atomics): dx[r,y,x,c] = sum_{ky,kx} dcol[(r,y+1-ky,x+1-kx), c*9+ky*3+kx]
+// transpose of the above (gather form, no atomics): dx[r,y,x,c] = sum_{ky,kx} dcol[(r,y+1-ky,x+1-kx), (ky*3+kx)*C+c]
 __global__ void col2im_3x3_kernel(const void* __restrict__ dcol, int cdt, int H, int W, int C, long long total,
                                   float* __restrict__ dx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +127,7 @@ __global__ void col2im_3x3_kernel(const void* __restrict__ dcol, int cdt, int H,
     for (int kx = 0; kx < 3; ++kx) {
       const int oy = y + 1 - ky, ox = x + 1 - kx;
       if (oy >= 0 && oy < H && ox >= 0 && ox < W)
-        acc += ld_as_float(dcol, cdt, (size_t)((r * H + oy) * W + ox) * K + c * 9 + ky * 3 + kx);
+        acc += ld_as_float(dcol, cdt, (size_t)((r * H + oy) * W + ox) * K + (ky * 3 + kx) * C + c);
     }
   dx[i] = acc;
 }
@@ -324,6 +337,8 @@ int nlv_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtyp
   NLV_CHECK_ARG(rows >= 0 && cols >= 0, "convert: bad sizes");
   if (rows * cols == 0) return NLV_OK;
   NLV_CHECK_ARG(src && dst, "convert: null pointer");
+  if ((rows == 1 || (lds == cols && ldd == cols)) && ((rows * cols) & 7) == 0 && al16(src) && al16(dst))
+    return launch_convert8(src, src_dtype, dst, dst_dtype, rows * cols, STREAM);
   convert_kernel<<<GRID1D(rows * cols)>>>(src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
@@ -355,6 +370,7 @@ int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_
 int nlv_im2col_mask(const float* masks, int r, void* dst, int dst_dtype, int ldd, void* stream) {
   NLV_CHECK_ARG(r >= 0 && ldd >= 98, "im2col_mask: bad sizes");
   if (r == 0) return NLV_OK;
+  if ((ldd & 7) == 0 && al16(dst)) return launch_im2col_mask_v8(masks, r, dst, dst_dtype, ldd, STREAM);
   const long long total = (long long)r * 196 * ldd;
   im2col_mask_kernel<<<GRID1D(total)>>>(masks, total, dst, dst_dtype, ldd);
   NLV_CHECK_LAUNCH();
@@ -364,6 +380,7 @@ int nlv_im2col_mask(const float* masks, int r, void* dst, int dst_dtype, int ldd
 int nlv_im2col_3x3(const void* x, int x_dtype, int r, int h, int w, int c, void* dst, int dst_dtype, void* stream) {
   NLV_CHECK_ARG(r >= 0 && h > 0 && w > 0 && c > 0, "im2col_3x3: bad sizes");
   if (r == 0) return NLV_OK;
+  if ((c & 7) == 0 && al16(x) && al16(dst)) return launch_im2col_3x3_v8(x, x_dtype, r, h, w, c, dst, dst_dtype, STREAM);
   const long long total = (long long)r * h * w * c * 9;
   im2col_3x3_kernel<<<GRID1D(total)>>>(x, x_dtype, h, w, c, total, dst, dst_dtype);
   NLV_CHECK_LAUNCH();
@@ -373,6 +390,7 @@ int nlv_im2col_3x3(const void* x, int x_dtype, int r, int h, int w, int c, void*
 int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, float* dx, void* stream) {
   NLV_CHECK_ARG(r >= 0 && h > 0 && w > 0 && c > 0, "col2im_3x3: bad sizes");
   if (r == 0) return NLV_OK;
+  if ((c & 7) == 0 && al16(dcol) && al16(dx)) return launch_col2im_3x3_v8(dcol, dtype, r, h, w, c, dx, STREAM);
   const long long total = (long long)r * h * w * c;
   col2im_3x3_kernel<<<GRID1D(total)>>>(dcol, dtype, h, w, c, total, dx);
   NLV_CHECK_LAUNCH();
@@ -382,6 +400,7 @@ int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, floa
 int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dtype, uint8_t* argmax, void* stream) {
   NLV_CHECK_ARG(r >= 0 && c > 0, "maxpool_fwd: bad sizes");
   if (r == 0) return NLV_OK;
+  if ((c & 7) == 0 && al16(x) && al16(y) && al16(argmax)) return launch_maxpool_fwd_v8(x, x_dtype, r, c, y, y_dtype, argmax, STREAM);
   const long long total = (long long)r * 49 * c;
   maxpool_fwd_kernel<<<GRID1D(total)>>>(x, x_dtype, c, total, y, y_dtype, argmax);
   NLV_CHECK_LAUNCH();
@@ -391,6 +410,7 @@ int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dty
 int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, float* dx, void* stream) {
   NLV_CHECK_ARG(r >= 0 && c > 0, "maxpool_bwd: bad sizes");
   if (r == 0) return NLV_OK;
+  if ((c & 7) == 0 && al16(dy) && al16(dx) && al16(argmax)) return launch_maxpool_bwd_v8(dy, argmax, r, c, dx, STREAM);
   const long long total = (long long)r * 196 * c;
   maxpool_bwd_kernel<<<GRID1D(total)>>>(dy, argmax, c, total, dx);
   NLV_CHECK_LAUNCH();
@@ -403,6 +423,10 @@ int nlv_gather_rows(const void* src, int src_dtype, int lds, const int* idx, con
   NLV_CHECK_ARG(n_out >= 0 && cols >= 0, "gather_rows: bad sizes");
   if (n_out * cols == 0) return NLV_OK;
   NLV_CHECK_ARG(src && (dst || dst2), "gather_rows: null pointer");
+  if (src_dtype == NLV_F32 && (dst == nullptr || dst_dtype == NLV_F32) && (cols & 3) == 0 && (lds & 3) == 0 && (ldd & 3) == 0 &&
+      (ldd2 & 3) == 0 && (ld_add & 3) == 0 && al16(src) && al16(dst) && al16(dst2) && al16(add))
+    return launch_gather_rows_v4((const float*)src, lds, idx, add, add_idx, ld_add, n_out, cols, (float*)dst, ldd, dst2, dst2_dtype,
+                                 ldd2, STREAM);
   gather_rows_kernel<<<GRID1D(n_out * cols)>>>(src, src_dtype, lds, idx, add, add_idx, ld_add, n_out, cols, dst,
                                               dst_dtype, ldd, dst2, dst2_dtype, ldd2);
   NLV_CHECK_LAUNCH();
@@ -462,6 +486,7 @@ int nlv_colsum(const void* x, int x_dtype, int ld, long long rows, int cols, con
   NLV_CHECK_ARG(rows >= 0 && cols >= 0 && n_class >= 1, "colsum: bad sizes");
   if (rows == 0 || cols == 0) return NLV_OK;
   NLV_CHECK_ARG(x && out, "colsum: null pointer");
+  if ((cols & 7) == 0 && (ld & 7) == 0 && al16(x)) return launch_colsum_v8(x, x_dtype, ld, rows, cols, row_class, n_class, out, STREAM);
   int splits = (int)((rows + 255) / 256);
   if (splits > 1024) splits = 1024;
   dim3 grid(cdiv(cols, 32), splits), block(32, 8);

@@ -17,7 +17,7 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D, const float* __restrict__ bias,
                  const void* residual, int M, int N, int K, int lda, int ldb, int ldd, int ldr, int ab_dtype,
-                 int d_dtype, int r_dtype, int relu, int k_per_split) {
+                 int d_dtype, int r_dtype, int relu, int k_per_split, const void* gate, int ldg, int gate_dtype) {
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int tid = threadIdx.x;
@@ -73,6 +73,7 @@ gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D
       if (split) { atomicAdd(reinterpret_cast<float*>(D) + (size_t)gm * ldd + gn, v); continue; }
       if (bias != nullptr) v += bias[gn];
       if (relu) v = fmaxf(v, 0.f);
+      if (gate != nullptr && !(ld_as_float(gate, gate_dtype, (size_t)gm * ldg + gn) > 0.f)) v = 0.f;
       if (residual != nullptr) v += ld_as_float(residual, r_dtype, (size_t)gm * ldr + gn);
       st_from_float(D, d_dtype, (size_t)gm * ldd + gn, v);
     }
@@ -84,7 +85,7 @@ int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
   NLV_CHECK_ARG(grid.y <= 65535, "gemm(simt): m=%d too large", g.m);
   int k_per_split = g.k;
   const int tiles = (int)(grid.x * grid.y);
-  if (tiles < 2 * sm_count() && g.k >= 2048 && g.d_dtype == NLV_F32 && !g.bias && !g.residual && !g.relu) {
+  if (tiles < 2 * sm_count() && g.k >= 2048 && g.d_dtype == NLV_F32 && !g.bias && !g.residual && !g.relu && !g.gate) {
     int want = cdiv(4 * sm_count(), tiles);
     if (want > g.k / 256) want = g.k / 256;
     if (want > 1) {
@@ -95,7 +96,7 @@ int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
   }
 #define LAUNCH(AM, BM)                                                                                          \
   gemm_simt_kernel<AM, BM><<<grid, 256, 0, s>>>(g.a, g.b, g.d, g.bias, g.residual, g.m, g.n, g.k, g.lda, g.ldb, \
-                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu, k_per_split)
+                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu, k_per_split, g.gate, g.ldg, g.gate_dtype)
   if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) LAUNCH(false, false);
   else if (g.a_major == NLV_MAJOR_K) LAUNCH(false, true);
   else if (g.b_major == NLV_MAJOR_K) LAUNCH(true, false);

@@ -121,6 +121,8 @@ struct Params {
   int ldd, ldr;
   int d_dtype, r_dtype;
   int relu;
+  const void* gate;
+  int ldg, gate_dtype;
   int num_m_blocks, num_n_blocks;
   int k_splits, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to a zeroed fp32 D
 };
@@ -299,6 +301,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.gate != nullptr) {
+          const size_t goff = (size_t)row * p.ldg + n0 + c0;
+          if (p.gate_dtype == NLV_BF16) {
+            const __nv_bfloat16* gt = reinterpret_cast<const __nv_bfloat16*>(p.gate) + goff;
+            if (ncol == 32 && (p.ldg & 7) == 0 && ((uintptr_t)p.gate & 15) == 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                const uint4 t = *reinterpret_cast<const uint4*>(gt + j);
+                const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 g2 = __bfloat1622float2(h[q]);
+                  if (!(g2.x > 0.f)) f[j + 2 * q] = 0.f;
+                  if (!(g2.y > 0.f)) f[j + 2 * q + 1] = 0.f;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < ncol && !(__bfloat162float(gt[j]) > 0.f)) f[j] = 0.f;
+            }
+          } else {
+            const float* gt = reinterpret_cast<const float*>(p.gate) + goff;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol && !(gt[j] > 0.f)) f[j] = 0.f;
+          }
+        }
         if (p.residual != nullptr) {
           const size_t roff = (size_t)row * p.ldr + n0 + c0;
           if (p.r_dtype == NLV_BF16) {
@@ -420,6 +450,7 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   p.d = g.d; p.bias = g.bias; p.residual = g.residual;
   p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.ldr = g.ldr;
   p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
+  p.gate = g.gate; p.ldg = g.ldg; p.gate_dtype = g.gate_dtype;
   p.num_m_blocks = cdiv(g.m, BLOCK_M);
   p.num_n_blocks = cdiv(g.n, BLOCK_N);
   // split-K when the output has too few tiles to fill the GPU and the reduction is long (weight gradients of the
@@ -428,7 +459,7 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   const int tiles0 = p.num_m_blocks * p.num_n_blocks;
   p.k_splits = 1;
   p.kb_per_split = nkb;
-  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu) {
+  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu && g.gate == nullptr) {
     int want = sm_count() / tiles0;
     if (want > nkb / 8) want = nkb / 8;
     if (want > 1) {

@@ -93,30 +93,35 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ dy, const floa
 }
 
 // LayerNorm backward, parameter gradients: dw[c] += sum_r dy*xhat, db[c] += sum_r dy.
-// grid (ceil(cols/32), row_splits), block 32 x 8
+// Each thread owns 4 consecutive columns (float4); grid (ceil(cols/128), row_splits), block 32 x 8.
 __global__ void layernorm_bwd_param_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                            const float* __restrict__ mean, const float* __restrict__ rstd, long long rows,
                                            int cols, float* __restrict__ dw, float* __restrict__ db) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = (long long)blockIdx.y * per, r1 = min(rows, r0 + per);
-  float a = 0.f, b = 0.f;
-  if (c < cols)
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c < cols)   // cols % 4 == 0 is checked by the launcher
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      const float d = dy[(size_t)r * cols + c];
-      a += d * (x[(size_t)r * cols + c] - mean[r]) * rstd[r];
-      b += d;
+      const float4 d = *reinterpret_cast<const float4*>(dy + (size_t)r * cols + c);
+      const float4 xv = *reinterpret_cast<const float4*>(x + (size_t)r * cols + c);
+      const float m = mean[r], rs = rstd[r];
+      a[0] += d.x * (xv.x - m) * rs; a[1] += d.y * (xv.y - m) * rs; a[2] += d.z * (xv.z - m) * rs; a[3] += d.w * (xv.w - m) * rs;
+      b[0] += d.x; b[1] += d.y; b[2] += d.z; b[3] += d.w;
     }
-  __shared__ float red[2][8][33];
-  red[0][threadIdx.y][threadIdx.x] = a;
-  red[1][threadIdx.y][threadIdx.x] = b;
+  __shared__ float red[2][8][32 * 4 + 4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { red[0][threadIdx.y][threadIdx.x * 4 + q] = a[q]; red[1][threadIdx.y][threadIdx.x * 4 + q] = b[q]; }
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
-    float t1 = 0.f, t2 = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { t1 += red[0][j][threadIdx.x]; t2 += red[1][j][threadIdx.x]; }
-    atomicAdd(dw + c, t1);
-    atomicAdd(db + c, t2);
+    for (int q = 0; q < 4; ++q) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { t1 += red[0][j][threadIdx.x * 4 + q]; t2 += red[1][j][threadIdx.x * 4 + q]; }
+      atomicAdd(dw + c + q, t1);
+      atomicAdd(db + c + q, t2);
+    }
   }
 }
 
@@ -230,7 +235,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
                                     const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
                                     const int* __restrict__ seg, const float* __restrict__ mean,
                                     const float* __restrict__ var, const float* __restrict__ w, float eps,
-                                    const double* __restrict__ sums, int use_batch_stats, long long rows, int C,
+                                    const double* __restrict__ sums, int use_batch_stats, int gate_by_x, long long rows, int C,
                                     void* __restrict__ dx, int dxdt, int lddx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * C) return;
@@ -250,6 +255,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
   } else {
     o = w[c] * rs * d;
   }
+  if (gate_by_x && !(ld_as_float(x, xdt, (size_t)r * ldx + c) > 0.f)) o = 0.f;   // ReLU that precedes the BN
   st_from_float(dx, dxdt, (size_t)r * lddx + c, o);
 }
 
@@ -273,6 +279,19 @@ int bn_splits(const int* /*seg device*/, long long rows, int nseg) {
 }
 
 }  // namespace
+
+// 16-byte vectorised variants (norm_vec.cu), used when C % 8 == 0 and everything is 16-byte aligned
+int launch_bn_sums_fwd_v8(const void* x, int xdt, int ld, const int* seg, int nseg, long long rows, int C, double* sums, cudaStream_t s);
+int launch_bn_sums_bwd_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
+                          int nseg, const float* mean, const float* var, float eps, long long rows, int C, double* sums, cudaStream_t s);
+int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
+                       const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
+                       int ldy2, cudaStream_t s);
+int launch_bn_bwd_apply_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
+                           const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
+                           const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
+                           cudaStream_t s);
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace nlv
 
 using namespace nlv;
@@ -299,9 +318,10 @@ int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
   NLV_CHECK_ARG(dy && x && mean && rstd && w && dw && db && (dx || dx2), "layernorm_bwd: null pointer");
   layernorm_bwd_dx_kernel<<<cdiv(rows, 4), 128, 0, STREAM>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype);
   NLV_CHECK_LAUNCH();
-  int splits = (int)((rows + 127) / 128);
-  if (splits > 512) splits = 512;
-  dim3 grid(cdiv(cols, 32), splits), block(32, 8);
+  NLV_CHECK_ARG((cols & 3) == 0, "layernorm_bwd: cols=%d must be a multiple of 4", cols);
+  int splits = (int)((rows + 255) / 256);
+  if (splits > 1024) splits = 1024;
+  dim3 grid(cdiv(cols, 128), splits), block(32, 8);
   layernorm_bwd_param_kernel<<<grid, block, 0, STREAM>>>(dy, x, mean, rstd, rows, cols, dw, db);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
@@ -316,9 +336,14 @@ int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, l
   { int zrc = zero_fill(reinterpret_cast<float*>(sums_ws), 1, 4 * nseg * c, 4 * nseg * c, STREAM); if (zrc != NLV_OK) return zrc; }
   if (rows > 0) {
     NLV_CHECK_ARG(nseg <= 65535, "bn_stats: too many segments");
-    dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
-    bn_stats_kernel<<<grid, block, 0, STREAM>>>(x, x_dtype, ld, seg, c, sums_ws);
-    NLV_CHECK_LAUNCH();
+    if ((c & 7) == 0 && (ld & 7) == 0 && al16(x)) {
+      int rc = launch_bn_sums_fwd_v8(x, x_dtype, ld, seg, nseg, rows, c, sums_ws, STREAM);
+      if (rc != NLV_OK) return rc;
+    } else {
+      dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
+      bn_stats_kernel<<<grid, block, 0, STREAM>>>(x, x_dtype, ld, seg, c, sums_ws);
+      NLV_CHECK_LAUNCH();
+    }
   }
   bn_finalize_kernel<<<cdiv(c, 128), 128, 0, STREAM>>>(sums_ws, seg, nseg, c, momentum, mean, var, running_mean, running_var);
   NLV_CHECK_LAUNCH();
@@ -332,28 +357,43 @@ int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const 
   NLV_CHECK_ARG(rows >= 0 && c > 0, "bn_apply: bad sizes");
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(x && mean && var && w && b && (y || y2), "bn_apply: null pointer");
+  if ((c & 7) == 0 && (ldx & 7) == 0 && (ldy & 7) == 0 && (ldy2 & 7) == 0 && al16(x) && al16(y) && al16(y2) && al16(mean) && al16(var) &&
+      al16(w) && al16(b))
+    return launch_bn_apply_v8(x, x_dtype, ldx, row_seg, mean, var, w, b, eps, relu, rows, c, y, y_dtype, ldy, y2, y2_dtype, ldy2, STREAM);
   bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(x, x_dtype, ldx, row_seg, mean, var, w, b, eps, relu, rows, c, y,
                                                           y_dtype, ldy, y2, y2_dtype, ldy2);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 
-/* Backward.  yout (optional) = the ReLU'd forward output, masks dy.  dw/db accumulated.  sums_ws as in bn_stats. */
+/* Backward.  yout (optional) = the ReLU'd forward output, masks dy (Linear -> BN -> ReLU).  gate_by_x: zero dx where x <= 0
+ * (conv -> ReLU -> BN: x is the ReLU output, so this is the ReLU backward fused in).  dw/db accumulated.  sums_ws as in bn_stats. */
 int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
                const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
-               int use_batch_stats, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
+               int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
                float* db, void* stream) {
   NLV_CHECK_ARG(nseg >= 1 && c > 0 && rows >= 0, "bn_bwd: bad sizes");
   NLV_CHECK_ARG(dy && x && seg && mean && var && w && sums_ws && dx && dw && db, "bn_bwd: null pointer");
   { int zrc = zero_fill(reinterpret_cast<float*>(sums_ws), 1, 4 * nseg * c, 4 * nseg * c, STREAM); if (zrc != NLV_OK) return zrc; }
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(nseg <= 65535, "bn_bwd: too many segments");
-  dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
-  bn_bwd_stats_kernel<<<grid, block, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, mean, var, eps, c, sums_ws);
-  NLV_CHECK_LAUNCH();
-  bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean,
-                                                              var, w, eps, sums_ws, use_batch_stats, rows, c, dx, dx_dtype, lddx);
-  NLV_CHECK_LAUNCH();
+  const bool vec = (c & 7) == 0 && (lddy & 7) == 0 && (ldx & 7) == 0 && (ldy & 7) == 0 && (lddx & 7) == 0 && al16(dy) && al16(x) &&
+                   al16(yout) && al16(dx) && al16(mean) && al16(var) && al16(w);
+  if (vec) {
+    int rc = launch_bn_sums_bwd_v8(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, nseg, mean, var, eps, rows, c, sums_ws, STREAM);
+    if (rc != NLV_OK) return rc;
+    rc = launch_bn_bwd_apply_v8(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean, var, w, eps, sums_ws, use_batch_stats,
+                                gate_by_x, rows, c, dx, dx_dtype, lddx, STREAM);
+    if (rc != NLV_OK) return rc;
+  } else {
+    dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
+    bn_bwd_stats_kernel<<<grid, block, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, mean, var, eps, c, sums_ws);
+    NLV_CHECK_LAUNCH();
+    bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean,
+                                                                var, w, eps, sums_ws, use_batch_stats, gate_by_x, rows, c, dx, dx_dtype,
+                                                                lddx);
+    NLV_CHECK_LAUNCH();
+  }
   bn_bwd_param_kernel<<<cdiv(c, 128), 128, 0, STREAM>>>(sums_ws, nseg, c, dw, db);
   NLV_CHECK_LAUNCH();
   return NLV_OK;

@@ -74,7 +74,7 @@ class Kernels:
 
     # ---- GEMM --------------------------------------------------------------------------------
     def mm(self, a, b, *, a_major=K_, b_major=K_, out=None, out_dtype=None, bias=None, residual=None, relu=False,
-           exact=False):
+           exact=False, gate=None):
         m = a.shape[0] if a_major == K_ else a.shape[1]
         n = b.shape[0] if b_major == K_ else b.shape[1]
         if out is None:
@@ -87,13 +87,13 @@ class Kernels:
                 a = ops.convert(a, F32)
             if b.dtype != F32:
                 b = ops.convert(b, F32)
-            return ops.gemm(a, b, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu)
+            return ops.gemm(a, b, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu, gate=gate)
         if self.precision == "bf16x3":
             a3 = ops.split3(a, 1 if a_major == K_ else 0, 0)
             b3 = ops.split3(b, 1 if b_major == K_ else 0, 1)
-            return ops.gemm(a3, b3, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu)
+            return ops.gemm(a3, b3, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu, gate=gate)
         a, b = self._tma_ready(a), self._tma_ready(b)
-        return ops.gemm(a, b, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu)
+        return ops.gemm(a, b, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu, gate=gate)
 
     def _tma_ready(self, x):
         if x.dtype != BF16:
@@ -147,8 +147,7 @@ def encoder_bwd(k: Kernels, P: dict, pre: str, attn: str, c: dict, dx2, work, n_
     if dy2op is None:
         dy2op = dy2
     grads[pre + "linear2.weight"], grads[pre + "linear2.bias"] = _lin_grads(k, dy2op, c["h"], dy2)
-    dh = k.mm(dy2op, w("linear2.weight"), b_major=MN_, out_dtype=k.AD)
-    dh = ops.relu_mask(dh, c["h"], k.AD)
+    dh = k.mm(dy2op, w("linear2.weight"), b_major=MN_, out_dtype=k.AD, gate=c["h"])       # ReLU backward fused
     grads[pre + "linear1.weight"], grads[pre + "linear1.bias"] = _lin_grads(k, dh, c["x1op"], dh)
     dx1 = k.mm(dh, w("linear1.weight"), b_major=MN_, residual=dy2)
     dy1, dy1op, dw, db = ops.layernorm_bwd(dx1, c["y1"], c["m1"], c["r1"], P[pre + "norm1.weight"], dx2_dtype=opd)
@@ -197,8 +196,7 @@ def decoder_bwd(k: Kernels, P: dict, pre: str, c: dict, dout, slot, work, n_work
     w = lambda n: k.weight(pre + n, P[pre + n])
     doutop = k.opnd(dout)
     grads[pre + "linear2.weight"], grads[pre + "linear2.bias"] = _lin_grads(k, doutop, c["h"], dout)
-    dh = k.mm(doutop, w("linear2.weight"), b_major=MN_, out_dtype=k.AD)
-    dh = ops.relu_mask(dh, c["h"], k.AD)
+    dh = k.mm(doutop, w("linear2.weight"), b_major=MN_, out_dtype=k.AD, gate=c["h"])      # ReLU backward fused
     grads[pre + "linear1.weight"], grads[pre + "linear1.bias"] = _lin_grads(k, dh, c["top"], dh)
     dt = k.mm(dh, w("linear1.weight"), b_major=MN_, residual=dout)
     dy, dyop, dw, db = ops.layernorm_bwd(dt, c["y"], c["m3"], c["r3"], P[pre + "norm3.weight"],
@@ -282,6 +280,10 @@ def object_classifier_bwd(k: Kernels, P: dict, plan: Plan, c: dict, dlogits, gra
     grads[pre + "pos_embed.0.weight"], grads[pre + "pos_embed.0.bias"] = dw, db
 
 
+def _perm_c4(w):      # conv.4.weight [256,128,3,3] -> [256, (ky,kx,c)] to match the channels-innermost im2col
+    return w.permute(0, 2, 3, 1).reshape(256, 1152)
+
+
 def _perm_vr(w):      # vr_fc.weight [512, c*49 + hw] -> [512, hw*256 + c] (rows of the NHWC union tensor)
     return w.view(512, 256, 49).permute(0, 2, 1).reshape(512, 12544)
 
@@ -305,7 +307,7 @@ def pair_tokens_fwd(k: Kernels, P: dict, plan: Plan, feat_op, union_feat, spatia
     b1, mean2, var2 = _bn_fwd(c1, plan.seg196, plan.row196, plan.nv, P, "conv.2", 0.01, training, False, out_dtype=k.AD)
     p1, arg = ops.maxpool_fwd(b1, R, 128, k.AD)
     col2 = ops.im2col_3x3(p1, R, 7, 7, 128, k.AD)                                    # [R*49, 1152]
-    w_c4 = k.weight("conv.4.weight", P["conv.4.weight"], lambda w: w.reshape(256, 1152))
+    w_c4 = k.weight("conv.4.weight.taps", P["conv.4.weight"], _perm_c4)
     c2 = k.mm(col2, w_c4, bias=P["conv.4.bias"], relu=True, out_dtype=k.AD)
     b2, mean6, var6 = _bn_fwd(c2, plan.seg49, plan.row49, plan.nv, P, "conv.6", 0.01, training, False, out_dtype=k.AD)
     w_u = k.weight("union_func1.weight", P["union_func1.weight"], lambda w: w.reshape(256, 2048))
@@ -339,19 +341,17 @@ def pair_tokens_bwd(k: Kernels, P: dict, plan: Plan, c: dict, drel, grads: dict)
     grads["union_func1.weight"] = k.mm(dvr_op, c["uf_op"], a_major=MN_, b_major=MN_).view(256, 2048, 1, 1)
     grads["union_func1.bias"] = ops.colsum(dvr_in).reshape(-1)
     dc2, dw, db = ops.bn_bwd(dvr_in, c["c2"], None, plan.seg49, plan.row49, plan.nv, c["mean6"], c["var6"],
-                             P["conv.6.weight"], tr)
+                             P["conv.6.weight"], tr, dx_dtype=k.AD, gate_by_x=True)     # BN backward + ReLU backward fused
     grads["conv.6.weight"], grads["conv.6.bias"] = dw, db
-    dc2 = ops.relu_mask(dc2, c["c2"], k.AD)
-    grads["conv.4.weight"] = k.mm(dc2, c["col2"], a_major=MN_, b_major=MN_).view(256, 128, 3, 3)
+    grads["conv.4.weight"] = k.mm(dc2, c["col2"], a_major=MN_, b_major=MN_).view(256, 3, 3, 128).permute(0, 3, 1, 2).contiguous()
     grads["conv.4.bias"] = ops.colsum(dc2).reshape(-1)
-    w_c4 = k.weight("conv.4.weight", P["conv.4.weight"], lambda w: w.reshape(256, 1152))
+    w_c4 = k.weight("conv.4.weight.taps", P["conv.4.weight"], _perm_c4)
     dcol2 = k.mm(dc2, w_c4, b_major=MN_, out_dtype=k.AD)
     dp1 = ops.col2im_3x3(dcol2, R, 7, 7, 128)
     db1 = ops.maxpool_bwd(dp1, c["arg"], R, 128)
     dc1, dw, db = ops.bn_bwd(db1, c["c1"], None, plan.seg196, plan.row196, plan.nv, c["mean2"], c["var2"],
-                             P["conv.2.weight"], tr)
+                             P["conv.2.weight"], tr, dx_dtype=k.AD, gate_by_x=True)
     grads["conv.2.weight"], grads["conv.2.bias"] = dw, db
-    dc1 = ops.relu_mask(dc1, c["c1"], k.AD)
     grads["conv.0.weight"] = k.mm(dc1, c["col1"], a_major=MN_, b_major=MN_)[:, :98].reshape(128, 2, 7, 7).contiguous()
     grads["conv.0.bias"] = ops.colsum(dc1).reshape(-1)
     dwso = k.mm(k.opnd(dfo), c["feat_op"], a_major=MN_, b_major=MN_)

@@ -33,7 +33,7 @@ def _need_cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_major: int = MAJOR_K, b_major: int = MAJOR_K,
          bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, relu: bool = False,
-         force_simt: bool = False) -> torch.Tensor:
+         force_simt: bool = False, gate: torch.Tensor | None = None) -> torch.Tensor:
     """out[m,n] = act(sum_k A(m,k) B(n,k) + bias[n]) + residual[m,n].
 
     a: [m,k] (K-major) or [k,m] (MN-major); b: [n,k] or [k,n]; rows may be strided (stride(1) == 1)."""
@@ -61,6 +61,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_major: int = 
     g.d_dtype = _dt(out)
     g.r_dtype = _dt(residual) if residual is not None else NLV_F32
     g.relu = 1 if relu else 0
+    if gate is not None:
+        assert tuple(gate.shape) == (m, n) and gate.stride(1) == 1
+        g.gate, g.ldg, g.gate_dtype = gate.data_ptr(), gate.stride(0), _dt(gate)
+    else:
+        g.gate, g.ldg, g.gate_dtype = None, 0, 0
     if PROFILE is None:
         _C.check(_C.lib().nlv_gemm(ctypes.byref(g), _stream()), "gemm")
         return out
@@ -301,7 +306,7 @@ def bn_apply(x, row_seg, mean, var, w, b, relu, out=None, out_dtype=None, out2_d
     return out, out2
 
 
-def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dtype=torch.float32, eps=1e-5):
+def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dtype=torch.float32, eps=1e-5, gate_by_x=False):
     rows, c = x.shape
     ws = torch.empty(nseg * 2 * c, device=x.device, dtype=torch.float64)
     dx = torch.empty(rows, c, device=x.device, dtype=dx_dtype)
@@ -309,7 +314,8 @@ def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dt
     db = torch.zeros(c, device=x.device, dtype=torch.float32)
     _call("nlv_bn_bwd", _ptr(dy), dy.stride(0), _ptr(x), _dt(x), x.stride(0), _ptr(yout),
           _dt(yout) if yout is not None else 0, yout.stride(0) if yout is not None else 0, _ptr(seg), _ptr(row_seg), nseg,
-          _ptr(mean), _ptr(var), _ptr(w), _F(eps), 1 if use_batch_stats else 0, _LL(rows), c, _ptr(ws), _ptr(dx), _dt(dx), c,
+          _ptr(mean), _ptr(var), _ptr(w), _F(eps), 1 if use_batch_stats else 0, 1 if gate_by_x else 0, _LL(rows), c, _ptr(ws), _ptr(dx),
+          _dt(dx), c,
           _ptr(dw), _ptr(db))
     return dx, dw, db
 

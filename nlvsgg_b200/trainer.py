@@ -7,6 +7,7 @@ from typing import Dict, List
 
 import torch
 
+from . import dist as D
 from . import engine as E
 from . import model as M
 from . import ops
@@ -98,7 +99,6 @@ class Trainer:
                                   "object_classifier.obj_embed.weight", "object_classifier.pos_embed.1.weight",
                                   "object_classifier.decoder_lin.3.weight"):
                 mir[n] = bview(n, tuple(t.shape))
-        mir["conv.4.weight"] = bview("conv.4.weight", (256, 1152))
         mir["union_func1.weight"] = bview("union_func1.weight", (256, 2048))
 
     def forward_backward(self, batch: M.Batch, plan=None):
@@ -117,14 +117,7 @@ class Trainer:
         return loss, out
 
     def optimizer_step(self):
-        if torch.distributed.is_available() and torch.distributed.is_initialized() and torch.distributed.get_world_size() > 1:
-            ws = torch.distributed.get_world_size()
-            chunk = 32 * 1024 * 1024  # 128 MB buckets over NVLink
-            works = [torch.distributed.all_reduce(self.flat_g[i:i + chunk], async_op=True)
-                     for i in range(0, self.n_params, chunk)]
-            for w in works:
-                w.wait()
-            self.flat_g.mul_(1.0 / ws)
+        D.allreduce_mean_(self.flat_g)      # no-op on one rank
         self.step_count += 1
         self.total_sq.zero_()
         ops.sumsq(self.flat_g, self.total_sq)
