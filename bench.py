@@ -125,7 +125,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=dev)
+        import datetime
+        torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     from nlvsgg_b200 import _C, model as M, ops, shapes, synth
     from nlvsgg_b200.trainer import Trainer
     _C.lib()
@@ -199,43 +200,50 @@ def main():
     sampler.join(timeout=2)
 
     # ---- roofline of the dominant kernel (the tcgen05 GEMM): events around every launch of one step ----
+    # every rank runs this extra step (it contains the gradient allreduce); only rank 0 instruments it
     roof = None
-    if rank == 0:
-        recs = []
-        orig = ops.gemm
+    recs = []
+    orig = ops.gemm
 
-        def timed_gemm(a_, b_, out, **kw):
-            if a_.dtype == torch.bfloat16 and not kw.get("force_simt"):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record()
-                r = orig(a_, b_, out, **kw)
-                e.record()
-                m_, n_ = out.shape
-                k_ = a_.shape[1] if kw.get("a_major", 0) == 0 else a_.shape[0]
-                recs.append((s, e, 2.0 * m_ * n_ * k_))
-                return r
-            return orig(a_, b_, out, **kw)
+    def timed_gemm(a_, b_, out, **kw):
+        if a_.dtype == torch.bfloat16 and not kw.get("force_simt"):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = orig(a_, b_, out, **kw)
+            e.record()
+            m_, n_ = out.shape
+            k_ = a_.shape[1] if kw.get("a_major", 0) == 0 else a_.shape[0]
+            recs.append((s, e, 2.0 * m_ * n_ * k_))
+            return r
+        return orig(a_, b_, out, **kw)
+    if rank == 0:
         ops.gemm = timed_gemm
-        step_s, step_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        step_s.record()
-        resident_step()
-        step_e.record()
-        torch.cuda.synchronize()
-        ops.gemm = orig
-        if recs:
-            tsum = sum(s.elapsed_time(e) for s, e, _ in recs) / 1e3
-            fsum = sum(f for _, _, f in recs)
-            peaks = {}
-            try:
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except Exception:
-                pass
-            peak = peaks.get("bf16_tflops_sustained") or 1400.0
-            ach = fsum / tsum / 1e12
-            roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": ach / peak, "traffic": None, "launches_per_step": len(recs), "algorithmic_flop_per_step": fsum,
-                    "kernel_share_of_step": tsum * 1e3 / step_s.elapsed_time(step_e),
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback"}
+    step_s, step_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_s.record()
+    resident_step()
+    step_e.record()
+    torch.cuda.synchronize()
+    ops.gemm = orig
+    if rank == 0 and recs:
+        tsum = sum(s.elapsed_time(e) for s, e, _ in recs) / 1e3
+        fsum = sum(f for _, _, f in recs)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained") or 1400.0
+        ach = fsum / tsum / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "gemm_traffic.json"))).get("dram_bytes_per_launch_avg")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "traffic": traffic, "launches_per_step": len(recs), "algorithmic_flop_per_step": fsum,
+                "algorithmic_flop_per_launch_avg": fsum / len(recs), "avg_launch_ms": tsum * 1e3 / len(recs),
+                "kernel_share_of_step": tsum * 1e3 / step_s.elapsed_time(step_e),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400 (B200_PROFILING.md sustained)"}
 
     if world > 1:
         torch.distributed.barrier()
