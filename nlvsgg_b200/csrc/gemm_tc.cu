@@ -15,6 +15,7 @@
 // Replaces (through cuBLAS) nn.Linear / MHA projections / 1x1 conv of lib/sttran.py:336-348,370-372 and
 // lib/transformer.py:9-13,38-42.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -75,6 +76,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tma
       ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// multicast variant: the box lands at the same shared-memory offset in every CTA of `mask`, and completes bytes on the
+// mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(dst), "l"(tmap), "r"(bar), "h"(mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -130,7 +151,10 @@ struct Params {
 // ---------------------------------------------------------------------------------------------
 // Kernel
 // ---------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool A_MN, bool B_MN>
+// CM = CTAs per cluster along M (1 or 2).  With CM == 2 the two CTAs compute vertically adjacent 128 x BLOCK_N tiles and
+// share the B tile: each loads half of it and multicasts it into both shared memories, cutting the L2->SM operand
+// traffic per tile from (128 + BLOCK_N) to (128 + BLOCK_N/2) rows per k-block.
+template <int BLOCK_N, bool A_MN, bool B_MN, int CM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
   using C = Cfg<BLOCK_N>;
@@ -155,7 +179,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), CM);   // one tcgen05.commit arrival per CTA that received the stage's data
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 1);
@@ -171,24 +195,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();   // peers' barriers are initialised before any remote arrival / multicast
   tc_fence_after();
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
 
   const int num_k_blocks = (p.k + BLOCK_K - 1) / BLOCK_K;
-  const int num_work = p.num_m_blocks * p.num_n_blocks * p.k_splits;
+  const int cta_rank = CM > 1 ? (int)cluster_ctarank() : 0;
+  const int num_mp = (p.num_m_blocks + CM - 1) / CM;          // groups of CM vertically adjacent tiles
+  const int num_work = num_mp * p.num_n_blocks * p.k_splits;
+  const int work0 = blockIdx.x / CM, work_stride = gridDim.x / CM;
 
   if (warp == 0) {
     if (lane == 0) {
       // ===================== TMA producer =====================
       int stage = 0;
       uint32_t phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (int work = work0; work < num_work; work += work_stride) {
         const int tile = work / p.k_splits;
         const int kb0 = (work % p.k_splits) * p.kb_per_split;
         const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
-        const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
-        const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
+        const int m0 = ((tile % num_mp) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+        const int n0 = (tile / num_mp) * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
@@ -201,11 +229,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           } else {
             tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
           }
-          if constexpr (B_MN) {
+          if constexpr (CM == 1) {
+            if constexpr (B_MN) {
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(sb + i * ATOM_BYTES, &tmap_b, full_bar(stage), n0 + 64 * i, k0);
+              for (int i = 0; i < BLOCK_N / 64; ++i) tma_load_2d(sb + i * ATOM_BYTES, &tmap_b, full_bar(stage), n0 + 64 * i, k0);
+            } else {
+              tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+            }
           } else {
-            tma_load_2d(sb, &tmap_b, full_bar(stage), k0, n0);
+            // this CTA fetches its half of the shared B tile and multicasts it to both CTAs of the pair
+            constexpr uint16_t kMask = (1u << CM) - 1;
+            if constexpr (B_MN) {
+              constexpr int kPer = BLOCK_N / 64 / CM;
+#pragma unroll
+              for (int i = 0; i < kPer; ++i) {
+                const int a = cta_rank * kPer + i;
+                tma_load_2d_mc(sb + a * ATOM_BYTES, &tmap_b, full_bar(stage), n0 + 64 * a, k0, kMask);
+              }
+            } else {
+              constexpr int kRows = BLOCK_N / CM;
+              tma_load_2d_mc(sb + cta_rank * kRows * (BLOCK_K * 2), &tmap_b, full_bar(stage), k0, n0 + cta_rank * kRows, kMask);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -224,7 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++iter) {
+      for (int work = work0; work < num_work; work += work_stride, ++iter) {
         const int kb0 = (work % p.k_splits) * p.kb_per_split;
         const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
         const int acc = iter & 1;
@@ -243,7 +287,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const uint64_t bdesc = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
             tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          tc_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire — in BOTH CTAs of a pair, since each also wrote the peer's copy
+          if constexpr (CM == 1) tc_commit(empty_bar(stage));
+          else tc_commit_mc(empty_bar(stage), (uint16_t)((1u << CM) - 1));
           if (kb == kb1 - 1) tc_commit(tmem_full_bar(acc));
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
@@ -257,10 +303,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool vec_ok = d_bf16 ? ((p.ldd & 7) == 0 && ((uintptr_t)p.d & 15) == 0)
                                : ((p.ldd & 3) == 0 && ((uintptr_t)p.d & 15) == 0);
     const bool split = p.k_splits > 1;
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x, ++iter) {
+    for (int work = work0; work < num_work; work += work_stride, ++iter) {
       const int tile = work / p.k_splits;
-      const int m0 = (tile % p.num_m_blocks) * BLOCK_M;
-      const int n0 = (tile / p.num_m_blocks) * BLOCK_N;
+      const int m0 = ((tile % num_mp) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+      const int n0 = (tile / num_mp) * BLOCK_N;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_phase);
@@ -388,6 +434,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CM > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
@@ -435,7 +482,7 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, 
   return NLV_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int CM>
 int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   using C = Cfg<BLOCK_N>;
   CUtensorMap ta, tb;
@@ -444,7 +491,7 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   else      rc = make_tmap(&ta, g.a, g.m, g.k, g.lda, BLOCK_K, BLOCK_M);
   if (rc != NLV_OK) return rc;
   if (B_MN) rc = make_tmap(&tb, g.b, g.k, g.n, g.ldb, 64, BLOCK_K);
-  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N);
+  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N / CM);
   if (rc != NLV_OK) return rc;
   Params p;
   p.d = g.d; p.bias = g.bias; p.residual = g.residual;
@@ -468,25 +515,40 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
       { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, stream); if (zrc != NLV_OK) return zrc; }
     }
   }
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CM>;
   static bool attr_set = false;
   if (!attr_set) {
     NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = p.num_m_blocks * p.num_n_blocks * p.k_splits;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  const int groups = cdiv(p.num_m_blocks, CM) * p.num_n_blocks * p.k_splits;
+  const int max_groups = sm_count() / CM;
+  const int grid = (groups < max_groups ? groups : max_groups) * CM;
+  if (CM == 1) {
+    kern<<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(ta, tb, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CM; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NLV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, p));
+  }
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CM>
 int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
-  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false>(g, s);
-  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_MN) return launch<BLOCK_N, false, true>(g, s);
-  if (g.a_major == NLV_MAJOR_MN && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, true, false>(g, s);
-  return launch<BLOCK_N, true, true>(g, s);
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false, CM>(g, s);
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_MN) return launch<BLOCK_N, false, true, CM>(g, s);
+  if (g.a_major == NLV_MAJOR_MN && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, true, false, CM>(g, s);
+  return launch<BLOCK_N, true, true, CM>(g, s);
 }
 
 }  // namespace
@@ -494,8 +556,11 @@ int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
 int gemm_tc(const nlv_gemm_args& g, cudaStream_t stream) {
   NLV_CHECK_ARG(((uintptr_t)g.a & 15) == 0 && ((uintptr_t)g.b & 15) == 0, "gemm(bf16): a and b must be 16-byte aligned");
   NLV_CHECK_ARG((g.lda & 7) == 0 && (g.ldb & 7) == 0, "gemm(bf16): lda=%d and ldb=%d must be multiples of 8", g.lda, g.ldb);
-  if (g.n > 128) return dispatch_major<256>(g, stream);
-  return dispatch_major<128>(g, stream);
+  // pairs of CTAs sharing a multicast B tile whenever there are at least two row tiles (NLV_GEMM_CLUSTER=1 disables)
+  static const int cluster_ok = [] { const char* e = getenv("NLV_GEMM_CLUSTER"); return e == nullptr || atoi(e) != 1; }();
+  const bool pair = cluster_ok && g.m > BLOCK_M;
+  if (g.n > 128) return pair ? dispatch_major<256, 2>(g, stream) : dispatch_major<256, 1>(g, stream);
+  return pair ? dispatch_major<128, 2>(g, stream) : dispatch_major<128, 1>(g, stream);
 }
 
 }  // namespace nlv
