@@ -83,6 +83,7 @@ attn_fwd_kernel(AttnArgs a, TO* __restrict__ o, int ldo, float* __restrict__ lse
 
   stage_t<TI>(Q, a.ldq, seg0 + q0, nq, col0, hd, a.scale, Qs);
   __syncthreads();
+  if (warp * 4 >= nq) return;   // this warp's four rows are all beyond the segment (no block-wide sync follows)
   float m[4], l[4], acc[4][2 * NW];
 #pragma unroll
   for (int qi = 0; qi < 4; ++qi) {
@@ -92,12 +93,15 @@ attn_fwd_kernel(AttnArgs a, TO* __restrict__ o, int ldo, float* __restrict__ lse
   }
   for (int k0 = 0; k0 < L; k0 += KT) {
     const int nk = min(KT, L - k0);
-    // scores: lane = key; each lane walks its own K row
+    // scores: G = 1, 2 or 4 lanes per key (short segments would otherwise leave most lanes idle); each lane walks every
+    // G-th word of its key's row, partial dot products are combined with log2(G) shuffles
+    const int lg = nk <= 8 ? 2 : (nk <= 16 ? 1 : 0);
+    const int G = 1 << lg, key = lane >> lg, part = lane & (G - 1);
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane < nk) {
-      const TI* kr = K + (size_t)(seg0 + k0 + lane) * a.ldk + col0;
+    if (key < nk) {
+      const TI* kr = K + (size_t)(seg0 + k0 + key) * a.ldk + col0;
 #pragma unroll 4
-      for (int wd = 0; wd < nwords; ++wd) {
+      for (int wd = part; wd < nwords; wd += G) {
         const float2 kv = ld2<TI>(kr, wd);
         const float4 qa = *reinterpret_cast<const float4*>(Qs + (2 * wd) * QB + warp * 4);
         const float4 qb = *reinterpret_cast<const float4*>(Qs + (2 * wd + 1) * QB + warp * 4);
@@ -105,20 +109,25 @@ attn_fwd_kernel(AttnArgs a, TO* __restrict__ o, int ldo, float* __restrict__ lse
         s[0] = fmaf(qb.x, kv.y, s[0]); s[1] = fmaf(qb.y, kv.y, s[1]); s[2] = fmaf(qb.z, kv.y, s[2]); s[3] = fmaf(qb.w, kv.y, s[3]);
       }
     }
+    for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) s[qi] += __shfl_xor_sync(0xffffffffu, s[qi], o);
+    }
+    const bool valid = key < nk;
     float p[4];
 #pragma unroll
     for (int qi = 0; qi < 4; ++qi) {
-      const float sv = lane < nk ? s[qi] : -INFINITY;
+      const float sv = valid ? s[qi] : -INFINITY;
       const float mn = fmaxf(m[qi], warp_max(sv));
       const float corr = __expf(m[qi] - mn);  // m = -inf on the first tile -> 0
-      p[qi] = lane < nk ? __expf(sv - mn) : 0.f;
-      l[qi] = l[qi] * corr + warp_sum(p[qi]);
+      p[qi] = valid ? __expf(sv - mn) : 0.f;
+      l[qi] = l[qi] * corr + warp_sum(part == 0 ? p[qi] : 0.f);
       m[qi] = mn;
 #pragma unroll
       for (int i = 0; i < 2 * NW; ++i) acc[qi][i] *= corr;
     }
     __syncwarp();
-    *reinterpret_cast<float4*>(Ps + lane * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
+    if (valid && part == 0) *reinterpret_cast<float4*>(Ps + key * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
     __syncwarp();
     // PV: lane owns words lane + 32*i of the head; V rows stream from global, one line per warp
     for (int j = 0; j < nk; ++j) {
@@ -196,6 +205,7 @@ attn_bwd_dq_kernel(AttnArgs a, const TI* __restrict__ o, int ldo, const TG* __re
     if (lane == 0 && qr < nq) delta[(seg0 + q0 + qr) * a.heads + h] = dl[qi];
   }
   __syncthreads();
+  if (warp * 4 >= nq) return;
   float acc[4][2 * NW];
 #pragma unroll
   for (int qi = 0; qi < 4; ++qi)
@@ -203,12 +213,14 @@ attn_bwd_dq_kernel(AttnArgs a, const TI* __restrict__ o, int ldo, const TG* __re
     for (int i = 0; i < 2 * NW; ++i) acc[qi][i] = 0.f;
   for (int k0 = 0; k0 < L; k0 += KT) {
     const int nk = min(KT, L - k0);
+    const int lg = nk <= 8 ? 2 : (nk <= 16 ? 1 : 0);
+    const int G = 1 << lg, key = lane >> lg, part = lane & (G - 1);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-    if (lane < nk) {
-      const TI* kr = K + (size_t)(seg0 + k0 + lane) * a.ldk + col0;
-      const TI* vr = V + (size_t)(seg0 + k0 + lane) * a.ldv + col0;
+    if (key < nk) {
+      const TI* kr = K + (size_t)(seg0 + k0 + key) * a.ldk + col0;
+      const TI* vr = V + (size_t)(seg0 + k0 + key) * a.ldv + col0;
 #pragma unroll 2
-      for (int wd = 0; wd < nwords; ++wd) {
+      for (int wd = part; wd < nwords; wd += G) {
         const float2 kv = ld2<TI>(kr, wd), vv = ld2<TI>(vr, wd);
         const float4 qa = *reinterpret_cast<const float4*>(Qs + (2 * wd) * QB + warp * 4);
         const float4 qb = *reinterpret_cast<const float4*>(Qs + (2 * wd + 1) * QB + warp * 4);
@@ -220,14 +232,21 @@ attn_bwd_dq_kernel(AttnArgs a, const TI* __restrict__ o, int ldo, const TG* __re
         dp[0] = fmaf(gb.x, vv.y, dp[0]); dp[1] = fmaf(gb.y, vv.y, dp[1]); dp[2] = fmaf(gb.z, vv.y, dp[2]); dp[3] = fmaf(gb.w, vv.y, dp[3]);
       }
     }
+    for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+      for (int qi = 0; qi < 4; ++qi) {
+        s[qi] += __shfl_xor_sync(0xffffffffu, s[qi], o);
+        dp[qi] += __shfl_xor_sync(0xffffffffu, dp[qi], o);
+      }
+    }
     float ds[4];
 #pragma unroll
     for (int qi = 0; qi < 4; ++qi) {
-      const float p = lane < nk ? __expf(s[qi] - ls[qi]) : 0.f;
+      const float p = key < nk ? __expf(s[qi] - ls[qi]) : 0.f;
       ds[qi] = p * (dp[qi] - dl[qi]);
     }
     __syncwarp();
-    *reinterpret_cast<float4*>(Ss + lane * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    if (key < nk && part == 0) *reinterpret_cast<float4*>(Ss + key * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
     __syncwarp();
     for (int j = 0; j < nk; ++j) {
       const float4 s4 = *reinterpret_cast<const float4*>(Ss + j * QB + warp * 4);
@@ -284,6 +303,7 @@ attn_bwd_dkv_kernel(AttnArgs a, const TG* __restrict__ dout, int lddo, const flo
   stage_t<TI>(K, a.ldk, seg0 + k0, nkeys, col0, hd, 1.f, Kt);
   stage_t<TI>(V, a.ldv, seg0 + k0, nkeys, col0, hd, 1.f, Vt);
   __syncthreads();
+  if (warp * 4 >= nkeys) return;
   float accK[4][2 * NW], accV[4][2 * NW];
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk)
@@ -292,16 +312,18 @@ attn_bwd_dkv_kernel(AttnArgs a, const TG* __restrict__ dout, int lddo, const flo
   for (int q0 = 0; q0 < L; q0 += KT) {
     const int nq = min(KT, L - q0);
     // lane = query of the tile; 4 keys of this warp
+    const int lg = nq <= 8 ? 2 : (nq <= 16 ? 1 : 0);
+    const int G = 1 << lg, qrow = lane >> lg, part = lane & (G - 1);
     float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
     float lq = 0.f, dq_ = 0.f;
-    if (lane < nq) {
-      const long long row = seg0 + q0 + lane;
+    if (qrow < nq) {
+      const long long row = seg0 + q0 + qrow;
       const TI* qr = Q + (size_t)row * a.ldq + col0;
       const TG* gr = dout + (size_t)row * lddo + col0;
       lq = lse[row * a.heads + h];
       dq_ = delta[row * a.heads + h];
 #pragma unroll 2
-      for (int wd = 0; wd < nwords; ++wd) {
+      for (int wd = part; wd < nwords; wd += G) {
         const float2 qv = ld2<TI>(qr, wd), gv = ld2<TG>(gr, wd);
         const float4 ka = *reinterpret_cast<const float4*>(Kt + (2 * wd) * QB + warp * 4);
         const float4 kb = *reinterpret_cast<const float4*>(Kt + (2 * wd + 1) * QB + warp * 4);
@@ -313,16 +335,25 @@ attn_bwd_dkv_kernel(AttnArgs a, const TG* __restrict__ dout, int lddo, const flo
         dp[0] = fmaf(vb.x, gv.y, dp[0]); dp[1] = fmaf(vb.y, gv.y, dp[1]); dp[2] = fmaf(vb.z, gv.y, dp[2]); dp[3] = fmaf(vb.w, gv.y, dp[3]);
       }
     }
+    for (int o = 1; o < G; o <<= 1) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        s[kk] += __shfl_xor_sync(0xffffffffu, s[kk], o);
+        dp[kk] += __shfl_xor_sync(0xffffffffu, dp[kk], o);
+      }
+    }
     float p[4], ds[4];
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const bool ok = lane < nq && (warp * 4 + kk) < nkeys;
+      const bool ok = qrow < nq && (warp * 4 + kk) < nkeys;
       p[kk] = ok ? __expf(s[kk] * a.scale - lq) : 0.f;
       ds[kk] = p[kk] * (dp[kk] - dq_);
     }
     __syncwarp();
-    *reinterpret_cast<float4*>(Ps + lane * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
-    *reinterpret_cast<float4*>(Ss + lane * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    if (qrow < nq && part == 0) {
+      *reinterpret_cast<float4*>(Ps + qrow * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
+      *reinterpret_cast<float4*>(Ss + qrow * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    }
     __syncwarp();
     for (int j = 0; j < nq; ++j) {
       const float4 p4 = *reinterpret_cast<const float4*>(Ps + j * QB + warp * 4);

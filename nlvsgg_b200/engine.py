@@ -112,11 +112,19 @@ from .plan import Plan  # noqa: E402,F401  (host-side descriptors live in plan.p
 # ================================================================================================
 # transformer layers
 # ================================================================================================
-def _lin_grads(k: Kernels, dy_op, x_op, dy_for_bias):
-    """dW = dY^T X (both operands MN-major), db = column sums."""
-    dw = k.mm(dy_op, x_op, a_major=MN_, b_major=MN_)
-    db = ops.colsum(dy_for_bias).reshape(-1)
-    return dw, db
+def _lin_grads(k: Kernels, dy_op, x_op, dy_for_bias, grads, wname, bname):
+    """dW = dY^T X (both operands MN-major), db = column sums.  When `grads` exposes flat-buffer views (trainer.GradSink)
+    the GEMM and the column sum write straight into them; otherwise fresh tensors are stored in the mapping."""
+    views = getattr(grads, "views", None)
+    if views is not None and wname in views and views[wname].dim() == 2:
+        k.mm(dy_op, x_op, a_major=MN_, b_major=MN_, out=views[wname])
+        bv = views[bname].view(1, -1)
+        bv.zero_()
+        ops.colsum(dy_for_bias, out=bv)
+        grads.seen.update((wname, bname))
+        return
+    grads[wname] = k.mm(dy_op, x_op, a_major=MN_, b_major=MN_)
+    grads[bname] = ops.colsum(dy_for_bias).reshape(-1)
 
 
 def encoder_fwd(k: Kernels, P: dict, pre: str, attn: str, x, xop, work, n_work, want_ctx: bool, out_op: bool):
@@ -146,21 +154,21 @@ def encoder_bwd(k: Kernels, P: dict, pre: str, attn: str, c: dict, dx2, work, n_
     grads[pre + "norm2.weight"], grads[pre + "norm2.bias"] = dw, db
     if dy2op is None:
         dy2op = dy2
-    grads[pre + "linear2.weight"], grads[pre + "linear2.bias"] = _lin_grads(k, dy2op, c["h"], dy2)
+    _lin_grads(k, dy2op, c["h"], dy2, grads, pre + "linear2.weight", pre + "linear2.bias")
     dh = k.mm(dy2op, w("linear2.weight"), b_major=MN_, out_dtype=k.AD, gate=c["h"])       # ReLU backward fused
-    grads[pre + "linear1.weight"], grads[pre + "linear1.bias"] = _lin_grads(k, dh, c["x1op"], dh)
+    _lin_grads(k, dh, c["x1op"], dh, grads, pre + "linear1.weight", pre + "linear1.bias")
     dx1 = k.mm(dh, w("linear1.weight"), b_major=MN_, residual=dy2)
     dy1, dy1op, dw, db = ops.layernorm_bwd(dx1, c["y1"], c["m1"], c["r1"], P[pre + "norm1.weight"], dx2_dtype=opd)
     grads[pre + "norm1.weight"], grads[pre + "norm1.bias"] = dw, db
     if dy1op is None:
         dy1op = dy1
-    grads[pre + f"{attn}.out_proj.weight"], grads[pre + f"{attn}.out_proj.bias"] = _lin_grads(k, dy1op, c["o"], dy1)
+    _lin_grads(k, dy1op, c["o"], dy1, grads, pre + f"{attn}.out_proj.weight", pre + f"{attn}.out_proj.bias")
     do = k.mm(dy1op, w(f"{attn}.out_proj.weight"), b_major=MN_, out_dtype=k.AD)
     qkv = c["qkv"]
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], c["o"], do, c["lse"], HEAD_DIM, N_HEAD, work, n_work,
                  dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
-    grads[pre + f"{attn}.in_proj_weight"], grads[pre + f"{attn}.in_proj_bias"] = _lin_grads(k, dqkv, c["xop"], dqkv)
+    _lin_grads(k, dqkv, c["xop"], dqkv, grads, pre + f"{attn}.in_proj_weight", pre + f"{attn}.in_proj_bias")
     if not need_dx:
         return None
     return k.mm(dqkv, w(f"{attn}.in_proj_weight"), b_major=MN_, residual=dy1)
@@ -195,25 +203,30 @@ def decoder_bwd(k: Kernels, P: dict, pre: str, c: dict, dout, slot, work, n_work
     win = k.weight(pre + "multihead2.in_proj_weight", P[pre + "multihead2.in_proj_weight"])
     w = lambda n: k.weight(pre + n, P[pre + n])
     doutop = k.opnd(dout)
-    grads[pre + "linear2.weight"], grads[pre + "linear2.bias"] = _lin_grads(k, doutop, c["h"], dout)
+    _lin_grads(k, doutop, c["h"], dout, grads, pre + "linear2.weight", pre + "linear2.bias")
     dh = k.mm(doutop, w("linear2.weight"), b_major=MN_, out_dtype=k.AD, gate=c["h"])      # ReLU backward fused
-    grads[pre + "linear1.weight"], grads[pre + "linear1.bias"] = _lin_grads(k, dh, c["top"], dh)
+    _lin_grads(k, dh, c["top"], dh, grads, pre + "linear1.weight", pre + "linear1.bias")
     dt = k.mm(dh, w("linear1.weight"), b_major=MN_, residual=dout)
     dy, dyop, dw, db = ops.layernorm_bwd(dt, c["y"], c["m3"], c["r3"], P[pre + "norm3.weight"],
                                          dx2_dtype=BF16 if k.AD == BF16 else None)
     grads[pre + "norm3.weight"], grads[pre + "norm3.bias"] = dw, db
     if dyop is None:
         dyop = dy
-    grads[pre + "multihead2.out_proj.weight"], grads[pre + "multihead2.out_proj.bias"] = _lin_grads(k, dyop, c["o"], dy)
+    _lin_grads(k, dyop, c["o"], dy, grads, pre + "multihead2.out_proj.weight", pre + "multihead2.out_proj.bias")
     do = k.mm(dyop, w("multihead2.out_proj.weight"), b_major=MN_, out_dtype=k.AD)
     qkv = c["qkv"]
     dqkv = torch.empty_like(qkv)
     ops.attn_bwd(qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:], c["o"], do, c["lse"], HEAD_DIM, N_HEAD, work, n_work,
                  dqkv[:, :d], dqkv[:, d:2 * d], dqkv[:, 2 * d:])
-    dwin = torch.empty(3 * d, d, device=dout.device, dtype=F32)
+    views = getattr(grads, "views", None)
+    wname = pre + "multihead2.in_proj_weight"
+    dwin = views[wname] if views is not None else torch.empty(3 * d, d, device=dout.device, dtype=F32)
     k.mm(dqkv[:, :2 * d], c["xpop"], a_major=MN_, b_major=MN_, out=dwin[:2 * d])
     k.mm(dqkv[:, 2 * d:], c["xop"], a_major=MN_, b_major=MN_, out=dwin[2 * d:])
-    grads[pre + "multihead2.in_proj_weight"] = dwin
+    if views is not None:
+        grads.seen.add(wname)
+    else:
+        grads[wname] = dwin
     grads[pre + "multihead2.in_proj_bias"] = ops.colsum(dqkv).reshape(-1)
     dxp = k.mm(dqkv[:, :2 * d], win[:2 * d], b_major=MN_)                 # gradient w.r.t. (x + pos)
     dpos = ops.colsum(dxp, row_class=slot, n_class=2)
@@ -267,7 +280,7 @@ def object_classifier_bwd(k: Kernels, P: dict, plan: Plan, c: dict, dlogits, gra
                              P[pre + "decoder_lin.1.weight"], tr, dx_dtype=k.AD)
     grads[pre + "decoder_lin.1.weight"], grads[pre + "decoder_lin.1.bias"] = dw, db
     objfeat = c["objfeat"]
-    grads[pre + "decoder_lin.0.weight"], grads[pre + "decoder_lin.0.bias"] = _lin_grads(k, dh1, objfeat, dh1)
+    _lin_grads(k, dh1, objfeat, dh1, grads, pre + "decoder_lin.0.weight", pre + "decoder_lin.0.bias")
     w0 = k.weight(pre + "decoder_lin.0.weight", P[pre + "decoder_lin.0.weight"])
     dtail = k.mm(dh1, w0[:, 2048:], b_major=MN_)                                    # [N, 200 + 128] fp32
     grads[pre + "obj_embed.weight"] = k.mm(c["distribution"], dtail[:, :200], a_major=MN_, b_major=MN_, exact=True)
