@@ -6,18 +6,18 @@
 // a query only ever sees the keys of its own segment ("bool masking" semantics).
 //
 // Work decomposition: a work item = 16 consecutive rows of one segment; grid = (work items, heads); 4 warps per CTA,
-// 4 rows per warp.  Only the item's own 16 rows are staged (transposed, fp32) in shared memory; the other side
-// streams straight from global/L2 in tiles of 32 rows — one row per lane for the dot products (each lane walks its
-// row in 4/8-byte words; a segment-head is <= 15 KB and stays in L1), one 128-byte line per warp for the
-// accumulations.  Softmax is online (running max / sum in registers) with warp-shuffle reductions.
-// head_dim even and <= 256 (242 here); fp32 math; I/O fp32 or bf16.
+// 4 rows per warp, every warp self-contained.  A warp keeps its own 4 rows (Q, and dO / K,V in the backward) in
+// REGISTERS, sliced over the lanes: lane owns the 2-element words lane + 32 j of the head (j < 4 -> head_dim <= 256),
+// so every global access is a contiguous 128/256-byte run of one row.  The other side of the product streams by row:
+// a row is loaded once into registers, used for the per-lane partial dot products (all-reduced across the warp with
+// a halving/doubling shuffle schedule) and reused for the accumulation.  No shared memory, no barriers; softmax is
+// online in the forward (one rescale per chunk of 4 keys) and recomputed from the stored log-sum-exp in the backward.
+// fp32 math; I/O fp32 or bf16; head_dim even (242 here).
 #include "common.cuh"
 
 namespace nlv {
 namespace {
 
-constexpr int QB = 16;     // rows per work item
-constexpr int KT = 32;     // rows per streamed tile (one per lane)
 constexpr int NW = 4;      // words (element pairs) owned per lane: word lane + 32*i  -> head_dim <= 256
 constexpr int THREADS = 128;
 
@@ -29,14 +29,6 @@ struct AttnArgs {
   const int4* work;        // {segment first row, segment length, first row of this item relative to segment, unused}
 };
 
-// two consecutive elements as float2 (word index w within a row that starts at `row`)
-template <typename T> __device__ __forceinline__ float2 ld2(const T* row, int w);
-template <> __device__ __forceinline__ float2 ld2<float>(const float* row, int w) {
-  return *reinterpret_cast<const float2*>(row + 2 * w);
-}
-template <> __device__ __forceinline__ float2 ld2<__nv_bfloat16>(const __nv_bfloat16* row, int w) {
-  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(row + 2 * w));
-}
 template <typename T> __device__ __forceinline__ void st2(T* row, int w, float a, float b);
 template <> __device__ __forceinline__ void st2<float>(float* row, int w, float a, float b) {
   *reinterpret_cast<float2*>(row + 2 * w) = make_float2(a, b);
@@ -45,370 +37,396 @@ template <> __device__ __forceinline__ void st2<__nv_bfloat16>(__nv_bfloat16* ro
   *reinterpret_cast<__nv_bfloat162*>(row + 2 * w) = __floats2bfloat162_rn(a, b);
 }
 
-// stage `nrows` rows of one head transposed into t[d][QB] (fp32, times mul); missing rows are zero
+// Raw (still packed) words of one row, sliced over the warp: lane owns words lane + 32 j.  Loads are unconditional
+// (out-of-range lanes / rows re-read a valid word and are zeroed at unpack time) and go through volatile asm so that
+// the whole batch of a chunk is in flight before the first use — the compiler otherwise interleaves each load with
+// its consumer and the warp pays one DRAM latency per word instead of one per chunk.
+template <typename T> struct Raw;
+template <> struct Raw<float> {
+  typedef float2 W;
+  static __device__ __forceinline__ W ldg(const float* p) {
+    W v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+  }
+  static __device__ __forceinline__ float2 unpack(W v) { return v; }
+};
+template <> struct Raw<__nv_bfloat16> {
+  typedef unsigned int W;
+  static __device__ __forceinline__ W ldg(const __nv_bfloat16* p) {
+    W v;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+  }
+  static __device__ __forceinline__ float2 unpack(W v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
+};
+
 template <typename T>
-__device__ __forceinline__ void stage_t(const T* base, int ld, long long row0, int nrows, int col0, int hd, float mul, float* t) {
-  // lane = (row r, element e of the pair): shared-memory writes of a warp are 32 consecutive floats (conflict-free);
-  // the 16 rows' lines stay in L1 across the hd/2 iterations
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwords = hd >> 1;
-  const int r = lane & (QB - 1), e = lane >> 4;
-  const T* row = base + (size_t)(row0 + r) * ld + col0 + e;
-  for (int w = warp; w < nwords; w += THREADS / 32) {
-    float x = 0.f;
-    if (r < nrows) x = (float)row[2 * w];
-    t[(2 * w + e) * QB + r] = x * mul;
+__device__ __forceinline__ void load_raw(const T* row, int nwords, typename Raw<T>::W (&r)[NW]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    const int wd = lane + 32 * j;
+    r[j] = Raw<T>::ldg(row + 2 * (wd < nwords ? wd : 0));
+  }
+}
+template <typename T>
+__device__ __forceinline__ void unpack_row(const typename Raw<T>::W (&r)[NW], int nwords, bool valid, float mul, float (&x)[2 * NW]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    const float2 t = Raw<T>::unpack(r[j]);
+    const bool ok = valid && lane + 32 * j < nwords;
+    x[2 * j] = ok ? t.x * mul : 0.f; x[2 * j + 1] = ok ? t.y * mul : 0.f;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_row(T* row, int nwords, const float (&x)[2 * NW], float mul) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int j = 0; j < NW; ++j) {
+    const int wd = lane + 32 * j;
+    if (wd < nwords) st2<T>(row, wd, x[2 * j] * mul, x[2 * j + 1] * mul);
+  }
+}
+__device__ __forceinline__ float dot8(const float (&a)[2 * NW], const float (&b)[2 * NW]) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2 * NW; ++i) s = fmaf(a[i], b[i], s);
+  return s;
+}
+__device__ __forceinline__ void axpy8(float c, const float (&x)[2 * NW], float (&acc)[2 * NW]) {
+#pragma unroll
+  for (int i = 0; i < 2 * NW; ++i) acc[i] = fmaf(c, x[i], acc[i]);
+}
+
+// All-reduce N (power of two, <= 16) per-lane partial sums over the warp; every lane ends with all N totals.
+// Reduce-scatter by recursive halving (each exchange carries half of what is left), plain butterflies for the
+// remaining lane bits, then the mirror-image all-gather: 2(N-1) + log2(32/N) shuffles instead of 5 N.
+template <int N>
+__device__ __forceinline__ void allreduce(float (&v)[N]) {
+  static_assert(N >= 2 && N <= 16 && (N & (N - 1)) == 0, "N must be 2, 4, 8 or 16");
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int half = N / 2, o = 16; half >= 1; half >>= 1, o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      if (i < half) {
+        const float send = up ? v[i] : v[i + half];
+        const float keep = up ? v[i + half] : v[i];
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+    }
+  }
+  constexpr int rem = 32 / N;
+#pragma unroll
+  for (int o = rem / 2; o >= 1; o >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], o);
+#pragma unroll
+  for (int cnt = 1, o = rem; cnt < N; cnt <<= 1, o <<= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+      if (i < cnt) {
+        const float other = __shfl_xor_sync(0xffffffffu, v[i], o);
+        v[i + cnt] = up ? v[i] : other;
+        v[i] = up ? other : v[i];
+      }
+    }
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// forward
+// forward: keys in chunks of 4 (16 scores all-reduced at once, one softmax rescale per chunk); the K and V rows of
+// the next chunk are requested before the current chunk is computed.
 // ------------------------------------------------------------------------------------------
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(THREADS)
 attn_fwd_kernel(AttnArgs a, TO* __restrict__ o, int ldo, float* __restrict__ lse) {
-  extern __shared__ float sm[];
+  constexpr int C = 4;
+  typedef typename Raw<TI>::W W;
   const int hd = a.hd, nwords = hd >> 1;
-  float* Qs = sm;                    // [hd][QB]   (pre-scaled)
-  float* Ps = Qs + hd * QB;          // [KT][QB]
-  const int4 w = a.work[blockIdx.x];
-  const int h = blockIdx.y, col0 = h * hd;
-  const long long seg0 = w.x;
-  const int L = w.y, q0 = w.z;
-  const int nq = min(QB, L - q0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TI* Q = reinterpret_cast<const TI*>(a.q);
-  const TI* K = reinterpret_cast<const TI*>(a.k);
-  const TI* V = reinterpret_cast<const TI*>(a.v);
+  const int4 w = a.work[blockIdx.x / a.heads];            // heads of one item are neighbouring CTAs: together they
+  const int h = blockIdx.x % a.heads, col0 = h * hd;       // read whole contiguous rows (DRAM page / TLB locality)
+  const long long seg0 = w.x;
+  const int L = w.y, q0 = w.z + warp * 4;       // first row of this warp inside the segment
+  const int nq = min(4, L - q0);
+  if (nq <= 0) return;                          // warps are independent: no barrier anywhere
+  const TI* Q = reinterpret_cast<const TI*>(a.q) + col0;
+  const TI* K = reinterpret_cast<const TI*>(a.k) + col0;
+  const TI* V = reinterpret_cast<const TI*>(a.v) + col0;
 
-  stage_t<TI>(Q, a.ldq, seg0 + q0, nq, col0, hd, a.scale, Qs);
-  __syncthreads();
-  if (warp * 4 >= nq) return;   // this warp's four rows are all beyond the segment (no block-wide sync follows)
-  float m[4], l[4], acc[4][2 * NW];
+  W rk[C][NW], rv[C][NW];
+  float q[4][2 * NW], acc[4][2 * NW], m[4], l[4];
+  {
+    W rq[4][NW];
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    m[qi] = -INFINITY; l[qi] = 0.f;
+    for (int i = 0; i < 4; ++i) load_raw<TI>(Q + (size_t)(seg0 + min(q0 + i, L - 1)) * a.ldq, nwords, rq[i]);
 #pragma unroll
-    for (int i = 0; i < 2 * NW; ++i) acc[qi][i] = 0.f;
-  }
-  for (int k0 = 0; k0 < L; k0 += KT) {
-    const int nk = min(KT, L - k0);
-    // scores: G = 1, 2 or 4 lanes per key (short segments would otherwise leave most lanes idle); each lane walks every
-    // G-th word of its key's row, partial dot products are combined with log2(G) shuffles
-    const int lg = nk <= 8 ? 2 : (nk <= 16 ? 1 : 0);
-    const int G = 1 << lg, key = lane >> lg, part = lane & (G - 1);
-    float s[4] = {0.f, 0.f, 0.f, 0.f};
-    if (key < nk) {
-      const TI* kr = K + (size_t)(seg0 + k0 + key) * a.ldk + col0;
-#pragma unroll 4
-      for (int wd = part; wd < nwords; wd += G) {
-        const float2 kv = ld2<TI>(kr, wd);
-        const float4 qa = *reinterpret_cast<const float4*>(Qs + (2 * wd) * QB + warp * 4);
-        const float4 qb = *reinterpret_cast<const float4*>(Qs + (2 * wd + 1) * QB + warp * 4);
-        s[0] = fmaf(qa.x, kv.x, s[0]); s[1] = fmaf(qa.y, kv.x, s[1]); s[2] = fmaf(qa.z, kv.x, s[2]); s[3] = fmaf(qa.w, kv.x, s[3]);
-        s[0] = fmaf(qb.x, kv.y, s[0]); s[1] = fmaf(qb.y, kv.y, s[1]); s[2] = fmaf(qb.z, kv.y, s[2]); s[3] = fmaf(qb.w, kv.y, s[3]);
-      }
+    for (int c = 0; c < C; ++c) {
+      const size_t row = seg0 + min(c, L - 1);
+      load_raw<TI>(K + row * a.ldk, nwords, rk[c]);
+      load_raw<TI>(V + row * a.ldv, nwords, rv[c]);
     }
-    for (int o = 1; o < G; o <<= 1) {
 #pragma unroll
-      for (int qi = 0; qi < 4; ++qi) s[qi] += __shfl_xor_sync(0xffffffffu, s[qi], o);
-    }
-    const bool valid = key < nk;
-    float p[4];
+    for (int i = 0; i < 4; ++i) {
+      unpack_row<TI>(rq[i], nwords, i < nq, a.scale, q[i]);
+      m[i] = -INFINITY; l[i] = 0.f;
 #pragma unroll
-    for (int qi = 0; qi < 4; ++qi) {
-      const float sv = valid ? s[qi] : -INFINITY;
-      const float mn = fmaxf(m[qi], warp_max(sv));
-      const float corr = __expf(m[qi] - mn);  // m = -inf on the first tile -> 0
-      p[qi] = valid ? __expf(sv - mn) : 0.f;
-      l[qi] = l[qi] * corr + warp_sum(part == 0 ? p[qi] : 0.f);
-      m[qi] = mn;
-#pragma unroll
-      for (int i = 0; i < 2 * NW; ++i) acc[qi][i] *= corr;
-    }
-    __syncwarp();
-    if (valid && part == 0) *reinterpret_cast<float4*>(Ps + key * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
-    __syncwarp();
-    // PV: lane owns words lane + 32*i of the head; V rows stream from global, one line per warp
-    for (int j = 0; j < nk; ++j) {
-      const float4 p4 = *reinterpret_cast<const float4*>(Ps + j * QB + warp * 4);
-      const TI* vr = V + (size_t)(seg0 + k0 + j) * a.ldv + col0;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const int wd = lane + 32 * i;
-        if (wd < nwords) {
-          const float2 vv = ld2<TI>(vr, wd);
-          acc[0][2 * i] = fmaf(p4.x, vv.x, acc[0][2 * i]); acc[0][2 * i + 1] = fmaf(p4.x, vv.y, acc[0][2 * i + 1]);
-          acc[1][2 * i] = fmaf(p4.y, vv.x, acc[1][2 * i]); acc[1][2 * i + 1] = fmaf(p4.y, vv.y, acc[1][2 * i + 1]);
-          acc[2][2 * i] = fmaf(p4.z, vv.x, acc[2][2 * i]); acc[2][2 * i + 1] = fmaf(p4.z, vv.y, acc[2][2 * i + 1]);
-          acc[3][2 * i] = fmaf(p4.w, vv.x, acc[3][2 * i]); acc[3][2 * i + 1] = fmaf(p4.w, vv.y, acc[3][2 * i + 1]);
-        }
-      }
+      for (int e = 0; e < 2 * NW; ++e) acc[i][e] = 0.f;
     }
   }
+  for (int k0 = 0; k0 < L; k0 += C) {
+    W nk[C][NW], nv[C][NW];
+    const bool more = k0 + C < L;
+    if (more) {
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int qr = warp * 4 + qi;
-    if (qr >= nq) continue;
-    const long long row = seg0 + q0 + qr;
-    const float inv = 1.f / l[qi];
-    TO* orow = o + (size_t)row * ldo + col0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int wd = lane + 32 * i;
-      if (wd < nwords) st2<TO>(orow, wd, acc[qi][2 * i] * inv, acc[qi][2 * i + 1] * inv);
+      for (int c = 0; c < C; ++c) {
+        const size_t row = seg0 + min(k0 + C + c, L - 1);
+        load_raw<TI>(K + row * a.ldk, nwords, nk[c]);
+        load_raw<TI>(V + row * a.ldv, nwords, nv[c]);
+      }
     }
-    if (lane == 0 && lse != nullptr) lse[row * a.heads + h] = m[qi] + __logf(l[qi]);
+    float s[C * 4];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float kr[2 * NW];
+      unpack_row<TI>(rk[c], nwords, k0 + c < L, 1.f, kr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[c * 4 + i] = dot8(q[i], kr);
+    }
+    allreduce<C * 4>(s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float mx = m[i];
+#pragma unroll
+      for (int c = 0; c < C; ++c) if (k0 + c < L) mx = fmaxf(mx, s[c * 4 + i]);
+      const float corr = __expf(m[i] - mx);     // m = -inf on the first chunk -> 0
+      m[i] = mx;
+      float ps = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float p = k0 + c < L ? __expf(s[c * 4 + i] - mx) : 0.f;
+        s[c * 4 + i] = p;
+        ps += p;
+      }
+      l[i] = l[i] * corr + ps;
+#pragma unroll
+      for (int e = 0; e < 2 * NW; ++e) acc[i][e] *= corr;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      float vr[2 * NW];
+      unpack_row<TI>(rv[c], nwords, k0 + c < L, 1.f, vr);   // p = 0 for the rows beyond L anyway
+#pragma unroll
+      for (int i = 0; i < 4; ++i) axpy8(s[c * 4 + i], vr, acc[i]);
+    }
+    if (more) {
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int j = 0; j < NW; ++j) { rk[c][j] = nk[c][j]; rv[c][j] = nv[c][j]; }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i >= nq) continue;
+    const long long row = seg0 + q0 + i;
+    store_row<TO>(o + (size_t)row * ldo + col0, nwords, acc[i], 1.f / l[i]);
+    if (lane == 0 && lse != nullptr) lse[row * a.heads + h] = m[i] + __logf(l[i]);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// backward, query side: dQ (and delta = rowsum(dO * O), stored for the key side)
+// backward, query side: dQ (and delta = rowsum(dO * O), stored for the key side).  Keys two at a time, next pair
+// prefetched; the key row loaded for the score is reused from registers for the dQ accumulation.
 // ------------------------------------------------------------------------------------------
 template <typename TI, typename TG>
 __global__ void __launch_bounds__(THREADS)
 attn_bwd_dq_kernel(AttnArgs a, const TI* __restrict__ o, int ldo, const TG* __restrict__ dout, int lddo,
                    const float* __restrict__ lse, float* __restrict__ delta, TI* __restrict__ dq, int lddq) {
-  extern __shared__ float sm[];
+  constexpr int C = 2;
+  typedef typename Raw<TI>::W W;
+  typedef typename Raw<TG>::W WG;
   const int hd = a.hd, nwords = hd >> 1;
-  float* Qs = sm;                    // [hd][QB] pre-scaled
-  float* dOs = Qs + hd * QB;         // [hd][QB]
-  float* Ss = dOs + hd * QB;         // [KT][QB]  dS
-  const int4 w = a.work[blockIdx.x];
-  const int h = blockIdx.y, col0 = h * hd;
-  const long long seg0 = w.x;
-  const int L = w.y, q0 = w.z;
-  const int nq = min(QB, L - q0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TI* Q = reinterpret_cast<const TI*>(a.q);
-  const TI* K = reinterpret_cast<const TI*>(a.k);
-  const TI* V = reinterpret_cast<const TI*>(a.v);
+  const int4 w = a.work[blockIdx.x / a.heads];
+  const int h = blockIdx.x % a.heads, col0 = h * hd;
+  const long long seg0 = w.x;
+  const int L = w.y, q0 = w.z + warp * 4;
+  const int nq = min(4, L - q0);
+  if (nq <= 0) return;
+  const TI* Q = reinterpret_cast<const TI*>(a.q) + col0;
+  const TI* K = reinterpret_cast<const TI*>(a.k) + col0;
+  const TI* V = reinterpret_cast<const TI*>(a.v) + col0;
 
-  stage_t<TI>(Q, a.ldq, seg0 + q0, nq, col0, hd, a.scale, Qs);
-  stage_t<TG>(dout, lddo, seg0 + q0, nq, col0, hd, 1.f, dOs);
-  float dl[4], ls[4];
+  W rk[C][NW], rv[C][NW];
+  float q[4][2 * NW], g[4][2 * NW], acc[4][2 * NW], dl[4], ls[4];
+  {
+    W rq[4][NW], ro[4][NW];
+    WG rg[4][NW];
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int qr = warp * 4 + qi;
-    float t = 0.f;
-    if (qr < nq) {
-      const long long row = seg0 + q0 + qr;
-      const TG* gr = dout + (size_t)row * lddo + col0;
-      const TI* orow = o + (size_t)row * ldo + col0;
-      for (int wd = lane; wd < nwords; wd += 32) {
-        const float2 g = ld2<TG>(gr, wd), ov = ld2<TI>(orow, wd);
-        t = fmaf(g.x, ov.x, fmaf(g.y, ov.y, t));
-      }
+    for (int i = 0; i < 4; ++i) {
+      const size_t row = seg0 + min(q0 + i, L - 1);
+      load_raw<TI>(Q + row * a.ldq, nwords, rq[i]);
+      load_raw<TG>(dout + row * lddo + col0, nwords, rg[i]);
+      load_raw<TI>(o + row * ldo + col0, nwords, ro[i]);
     }
-    dl[qi] = warp_sum(t);
-    ls[qi] = qr < nq ? lse[(seg0 + q0 + qr) * a.heads + h] : 0.f;
-    if (lane == 0 && qr < nq) delta[(seg0 + q0 + qr) * a.heads + h] = dl[qi];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const size_t row = seg0 + min(c, L - 1);
+      load_raw<TI>(K + row * a.ldk, nwords, rk[c]);
+      load_raw<TI>(V + row * a.ldv, nwords, rv[c]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float orow[2 * NW];
+      unpack_row<TI>(rq[i], nwords, i < nq, a.scale, q[i]);
+      unpack_row<TG>(rg[i], nwords, i < nq, 1.f, g[i]);
+      unpack_row<TI>(ro[i], nwords, i < nq, 1.f, orow);
+      dl[i] = dot8(g[i], orow);
+      ls[i] = i < nq ? lse[(seg0 + q0 + i) * a.heads + h] : 0.f;
+#pragma unroll
+      for (int e = 0; e < 2 * NW; ++e) acc[i][e] = 0.f;
+    }
   }
-  __syncthreads();
-  if (warp * 4 >= nq) return;
-  float acc[4][2 * NW];
+  allreduce<4>(dl);
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi)
+  for (int i = 0; i < 4; ++i)
+    if (lane == 0 && i < nq) delta[(seg0 + q0 + i) * a.heads + h] = dl[i];
+
+  for (int k0 = 0; k0 < L; k0 += C) {
+    W nk[C][NW], nv[C][NW];
+    const bool more = k0 + C < L;
+    if (more) {
 #pragma unroll
-    for (int i = 0; i < 2 * NW; ++i) acc[qi][i] = 0.f;
-  for (int k0 = 0; k0 < L; k0 += KT) {
-    const int nk = min(KT, L - k0);
-    const int lg = nk <= 8 ? 2 : (nk <= 16 ? 1 : 0);
-    const int G = 1 << lg, key = lane >> lg, part = lane & (G - 1);
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-    if (key < nk) {
-      const TI* kr = K + (size_t)(seg0 + k0 + key) * a.ldk + col0;
-      const TI* vr = V + (size_t)(seg0 + k0 + key) * a.ldv + col0;
-#pragma unroll 2
-      for (int wd = part; wd < nwords; wd += G) {
-        const float2 kv = ld2<TI>(kr, wd), vv = ld2<TI>(vr, wd);
-        const float4 qa = *reinterpret_cast<const float4*>(Qs + (2 * wd) * QB + warp * 4);
-        const float4 qb = *reinterpret_cast<const float4*>(Qs + (2 * wd + 1) * QB + warp * 4);
-        const float4 ga = *reinterpret_cast<const float4*>(dOs + (2 * wd) * QB + warp * 4);
-        const float4 gb = *reinterpret_cast<const float4*>(dOs + (2 * wd + 1) * QB + warp * 4);
-        s[0] = fmaf(qa.x, kv.x, s[0]); s[1] = fmaf(qa.y, kv.x, s[1]); s[2] = fmaf(qa.z, kv.x, s[2]); s[3] = fmaf(qa.w, kv.x, s[3]);
-        s[0] = fmaf(qb.x, kv.y, s[0]); s[1] = fmaf(qb.y, kv.y, s[1]); s[2] = fmaf(qb.z, kv.y, s[2]); s[3] = fmaf(qb.w, kv.y, s[3]);
-        dp[0] = fmaf(ga.x, vv.x, dp[0]); dp[1] = fmaf(ga.y, vv.x, dp[1]); dp[2] = fmaf(ga.z, vv.x, dp[2]); dp[3] = fmaf(ga.w, vv.x, dp[3]);
-        dp[0] = fmaf(gb.x, vv.y, dp[0]); dp[1] = fmaf(gb.y, vv.y, dp[1]); dp[2] = fmaf(gb.z, vv.y, dp[2]); dp[3] = fmaf(gb.w, vv.y, dp[3]);
+      for (int c = 0; c < C; ++c) {
+        const size_t row = seg0 + min(k0 + C + c, L - 1);
+        load_raw<TI>(K + row * a.ldk, nwords, nk[c]);
+        load_raw<TI>(V + row * a.ldv, nwords, nv[c]);
       }
     }
-    for (int o = 1; o < G; o <<= 1) {
+    float kr[C][2 * NW], sv[C * 8];
 #pragma unroll
-      for (int qi = 0; qi < 4; ++qi) {
-        s[qi] += __shfl_xor_sync(0xffffffffu, s[qi], o);
-        dp[qi] += __shfl_xor_sync(0xffffffffu, dp[qi], o);
+    for (int c = 0; c < C; ++c) {
+      float vr[2 * NW];
+      unpack_row<TI>(rk[c], nwords, k0 + c < L, 1.f, kr[c]);
+      unpack_row<TI>(rv[c], nwords, k0 + c < L, 1.f, vr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        sv[c * 8 + i] = dot8(q[i], kr[c]);
+        sv[c * 8 + 4 + i] = dot8(g[i], vr);
       }
     }
-    float ds[4];
+    allreduce<C * 8>(sv);
 #pragma unroll
-    for (int qi = 0; qi < 4; ++qi) {
-      const float p = key < nk ? __expf(s[qi] - ls[qi]) : 0.f;
-      ds[qi] = p * (dp[qi] - dl[qi]);
-    }
-    __syncwarp();
-    if (key < nk && part == 0) *reinterpret_cast<float4*>(Ss + key * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-    __syncwarp();
-    for (int j = 0; j < nk; ++j) {
-      const float4 s4 = *reinterpret_cast<const float4*>(Ss + j * QB + warp * 4);
-      const TI* kj = K + (size_t)(seg0 + k0 + j) * a.ldk + col0;
+    for (int c = 0; c < C; ++c) {
+      if (k0 + c < L) {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const int wd = lane + 32 * i;
-        if (wd < nwords) {
-          const float2 kv = ld2<TI>(kj, wd);
-          acc[0][2 * i] = fmaf(s4.x, kv.x, acc[0][2 * i]); acc[0][2 * i + 1] = fmaf(s4.x, kv.y, acc[0][2 * i + 1]);
-          acc[1][2 * i] = fmaf(s4.y, kv.x, acc[1][2 * i]); acc[1][2 * i + 1] = fmaf(s4.y, kv.y, acc[1][2 * i + 1]);
-          acc[2][2 * i] = fmaf(s4.z, kv.x, acc[2][2 * i]); acc[2][2 * i + 1] = fmaf(s4.z, kv.y, acc[2][2 * i + 1]);
-          acc[3][2 * i] = fmaf(s4.w, kv.x, acc[3][2 * i]); acc[3][2 * i + 1] = fmaf(s4.w, kv.y, acc[3][2 * i + 1]);
+        for (int i = 0; i < 4; ++i) {
+          const float p = __expf(sv[c * 8 + i] - ls[i]);
+          axpy8(p * (sv[c * 8 + 4 + i] - dl[i]), kr[c], acc[i]);
         }
       }
     }
-  }
+    if (more) {
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int qr = warp * 4 + qi;
-    if (qr >= nq) continue;
-    TI* drow = dq + (size_t)(seg0 + q0 + qr) * lddq + col0;
+      for (int c = 0; c < C; ++c)
 #pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int wd = lane + 32 * i;
-      if (wd < nwords) st2<TI>(drow, wd, acc[qi][2 * i] * a.scale, acc[qi][2 * i + 1] * a.scale);
+        for (int j = 0; j < NW; ++j) { rk[c][j] = nk[c][j]; rv[c][j] = nv[c][j]; }
     }
   }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (i < nq) store_row<TI>(dq + (size_t)(seg0 + q0 + i) * lddq + col0, nwords, acc[i], a.scale);
 }
 
 // ------------------------------------------------------------------------------------------
-// backward, key side: dK, dV.  The work item's 16 rows are the KEYS; queries stream in tiles of 32.
+// backward, key side: dK, dV.  The warp's 4 rows are KEYS (K and V rows live in registers); queries stream by,
+// the next query's Q / dO rows prefetched while the current one is processed.
 // ------------------------------------------------------------------------------------------
 template <typename TI, typename TG>
 __global__ void __launch_bounds__(THREADS)
 attn_bwd_dkv_kernel(AttnArgs a, const TG* __restrict__ dout, int lddo, const float* __restrict__ lse,
                     const float* __restrict__ delta, TI* __restrict__ dk, int lddk, TI* __restrict__ dv, int lddv) {
-  extern __shared__ float sm[];
+  typedef typename Raw<TI>::W W;
+  typedef typename Raw<TG>::W WG;
   const int hd = a.hd, nwords = hd >> 1;
-  float* Kt = sm;                    // [hd][QB]  this item's keys, transposed
-  float* Vt = Kt + hd * QB;          // [hd][QB]
-  float* Ps = Vt + hd * QB;          // [KT][QB]
-  float* Ss = Ps + KT * QB;          // [KT][QB]
-  const int4 w = a.work[blockIdx.x];
-  const int h = blockIdx.y, col0 = h * hd;
+  const int warp = threadIdx.x >> 5;
+  const int4 w = a.work[blockIdx.x / a.heads];
+  const int h = blockIdx.x % a.heads, col0 = h * hd;
   const long long seg0 = w.x;
-  const int L = w.y, k0 = w.z;
-  const int nkeys = min(QB, L - k0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const TI* Q = reinterpret_cast<const TI*>(a.q);
-  const TI* K = reinterpret_cast<const TI*>(a.k);
-  const TI* V = reinterpret_cast<const TI*>(a.v);
+  const int L = w.y, k0 = w.z + warp * 4;
+  const int nkeys = min(4, L - k0);
+  if (nkeys <= 0) return;
+  const TI* Q = reinterpret_cast<const TI*>(a.q) + col0;
+  const TI* K = reinterpret_cast<const TI*>(a.k) + col0;
+  const TI* V = reinterpret_cast<const TI*>(a.v) + col0;
+  const TG* G = dout + col0;
 
-  stage_t<TI>(K, a.ldk, seg0 + k0, nkeys, col0, hd, 1.f, Kt);
-  stage_t<TI>(V, a.ldv, seg0 + k0, nkeys, col0, hd, 1.f, Vt);
-  __syncthreads();
-  if (warp * 4 >= nkeys) return;
-  float accK[4][2 * NW], accV[4][2 * NW];
+  W rq[NW];
+  WG rg[NW];
+  float kk[4][2 * NW], vv[4][2 * NW], accK[4][2 * NW], accV[4][2 * NW];
+  float lq, dr;
+  {
+    W rk[4][NW], rv[4][NW];
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk)
+    for (int i = 0; i < 4; ++i) {
+      const size_t row = seg0 + min(k0 + i, L - 1);
+      load_raw<TI>(K + row * a.ldk, nwords, rk[i]);
+      load_raw<TI>(V + row * a.ldv, nwords, rv[i]);
+    }
+    load_raw<TI>(Q + (size_t)seg0 * a.ldq, nwords, rq);
+    load_raw<TG>(G + (size_t)seg0 * lddo, nwords, rg);
+    lq = lse[seg0 * a.heads + h];
+    dr = delta[seg0 * a.heads + h];
 #pragma unroll
-    for (int i = 0; i < 2 * NW; ++i) { accK[kk][i] = 0.f; accV[kk][i] = 0.f; }
-  for (int q0 = 0; q0 < L; q0 += KT) {
-    const int nq = min(KT, L - q0);
-    // lane = query of the tile; 4 keys of this warp
-    const int lg = nq <= 8 ? 2 : (nq <= 16 ? 1 : 0);
-    const int G = 1 << lg, qrow = lane >> lg, part = lane & (G - 1);
-    float s[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
-    float lq = 0.f, dq_ = 0.f;
-    if (qrow < nq) {
-      const long long row = seg0 + q0 + qrow;
-      const TI* qr = Q + (size_t)row * a.ldq + col0;
-      const TG* gr = dout + (size_t)row * lddo + col0;
+    for (int i = 0; i < 4; ++i) {
+      unpack_row<TI>(rk[i], nwords, i < nkeys, a.scale, kk[i]);
+      unpack_row<TI>(rv[i], nwords, i < nkeys, 1.f, vv[i]);
+#pragma unroll
+      for (int e = 0; e < 2 * NW; ++e) { accK[i][e] = 0.f; accV[i][e] = 0.f; }
+    }
+  }
+  for (int r = 0; r < L; ++r) {
+    float qr[2 * NW], gr[2 * NW], sv[8];
+    unpack_row<TI>(rq, nwords, true, 1.f, qr);
+    unpack_row<TG>(rg, nwords, true, 1.f, gr);
+    const float lq_c = lq, dr_c = dr;
+    if (r + 1 < L) {
+      const long long row = seg0 + r + 1;
+      load_raw<TI>(Q + (size_t)row * a.ldq, nwords, rq);
+      load_raw<TG>(G + (size_t)row * lddo, nwords, rg);
       lq = lse[row * a.heads + h];
-      dq_ = delta[row * a.heads + h];
-#pragma unroll 2
-      for (int wd = part; wd < nwords; wd += G) {
-        const float2 qv = ld2<TI>(qr, wd), gv = ld2<TG>(gr, wd);
-        const float4 ka = *reinterpret_cast<const float4*>(Kt + (2 * wd) * QB + warp * 4);
-        const float4 kb = *reinterpret_cast<const float4*>(Kt + (2 * wd + 1) * QB + warp * 4);
-        const float4 va = *reinterpret_cast<const float4*>(Vt + (2 * wd) * QB + warp * 4);
-        const float4 vb = *reinterpret_cast<const float4*>(Vt + (2 * wd + 1) * QB + warp * 4);
-        s[0] = fmaf(ka.x, qv.x, s[0]); s[1] = fmaf(ka.y, qv.x, s[1]); s[2] = fmaf(ka.z, qv.x, s[2]); s[3] = fmaf(ka.w, qv.x, s[3]);
-        s[0] = fmaf(kb.x, qv.y, s[0]); s[1] = fmaf(kb.y, qv.y, s[1]); s[2] = fmaf(kb.z, qv.y, s[2]); s[3] = fmaf(kb.w, qv.y, s[3]);
-        dp[0] = fmaf(va.x, gv.x, dp[0]); dp[1] = fmaf(va.y, gv.x, dp[1]); dp[2] = fmaf(va.z, gv.x, dp[2]); dp[3] = fmaf(va.w, gv.x, dp[3]);
-        dp[0] = fmaf(vb.x, gv.y, dp[0]); dp[1] = fmaf(vb.y, gv.y, dp[1]); dp[2] = fmaf(vb.z, gv.y, dp[2]); dp[3] = fmaf(vb.w, gv.y, dp[3]);
-      }
+      dr = delta[row * a.heads + h];
     }
-    for (int o = 1; o < G; o <<= 1) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        s[kk] += __shfl_xor_sync(0xffffffffu, s[kk], o);
-        dp[kk] += __shfl_xor_sync(0xffffffffu, dp[kk], o);
-      }
+    for (int i = 0; i < 4; ++i) {
+      sv[i] = dot8(kk[i], qr);        // already times scale
+      sv[4 + i] = dot8(vv[i], gr);
     }
-    float p[4], ds[4];
+    allreduce<8>(sv);
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      const bool ok = qrow < nq && (warp * 4 + kk) < nkeys;
-      p[kk] = ok ? __expf(s[kk] * a.scale - lq) : 0.f;
-      ds[kk] = p[kk] * (dp[kk] - dq_);
-    }
-    __syncwarp();
-    if (qrow < nq && part == 0) {
-      *reinterpret_cast<float4*>(Ps + qrow * QB + warp * 4) = make_float4(p[0], p[1], p[2], p[3]);
-      *reinterpret_cast<float4*>(Ss + qrow * QB + warp * 4) = make_float4(ds[0], ds[1], ds[2], ds[3]);
-    }
-    __syncwarp();
-    for (int j = 0; j < nq; ++j) {
-      const float4 p4 = *reinterpret_cast<const float4*>(Ps + j * QB + warp * 4);
-      const float4 s4 = *reinterpret_cast<const float4*>(Ss + j * QB + warp * 4);
-      const long long row = seg0 + q0 + j;
-      const TG* gj = dout + (size_t)row * lddo + col0;
-      const TI* qj = Q + (size_t)row * a.ldq + col0;
-#pragma unroll
-      for (int i = 0; i < NW; ++i) {
-        const int wd = lane + 32 * i;
-        if (wd < nwords) {
-          const float2 gv = ld2<TG>(gj, wd), qv = ld2<TI>(qj, wd);
-          accV[0][2 * i] = fmaf(p4.x, gv.x, accV[0][2 * i]); accV[0][2 * i + 1] = fmaf(p4.x, gv.y, accV[0][2 * i + 1]);
-          accV[1][2 * i] = fmaf(p4.y, gv.x, accV[1][2 * i]); accV[1][2 * i + 1] = fmaf(p4.y, gv.y, accV[1][2 * i + 1]);
-          accV[2][2 * i] = fmaf(p4.z, gv.x, accV[2][2 * i]); accV[2][2 * i + 1] = fmaf(p4.z, gv.y, accV[2][2 * i + 1]);
-          accV[3][2 * i] = fmaf(p4.w, gv.x, accV[3][2 * i]); accV[3][2 * i + 1] = fmaf(p4.w, gv.y, accV[3][2 * i + 1]);
-          accK[0][2 * i] = fmaf(s4.x, qv.x, accK[0][2 * i]); accK[0][2 * i + 1] = fmaf(s4.x, qv.y, accK[0][2 * i + 1]);
-          accK[1][2 * i] = fmaf(s4.y, qv.x, accK[1][2 * i]); accK[1][2 * i + 1] = fmaf(s4.y, qv.y, accK[1][2 * i + 1]);
-          accK[2][2 * i] = fmaf(s4.z, qv.x, accK[2][2 * i]); accK[2][2 * i + 1] = fmaf(s4.z, qv.y, accK[2][2 * i + 1]);
-          accK[3][2 * i] = fmaf(s4.w, qv.x, accK[3][2 * i]); accK[3][2 * i + 1] = fmaf(s4.w, qv.y, accK[3][2 * i + 1]);
-        }
-      }
+    for (int i = 0; i < 4; ++i) {
+      const float p = i < nkeys ? __expf(sv[i] - lq_c) : 0.f;
+      axpy8(p, gr, accV[i]);
+      axpy8(p * (sv[4 + i] - dr_c), qr, accK[i]);
     }
   }
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    const int kr = warp * 4 + kk;
-    if (kr >= nkeys) continue;
-    const long long row = seg0 + k0 + kr;
-    TI* dkr = dk + (size_t)row * lddk + col0;
-    TI* dvr = dv + (size_t)row * lddv + col0;
-#pragma unroll
-    for (int i = 0; i < NW; ++i) {
-      const int wd = lane + 32 * i;
-      if (wd < nwords) {
-        st2<TI>(dkr, wd, accK[kk][2 * i] * a.scale, accK[kk][2 * i + 1] * a.scale);
-        st2<TI>(dvr, wd, accV[kk][2 * i], accV[kk][2 * i + 1]);
-      }
-    }
+  for (int i = 0; i < 4; ++i) {
+    if (i >= nkeys) continue;
+    const long long row = seg0 + k0 + i;
+    store_row<TI>(dk + (size_t)row * lddk + col0, nwords, accK[i], a.scale);
+    store_row<TI>(dv + (size_t)row * lddv + col0, nwords, accV[i], 1.f);
   }
 }
-
-size_t fwd_smem(int hd) { return sizeof(float) * ((size_t)hd * QB + KT * QB); }
-size_t dq_smem(int hd) { return sizeof(float) * (2 * (size_t)hd * QB + KT * QB); }
-size_t dkv_smem(int hd) { return sizeof(float) * (2 * (size_t)hd * QB + 2 * KT * QB); }
 
 int check_common(int hd, int heads, int n_work, int ld_all_even) {
   NLV_CHECK_ARG(hd > 0 && hd <= 64 * NW && (hd & 1) == 0, "attention: head_dim=%d unsupported (even, max %d)", hd, 64 * NW);
-  NLV_CHECK_ARG(heads > 0 && heads <= 65535 && n_work >= 0, "attention: bad sizes");
+  NLV_CHECK_ARG(heads > 0 && n_work >= 0 && (long long)heads * n_work < (1ll << 31), "attention: bad sizes");
   NLV_CHECK_ARG(ld_all_even, "attention: row strides must be even (vector access)");
-  return NLV_OK;
-}
-
-template <typename K> int set_smem(K kern, size_t bytes) {
-  if (bytes > 48 * 1024) NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
   return NLV_OK;
 }
 
@@ -431,14 +449,8 @@ int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
   if (n_work == 0) return NLV_OK;
   NLV_CHECK_ARG(q && k && v && work && o, "attn_fwd: null pointer");
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
-  const size_t smem = fwd_smem(hd);
-  const dim3 grid(n_work, heads);
-#define FWD(TI, TO)                                                                    \
-  do {                                                                                 \
-    rc = set_smem(attn_fwd_kernel<TI, TO>, smem);                                      \
-    if (rc != NLV_OK) return rc;                                                       \
-    attn_fwd_kernel<TI, TO><<<grid, THREADS, smem, STREAM>>>(a, (TO*)o, ldo, lse);     \
-  } while (0)
+  const dim3 grid((unsigned)n_work * (unsigned)heads);
+#define FWD(TI, TO) attn_fwd_kernel<TI, TO><<<grid, THREADS, 0, STREAM>>>(a, (TO*)o, ldo, lse)
   if (in_dtype == NLV_BF16 && o_dtype == NLV_BF16) FWD(bf16, bf16);
   else if (in_dtype == NLV_BF16) FWD(bf16, float);
   else if (o_dtype == NLV_BF16) FWD(float, bf16);
@@ -460,19 +472,14 @@ int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
   NLV_CHECK_ARG(q && k && v && work && o && dout && lse && delta && dq && dk && dv, "attn_bwd: null pointer");
   NLV_CHECK_ARG(in_dtype == o_dtype && in_dtype == dqkv_dtype, "attn_bwd: q/k/v, o and dq/dk/dv must share one dtype");
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
-  const size_t s1 = dq_smem(hd), s2 = dkv_smem(hd);
-  const dim3 grid(n_work, heads);
+  const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define BWD(TI, TG)                                                                                                         \
   do {                                                                                                                      \
-    rc = set_smem(attn_bwd_dq_kernel<TI, TG>, s1);                                                                          \
-    if (rc != NLV_OK) return rc;                                                                                            \
-    rc = set_smem(attn_bwd_dkv_kernel<TI, TG>, s2);                                                                         \
-    if (rc != NLV_OK) return rc;                                                                                            \
-    attn_bwd_dq_kernel<TI, TG><<<grid, THREADS, s1, STREAM>>>(a, (const TI*)o, ldo, (const TG*)dout, lddo, lse, delta,      \
-                                                             (TI*)dq, lddq);                                                \
+    attn_bwd_dq_kernel<TI, TG><<<grid, THREADS, 0, STREAM>>>(a, (const TI*)o, ldo, (const TG*)dout, lddo, lse, delta,       \
+                                                            (TI*)dq, lddq);                                                 \
     NLV_CHECK_LAUNCH();                                                                                                     \
-    attn_bwd_dkv_kernel<TI, TG><<<grid, THREADS, s2, STREAM>>>(a, (const TG*)dout, lddo, lse, delta, (TI*)dk, lddk,         \
-                                                              (TI*)dv, lddv);                                               \
+    attn_bwd_dkv_kernel<TI, TG><<<grid, THREADS, 0, STREAM>>>(a, (const TG*)dout, lddo, lse, delta, (TI*)dk, lddk,          \
+                                                             (TI*)dv, lddv);                                                \
   } while (0)
   if (in_dtype == NLV_BF16 && do_dtype == NLV_BF16) BWD(bf16, bf16);
   else if (in_dtype == NLV_BF16) BWD(bf16, float);
