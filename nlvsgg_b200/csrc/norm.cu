@@ -291,6 +291,10 @@ int launch_bn_bwd_apply_v8(const float* dy, int lddy, const void* x, int xdt, in
                            const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s);
+int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
+                            int y2dt, float* mean, float* rstd, cudaStream_t s);
+int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
+                               int cols, float* dx, void* dx2, int dx2dt, cudaStream_t s);
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace nlv
 
@@ -304,6 +308,8 @@ int nlv_layernorm_fwd(const float* x, long long rows, int cols, const float* w, 
   NLV_CHECK_ARG(rows >= 0 && cols > 0 && cols <= 32 * LN_MAX_PER_LANE, "layernorm_fwd: cols=%d unsupported", cols);
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(x && w && b && (y || y2), "layernorm_fwd: null pointer");
+  if ((cols & 3) == 0 && al16(x) && al16(w) && al16(b) && al16(y) && (y2 == nullptr || (reinterpret_cast<uintptr_t>(y2) & 7) == 0))
+    return launch_layernorm_fwd_v4(x, rows, cols, w, b, eps, y, y2, y2_dtype, mean, rstd, STREAM);
   const int warps = 4;
   layernorm_fwd_kernel<<<cdiv(rows, warps), warps * 32, 0, STREAM>>>(x, rows, cols, w, b, eps, y, y2, y2_dtype, mean, rstd);
   NLV_CHECK_LAUNCH();
@@ -316,8 +322,13 @@ int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
   NLV_CHECK_ARG(rows >= 0 && cols > 0 && cols <= 32 * LN_MAX_PER_LANE, "layernorm_bwd: cols=%d unsupported", cols);
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(dy && x && mean && rstd && w && dw && db && (dx || dx2), "layernorm_bwd: null pointer");
-  layernorm_bwd_dx_kernel<<<cdiv(rows, 4), 128, 0, STREAM>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype);
-  NLV_CHECK_LAUNCH();
+  if ((cols & 3) == 0 && al16(dy) && al16(x) && al16(w) && al16(dx) && (dx2 == nullptr || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0)) {
+    const int rc = launch_layernorm_bwd_dx_v4(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, STREAM);
+    if (rc != NLV_OK) return rc;
+  } else {
+    layernorm_bwd_dx_kernel<<<cdiv(rows, 4), 128, 0, STREAM>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype);
+    NLV_CHECK_LAUNCH();
+  }
   NLV_CHECK_ARG((cols & 3) == 0, "layernorm_bwd: cols=%d must be a multiple of 4", cols);
   int splits = (int)((rows + 255) / 256);
   if (splits > 1024) splits = 1024;

@@ -103,67 +103,133 @@ __global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, 
   }
 }
 
-__global__ void bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __restrict__ row_seg,
-                                   const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ w,
-                                   const float* __restrict__ b, float eps, int relu, long long rows, int C,
-                                   void* __restrict__ y, int ydt, int ldy, void* __restrict__ y2, int y2dt, int ldy2) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// Apply kernels: a thread owns 8 consecutive channels and walks down the rows of its block's row range, so the
+// per-(segment, channel) coefficients live in registers and are rebuilt only when the segment (video) changes.
+// block (bx channel groups, by rows), grid (ceil(C8/bx), row ranges); U rows are in flight per thread.
+struct ApplyGeom { dim3 grid, block; long long rows_per_block; };
+ApplyGeom apply_geometry(int C, long long rows, int unroll) {
   const int C8 = C >> 3;
-  if (i >= rows * C8) return;
-  const long long r = i / C8;
-  const int c0 = (int)(i - r * C8) * 8;
-  const int s = row_seg ? row_seg[r] : 0;
-  const V8 xv = nv_ld8(x, xdt, (size_t)r * ldx + c0);
-  const V8 m = nv_ld8(mean, NLV_F32, (size_t)s * C + c0), v = nv_ld8(var, NLV_F32, (size_t)s * C + c0);
+  int bx = 1;
+  while (bx < C8 && bx < 32) bx <<= 1;
+  const int by = 128 / bx;
+  const int gx = cdiv(C8, bx);
+  long long want = (long long)sm_count() * 12 / gx;           // ~12 blocks of 4 warps per SM in total
+  if (want < 1) want = 1;
+  long long per = cdiv(rows, want);
+  const long long quantum = (long long)by * unroll;            // whole unrolled sweeps
+  per = cdiv(per, quantum) * quantum;
+  ApplyGeom g;
+  g.grid = dim3(gx, (unsigned)cdiv(rows, per));
+  g.block = dim3(bx, by);
+  g.rows_per_block = per;
+  return g;
+}
+
+template <int U>
+__global__ void __launch_bounds__(128)
+bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __restrict__ row_seg,
+                   const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ w,
+                   const float* __restrict__ b, float eps, int relu, long long rows, long long rows_per_block, int C,
+                   void* __restrict__ y, int ydt, int ldy, void* __restrict__ y2, int y2dt, int ldy2) {
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c8 >= (C >> 3)) return;
+  const int c0 = c8 * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   const V8 ww = nv_ld8(w, NLV_F32, c0), bb = nv_ld8(b, NLV_F32, c0);
-  V8 o;
+  int cur = -1;
+  float m[8], k[8];
+  for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
+    V8 xv[U];
+    int sg[U];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    o.v[q] = (xv.v[q] - m.v[q]) * rsqrtf(v.v[q] + eps) * ww.v[q] + bb.v[q];
-    if (relu) o.v[q] = fmaxf(o.v[q], 0.f);
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * blockDim.y;
+      if (rr < r1) {
+        xv[u] = nv_ld8(x, xdt, (size_t)rr * ldx + c0);
+        sg[u] = row_seg ? row_seg[rr] : 0;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * blockDim.y;
+      if (rr >= r1) break;
+      if (sg[u] != cur) {
+        cur = sg[u];
+        const V8 mm = nv_ld8(mean, NLV_F32, (size_t)cur * C + c0), vv = nv_ld8(var, NLV_F32, (size_t)cur * C + c0);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { m[q] = mm.v[q]; k[q] = rsqrtf(vv.v[q] + eps) * ww.v[q]; }
+      }
+      V8 o;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        o.v[q] = fmaf(xv[u].v[q] - m[q], k[q], bb.v[q]);
+        if (relu) o.v[q] = fmaxf(o.v[q], 0.f);
+      }
+      if (y) nv_st8(y, ydt, (size_t)rr * ldy + c0, o);
+      if (y2) nv_st8(y2, y2dt, (size_t)rr * ldy2 + c0, o);
+    }
   }
-  if (y) nv_st8(y, ydt, (size_t)r * ldy + c0, o);
-  if (y2) nv_st8(y2, y2dt, (size_t)r * ldy2 + c0, o);
 }
 
 // dx = w*rstd*(dy - sum_dy/n - xhat*sum_dy_xhat/n) [batch stats] or w*rstd*dy [running stats]; optional ReLU mask by
 // yout on dy, optional ReLU gate by `x > 0` on the RESULT (ReLU that precedes the BN: conv -> ReLU -> BN).
-__global__ void bn_bwd_apply_v8_kernel(const float* __restrict__ dy, int lddy, const void* __restrict__ x, int xdt, int ldx,
-                                       const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
-                                       const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
-                                       const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
-                                       int gate_by_x, long long rows, int C, void* __restrict__ dx, int dxdt, int lddx) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int C8 = C >> 3;
-  if (i >= rows * C8) return;
-  const long long r = i / C8;
-  const int c0 = (int)(i - r * C8) * 8;
-  const int s = row_seg ? row_seg[r] : 0;
-  const V8 xv = nv_ld8(x, xdt, (size_t)r * ldx + c0);
-  V8 g = nv_ld8(dy, NLV_F32, (size_t)r * lddy + c0);
-  if (yout != nullptr) {
-    const V8 yo = nv_ld8(yout, ydt, (size_t)r * ldy + c0);
+template <int U>
+__global__ void __launch_bounds__(128)
+bn_bwd_apply_v8_kernel(const float* __restrict__ dy, int lddy, const void* __restrict__ x, int xdt, int ldx,
+                       const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
+                       const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
+                       const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
+                       int gate_by_x, long long rows, long long rows_per_block, int C, void* __restrict__ dx, int dxdt, int lddx) {
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c8 >= (C >> 3)) return;
+  const int c0 = c8 * 8;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  const V8 ww = nv_ld8(w, NLV_F32, c0);
+  int cur = -1;
+  float m[8], k[8], s1[8], t2[8];   // k = w*rstd, s1 = sum_dy/n, t2 = rstd*sum_dy_xhat/n
+  for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
+    V8 xv[U], g[U], yo[U];
+    int sg[U];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-      if (!(yo.v[q] > 0.f)) g.v[q] = 0.f;
-  }
-  const V8 m = nv_ld8(mean, NLV_F32, (size_t)s * C + c0), v = nv_ld8(var, NLV_F32, (size_t)s * C + c0), ww = nv_ld8(w, NLV_F32, c0);
-  const float n = use_batch_stats ? (float)(seg[s + 1] - seg[s]) : 1.f;
-  V8 o;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float rs = rsqrtf(v.v[q] + eps);
-    if (use_batch_stats) {
-      const float xh = (xv.v[q] - m.v[q]) * rs;
-      const float s1 = (float)(sums[((size_t)s * 2 + 0) * C + c0 + q]) / n;
-      const float s2 = (float)(sums[((size_t)s * 2 + 1) * C + c0 + q]) / n;
-      o.v[q] = ww.v[q] * rs * (g.v[q] - s1 - xh * s2);
-    } else {
-      o.v[q] = ww.v[q] * rs * g.v[q];
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * blockDim.y;
+      if (rr < r1) {
+        xv[u] = nv_ld8(x, xdt, (size_t)rr * ldx + c0);
+        g[u] = nv_ld8(dy, NLV_F32, (size_t)rr * lddy + c0);
+        if (yout != nullptr) yo[u] = nv_ld8(yout, ydt, (size_t)rr * ldy + c0);
+        sg[u] = row_seg ? row_seg[rr] : 0;
+      }
     }
-    if (gate_by_x && !(xv.v[q] > 0.f)) o.v[q] = 0.f;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + (long long)u * blockDim.y;
+      if (rr >= r1) break;
+      if (sg[u] != cur) {
+        cur = sg[u];
+        const V8 mm = nv_ld8(mean, NLV_F32, (size_t)cur * C + c0), vv = nv_ld8(var, NLV_F32, (size_t)cur * C + c0);
+        const float n = use_batch_stats ? (float)(seg[cur + 1] - seg[cur]) : 1.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float rs = rsqrtf(vv.v[q] + eps);
+          m[q] = mm.v[q];
+          k[q] = ww.v[q] * rs;
+          if (use_batch_stats) {
+            s1[q] = (float)(sums[((size_t)cur * 2 + 0) * C + c0 + q]) / n;
+            t2[q] = rs * ((float)(sums[((size_t)cur * 2 + 1) * C + c0 + q]) / n);
+          } else { s1[q] = 0.f; t2[q] = 0.f; }
+        }
+      }
+      V8 o;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float gq = g[u].v[q];
+        if (yout != nullptr && !(yo[u].v[q] > 0.f)) gq = 0.f;
+        o.v[q] = k[q] * (gq - s1[q] - (xv[u].v[q] - m[q]) * t2[q]);
+        if (gate_by_x && !(xv[u].v[q] > 0.f)) o.v[q] = 0.f;
+      }
+      nv_st8(dx, dxdt, (size_t)rr * lddx + c0, o);
+    }
   }
-  nv_st8(dx, dxdt, (size_t)r * lddx + c0, o);
 }
 
 void sums_geometry(int C, long long rows, int nseg, dim3& grid, dim3& block) {
@@ -199,8 +265,9 @@ int launch_bn_sums_bwd_v8(const float* dy, int lddy, const void* x, int xdt, int
 int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
                        const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
                        int ldy2, cudaStream_t s) {
-  bn_apply_v8_kernel<<<cdiv(rows * (C / 8), 256), 256, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, C, y, ydt, ldy,
-                                                              y2, y2dt, ldy2);
+  const ApplyGeom g = apply_geometry(C, rows, 2);
+  bn_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
+                                                  ldy, y2, y2dt, ldy2);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
@@ -208,8 +275,150 @@ int launch_bn_bwd_apply_v8(const float* dy, int lddy, const void* x, int xdt, in
                            const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s) {
-  bn_bwd_apply_v8_kernel<<<cdiv(rows * (C / 8), 256), 256, 0, s>>>(dy, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps,
-                                                                  sums, use_batch_stats, gate_by_x, rows, C, dx, dxdt, lddx);
+  const ApplyGeom g = apply_geometry(C, rows, 2);
+  bn_bwd_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(dy, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+                                                      use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm, 16-byte vectorised: one warp per row, lane owns the float4 words lane + 32 j (cols % 4 == 0, cols <= 128 NV).
+// All loads of a row are issued back to back (volatile asm keeps the compiler from threading each load through its
+// consumer), so a warp pays one memory latency per row with 16-32 x 512 B in flight.
+// ------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ float4 ldg_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_row4(void* base, int dt, size_t elem, float4 o) {
+  if (dt == NLV_BF16) {
+    uint2 t;
+    *reinterpret_cast<__nv_bfloat162*>(&t.x) = __floats2bfloat162_rn(o.x, o.y);
+    *reinterpret_cast<__nv_bfloat162*>(&t.y) = __floats2bfloat162_rn(o.z, o.w);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(base) + elem) = t;
+  } else {
+    *reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + elem) = o;
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_fwd_v4_kernel(const float* __restrict__ x, long long rows, int cols, const float* __restrict__ w,
+                        const float* __restrict__ b, float eps, float* __restrict__ y, void* __restrict__ y2, int y2dt,
+                        float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int nv = cols >> 2;
+  const float* xr = x + (size_t)row * cols;
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    v[j] = ldg_f4(xr + 4 * (i < nv ? i : 0));
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (lane + 32 * j >= nv) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    if (lane + 32 * j < nv) {
+      const float a = v[j].x - mean, bq = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+      q += (a * a + bq * bq) + (c * c + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float4 ww = *reinterpret_cast<const float4*>(w + 4 * i), bb = *reinterpret_cast<const float4*>(b + 4 * i);
+      float4 o;
+      o.x = (v[j].x - mean) * rstd * ww.x + bb.x; o.y = (v[j].y - mean) * rstd * ww.y + bb.y;
+      o.z = (v[j].z - mean) * rstd * ww.z + bb.z; o.w = (v[j].w - mean) * rstd * ww.w + bb.w;
+      if (y) *reinterpret_cast<float4*>(y + (size_t)row * cols + 4 * i) = o;
+      if (y2) st_row4(y2, y2dt, (size_t)row * cols + 4 * i, o);
+    }
+  }
+}
+
+template <int NV>
+__global__ void __launch_bounds__(128)
+layernorm_bwd_dx_v4_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ w, long long rows, int cols,
+                           float* __restrict__ dx, void* __restrict__ dx2, int dx2dt) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (row >= rows) return;
+  const int nv = cols >> 2;
+  const float* dyr = dy + (size_t)row * cols;
+  const float* xr = x + (size_t)row * cols;
+  float4 g[NV], xh[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j, ic = 4 * (i < nv ? i : 0);
+    g[j] = ldg_f4(dyr + ic);
+    xh[j] = ldg_f4(xr + ic);
+  }
+  const float m = mean[row], rs = rstd[row];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      const float4 ww = *reinterpret_cast<const float4*>(w + 4 * i);
+      xh[j].x = (xh[j].x - m) * rs; xh[j].y = (xh[j].y - m) * rs; xh[j].z = (xh[j].z - m) * rs; xh[j].w = (xh[j].w - m) * rs;
+      g[j].x *= ww.x; g[j].y *= ww.y; g[j].z *= ww.z; g[j].w *= ww.w;
+      s1 += (g[j].x + g[j].y) + (g[j].z + g[j].w);
+      s2 += (g[j].x * xh[j].x + g[j].y * xh[j].y) + (g[j].z * xh[j].z + g[j].w * xh[j].w);
+    }
+  }
+  s1 = warp_sum(s1) / (float)cols;
+  s2 = warp_sum(s2) / (float)cols;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nv) {
+      float4 o;
+      o.x = rs * (g[j].x - s1 - xh[j].x * s2); o.y = rs * (g[j].y - s1 - xh[j].y * s2);
+      o.z = rs * (g[j].z - s1 - xh[j].z * s2); o.w = rs * (g[j].w - s1 - xh[j].w * s2);
+      if (dx) *reinterpret_cast<float4*>(dx + (size_t)row * cols + 4 * i) = o;
+      if (dx2) st_row4(dx2, dx2dt, (size_t)row * cols + 4 * i, o);
+    }
+  }
+}
+
+}  // namespace
+
+int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
+                            int y2dt, float* mean, float* rstd, cudaStream_t s) {
+  const unsigned grid = (unsigned)cdiv(rows, 4);
+  if (cols <= 512) layernorm_fwd_v4_kernel<4><<<grid, 128, 0, s>>>(x, rows, cols, w, b, eps, y, y2, y2dt, mean, rstd);
+  else if (cols <= 1024) layernorm_fwd_v4_kernel<8><<<grid, 128, 0, s>>>(x, rows, cols, w, b, eps, y, y2, y2dt, mean, rstd);
+  else layernorm_fwd_v4_kernel<16><<<grid, 128, 0, s>>>(x, rows, cols, w, b, eps, y, y2, y2dt, mean, rstd);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
+                               int cols, float* dx, void* dx2, int dx2dt, cudaStream_t s) {
+  const unsigned grid = (unsigned)cdiv(rows, 4);
+  if (cols <= 512) layernorm_bwd_dx_v4_kernel<4><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
+  else if (cols <= 1024) layernorm_bwd_dx_v4_kernel<8><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
+  else layernorm_bwd_dx_v4_kernel<16><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
