@@ -303,6 +303,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool vec_ok = d_bf16 ? ((p.ldd & 7) == 0 && ((uintptr_t)p.d & 15) == 0)
                                : ((p.ldd & 3) == 0 && ((uintptr_t)p.d & 15) == 0);
     const bool split = p.k_splits > 1;
+    const bool bias_vec = ((uintptr_t)p.bias & 15) == 0;
     for (int work = work0; work < num_work; work += work_stride, ++iter) {
       const int tile = work / p.k_splits;
       const int m0 = ((tile % num_mp) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
@@ -339,9 +340,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           continue;
         }
         if (p.bias != nullptr) {
+          if (ncol == 32 && bias_vec) {   // same address in every lane: 8 broadcast 16-byte loads instead of 32 scalar ones
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) f[j] += __ldg(p.bias + n0 + c0 + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 t = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c0 + j));
+              f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) f[j] += __ldg(p.bias + n0 + c0 + j);
+          }
         }
         if (p.relu) {
 #pragma unroll
