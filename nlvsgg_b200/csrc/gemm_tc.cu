@@ -2,11 +2,13 @@
 //
 //   D[m,n] = act( sum_k A(m,k) * B(n,k) + bias[n] ) + residual[m,n]       (bf16 in, fp32 accumulate)
 //
-// One persistent CTA per SM, 192 threads:
+// One persistent CTA per SM, 320 threads:
 //   warp 0 (lane 0) : TMA producer   — cp.async.bulk.tensor 2-D boxes into a 128B-swizzled smem ring
 //   warp 1 (lane 0) : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction,
 //                                      accumulators double-buffered in TMEM (2 x BLOCK_N columns)
-//   warps 2..5      : epilogue       — tcgen05.ld 32x32b (one TMEM lane = one output row per thread),
+//   warps 2..9      : epilogue       — tcgen05.ld 32x32b (one TMEM lane = one output row per thread); warps w and w+4
+//                                      share a TMEM lane quarter and take alternate 32-column chunks (the epilogue of
+//                                      small-K products is bound by memory instructions in flight per warp);
 //                                      bias / ReLU / residual fused, fp32 or bf16 stores
 // Both operands may be K-major ([MN,K] row-major) or MN-major ([K,MN] row-major), selected in the UMMA
 // instruction/smem descriptors, so the forward (X W^T), input-gradient (dY W) and weight-gradient
@@ -25,7 +27,8 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;   // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_EPI_WARPS = 8;               // two warps per TMEM lane quarter, alternating 32-column chunks
+constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int ATOM_BYTES = 64 * BLOCK_K * 2;          // one [64 mn x 64 k] MN-major box, 8 KiB
 
@@ -183,7 +186,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(s), NUM_EPI_WARPS);  // one arrive per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
@@ -298,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
+    const int chunk0 = ((warp - 2) >> 2) * 32;   // first 32-column chunk of this warp
     int iter = 0;
     const bool d_bf16 = p.d_dtype == NLV_BF16;
     const bool vec_ok = d_bf16 ? ((p.ldd & 7) == 0 && ((uintptr_t)p.d & 15) == 0)
@@ -315,17 +319,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.m;
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
+      bool released = false;
+      constexpr int CSTEP = 32 * (NUM_EPI_WARPS / 4);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      for (int c0 = chunk0; c0 < BLOCK_N; c0 += CSTEP) {
         if (n0 + c0 >= p.n) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr_row + c0, v);
         tmem_ld_wait();
-        if (c0 + 32 >= BLOCK_N || n0 + c0 + 32 >= p.n) {
-          // last chunk of this tile: the accumulator stage can be handed back to the MMA warp
+        if (c0 + CSTEP >= BLOCK_N || n0 + c0 + CSTEP >= p.n) {
+          // this warp's last chunk of the tile: its share of the accumulator stage goes back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          released = true;
         }
         if (!row_ok) continue;
         const int ncol = min(32, p.n - (n0 + c0));
@@ -437,6 +444,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (j < ncol) o[j] = f[j];
           }
         }
+      }
+      if (!released) {   // no column chunk fell to this warp (narrow last n-block)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
       }
     }
   }
