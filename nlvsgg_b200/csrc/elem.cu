@@ -73,6 +73,35 @@ __global__ void nchw_to_rows_kernel(const float* __restrict__ src, int C, void* 
   }
 }
 
+// bf16 output, C % 128 == 0: one CTA per (pair, 128-channel slab).  The slab is 128 x 49 contiguous floats: read with
+// 16-byte loads (all of a thread's loads in flight at once), parked in shared memory in the same linear order, and
+// written back as bf16 channel pairs: a warp-store is 128 contiguous bytes of one output row.
+__global__ void __launch_bounds__(256)
+nchw_to_rows_bf16_kernel(const float* __restrict__ src, int C, __nv_bfloat16* __restrict__ dst) {
+  constexpr int HW = 49, CS = 128, NF4 = CS * HW / 4;   // 1568 float4 per slab
+  __shared__ __align__(16) float tile[CS * HW];
+  const int r = blockIdx.y, c0 = blockIdx.x * CS;
+  const float4* s4 = reinterpret_cast<const float4*>(src + ((size_t)r * C + c0) * HW);
+  float4 v[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < NF4) v[k] = __ldcs(s4 + i);     // streamed once: do not keep in L2
+  }
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < NF4) reinterpret_cast<float4*>(tile)[i] = v[k];
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + (size_t)r * HW * C + c0;
+#pragma unroll 5
+  for (int e = threadIdx.x; e < HW * (CS / 2); e += 256) {
+    const int hw = e >> 6, c = (e & 63) * 2;
+    *reinterpret_cast<__nv_bfloat162*>(d + (size_t)hw * C + c) = __floats2bfloat162_rn(tile[c * HW + hw], tile[(c + 1) * HW + hw]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // im2col for Conv2d(2,128,k7,s2,p3) on spatial masks [R,2,27,27] -> [R*14*14, ld] (98 cols, zero pad)
 // column order (c, ky, kx) = the flattening of conv.0.weight [128, 2,7,7]  (lib/sttran.py:338)
@@ -361,6 +390,12 @@ int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_
   if (r == 0) return NLV_OK;
   NLV_CHECK_ARG(src && dst, "nchw_to_rows: null pointer");
   NLV_CHECK_ARG(r <= 65535, "nchw_to_rows: r=%d exceeds the grid limit; split the call", r);
+  if (dst_dtype == NLV_BF16 && (c & 127) == 0 && al16(src) && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
+    dim3 grid(c / 128, r);
+    nchw_to_rows_bf16_kernel<<<grid, 256, 0, STREAM>>>(src, c, (__nv_bfloat16*)dst);
+    NLV_CHECK_LAUNCH();
+    return NLV_OK;
+  }
   dim3 grid(cdiv(c, 64), r);
   nchw_to_rows_kernel<49><<<grid, 256, 0, STREAM>>>(src, c, dst, dst_dtype);
   NLV_CHECK_LAUNCH();
