@@ -82,6 +82,12 @@ class Kernels:
             if self.precision != "bf16":
                 od = F32
             out = torch.empty(m, n, device=a.device, dtype=od)
+        kdim = a.shape[1] if a_major == K_ else a.shape[0]
+        if exact and self.precision == "bf16" and a.dtype == F32 and b.dtype == F32 and kdim >= 256:
+            # fp32-grade product on the tensor cores (three bf16 terms per operand, error ~2^-17) instead of the SIMT kernel
+            a3 = ops.split3(a, 1 if a_major == K_ else 0, 0)
+            b3 = ops.split3(b, 1 if b_major == K_ else 0, 1)
+            return ops.gemm(a3, b3, out, a_major=a_major, b_major=b_major, bias=bias, residual=residual, relu=relu, gate=gate)
         if exact or self.precision == "fp32":
             if a.dtype != F32:
                 a = ops.convert(a, F32)
