@@ -218,8 +218,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int tile = work / p.k_splits;
         const int kb0 = (work % p.k_splits) * p.kb_per_split;
         const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
-        const int m0 = ((tile % num_mp) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
-        const int n0 = (tile / num_mp) * BLOCK_N;
+        // n-block fastest: the ~74 clusters running at any moment cover a band of ~9 m-pairs x all n-blocks, so an A
+        // row block is fetched from DRAM once and re-read from L2 by the other n-blocks (m-fastest order streamed all
+        // of A once per n-block: 3x the algorithmic DRAM traffic on the [22931 x 1936 x 1936] products)
+        const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+        const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
@@ -310,8 +313,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool bias_vec = ((uintptr_t)p.bias & 15) == 0;
     for (int work = work0; work < num_work; work += work_stride, ++iter) {
       const int tile = work / p.k_splits;
-      const int m0 = ((tile % num_mp) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
-      const int n0 = (tile / num_mp) * BLOCK_N;
+      const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+      const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1;
       mbar_wait(tmem_full_bar(acc), acc_phase);
