@@ -13,6 +13,8 @@
 // a halving/doubling shuffle schedule) and reused for the accumulation.  No shared memory, no barriers; softmax is
 // online in the forward (one rescale per chunk of 4 keys) and recomputed from the stored log-sum-exp in the backward.
 // fp32 math; I/O fp32 or bf16; head_dim even (242 here).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nlv {
@@ -433,6 +435,20 @@ int check_common(int hd, int heads, int n_work, int ld_all_even) {
 }  // namespace
 }  // namespace nlv
 
+// tensor-core path for bf16 I/O (attn_mma.cu); NLV_ATTN_SIMT=1 keeps the SIMT kernels (A/B runs, unit tests of both)
+namespace nlv {
+bool attn_mma_supported(int hd, int heads, int ld_or);
+int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
+                        const void* work, int n_work, void* o, int ldo, float* lse, cudaStream_t s);
+int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
+                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq,
+                        void* dk, int lddk, void* dv, int lddv, cudaStream_t s);
+static bool use_mma() {
+  const char* e = getenv("NLV_ATTN_SIMT");
+  return !(e != nullptr && e[0] == '1');
+}
+}  // namespace nlv
+
 using namespace nlv;
 #define STREAM ((cudaStream_t)stream)
 typedef __nv_bfloat16 bf16;
@@ -448,6 +464,8 @@ int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
   if (rc != NLV_OK) return rc;
   if (n_work == 0) return NLV_OK;
   NLV_CHECK_ARG(q && k && v && work && o, "attn_fwd: null pointer");
+  if (in_dtype == NLV_BF16 && o_dtype == NLV_BF16 && use_mma() && attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo))
+    return launch_attn_fwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, o, ldo, lse, STREAM);
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define FWD(TI, TO) attn_fwd_kernel<TI, TO><<<grid, THREADS, 0, STREAM>>>(a, (TO*)o, ldo, lse)
@@ -471,6 +489,10 @@ int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
   if (n_work == 0) return NLV_OK;
   NLV_CHECK_ARG(q && k && v && work && o && dout && lse && delta && dq && dk && dv, "attn_bwd: null pointer");
   NLV_CHECK_ARG(in_dtype == o_dtype && in_dtype == dqkv_dtype, "attn_bwd: q/k/v, o and dq/dk/dv must share one dtype");
+  if (in_dtype == NLV_BF16 && do_dtype == NLV_BF16 && use_mma() &&
+      attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv))
+    return launch_attn_bwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv,
+                               lddv, STREAM);
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define BWD(TI, TG)                                                                                                         \

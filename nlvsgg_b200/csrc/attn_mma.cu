@@ -1,0 +1,388 @@
+// Tensor-core variant of the varlen attention kernels (attn.cu) for bf16 inputs / outputs.
+//
+// Same work decomposition (16 rows of one segment x one head) but a whole work item is ONE warp: the 16 x hd Q tile and
+// 16-row K / V tiles are staged in shared memory with 4-byte cp.async (head slices start on 4-byte boundaries only:
+// head_dim 242 -> 484-byte slices; every warp-copy is one contiguous 128-byte run), zero-padded to 256 columns, and all
+// products run on mma.sync.m16n8k16 (bf16 in, fp32 accumulate):
+//   forward   S = Q K^T (A, B by ldmatrix), online softmax on the accumulator fragments, O += P V (P re-used from the
+//             accumulator registers as the A fragment, V by ldmatrix.trans)
+//   backward  query side: S, dP = dO V^T, dS = P o (dP - delta), dQ += dS K
+//             key side:   S^T = K Q^T, dP^T = V dO^T (operands swapped so P^T / dS^T come out as A fragments),
+//                         dV += P^T dO, dK += dS^T Q; two warps per work item, each owning half of the head columns
+//   delta = rowsum(dO o O) is obtained as rowsum(P o dP) inside the query-side kernel (no O tile needed).
+// tcgen05 is not used here on purpose: the segments are 6-40 rows, far below the 128-row UMMA tile; the kernels are bound
+// by moving Q/K/V/dO once (HBM), and mma.sync on 16-row tiles already makes the arithmetic a small fraction of the copy time.
+// Replaces torch.nn.MultiheadAttention's core (lib/transformer.py:9-13,38-42, lib/dsg_detr.py:21-22) with
+// key_padding_mask semantics folded into the segment bounds.
+#include "common.cuh"
+
+namespace nlv {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int KP = 264;            // padded tile row, bf16 elements (256 + 8: ldmatrix rows land on different banks)
+constexpr int ROWB = KP * 2;       // 528 bytes
+constexpr int TILE_B = 16 * ROWB;  // 8448 bytes: one 16-row tile
+constexpr int NT = 32;             // 8-column output tiles covering 256 columns
+
+struct MArgs {
+  const bf16 *q, *k, *v;
+  int ldq, ldk, ldv;
+  int hd, heads;
+  float scale;
+  const int4* work;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float quad_max(float x) {
+  x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 1));
+  return fmaxf(x, __shfl_xor_sync(0xffffffffu, x, 2));
+}
+__device__ __forceinline__ float quad_sum(float x) {
+  x += __shfl_xor_sync(0xffffffffu, x, 1);
+  return x + __shfl_xor_sync(0xffffffffu, x, 2);
+}
+
+// zero the padding words 121..127 (columns hd..255) of a 16-row tile; done once per tile buffer (copies never touch them)
+__device__ __forceinline__ void zero_pad(uint32_t tile, int nwords, int lane) {
+  const int npad = 128 - nwords;
+  for (int i = lane; i < 16 * npad; i += 32) {
+    const int r = i / npad, w = nwords + i % npad;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + r * ROWB + w * 4), "r"(0u) : "memory");
+  }
+}
+// rows [first, first + cnt) of `src` (already offset to the head's first column) -> tile rows [r0, r0 + nr); rows >= cnt are zeroed
+__device__ __forceinline__ void load_rows(uint32_t tile, const bf16* src, int ld, long long first, int cnt, int r0, int nr, int nwords,
+                                          int lane) {
+  for (int r = r0; r < r0 + nr; ++r) {
+    const uint32_t dst = tile + r * ROWB;
+    if (r < cnt) {
+      const bf16* s = src + (size_t)(first + r) * ld;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = lane + 32 * j;
+        if (w < nwords) cp_async4(dst + w * 4, s + 2 * w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int w = lane + 32 * j;
+        if (w < nwords) asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst + w * 4), "r"(0u) : "memory");
+      }
+    }
+  }
+}
+// coalesced copy of tile rows [0, cnt) (first nwords words) to global rows
+__device__ __forceinline__ void store_rows(uint32_t tile, bf16* dst, int ld, long long first, int cnt, int nwords, int lane, int r0 = 0,
+                                           int rstep = 1) {
+  for (int r = r0; r < cnt; r += rstep) {
+    bf16* d = dst + (size_t)(first + r) * ld;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int w = lane + 32 * j;
+      if (w < nwords) {
+        uint32_t v;
+        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(tile + r * ROWB + w * 4));
+        *reinterpret_cast<uint32_t*>(d + 2 * w) = v;
+      }
+    }
+  }
+}
+
+// C[2][4] (16 rows x 16 cols) = A(16 x 256, row tile) * B(16 x 256, row tile)^T : both tiles row-major in shared memory
+__device__ __forceinline__ void qk_product(uint32_t a_tile, uint32_t b_tile, int lane, float (&c)[2][4]) {
+  const uint32_t a_addr = a_tile + (lane & 15) * ROWB + (lane >> 4) * 16;
+  const uint32_t b_addr = b_tile + ((lane & 7) + ((lane >> 4) << 3)) * ROWB + ((lane >> 3) & 1) * 16;
+#pragma unroll
+  for (int ks = 0; ks < 16; ++ks) {
+    uint32_t a[4], b[4];
+    ldsm_x4(a, a_addr + ks * 32);
+    ldsm_x4(b, b_addr + ks * 32);
+    mma16816(c[0], a, b[0], b[1]);
+    mma16816(c[1], a, b[2], b[3]);
+  }
+}
+// acc[nt] (16 rows x 8 cols each, nt in [nt0, nt0 + N)) += A(16 x 16, register fragments) * B(16 rows x 256 cols tile, row-major)
+template <int N>
+__device__ __forceinline__ void pv_product(const uint32_t (&a)[4], uint32_t b_tile, int lane, int nt0, float (&acc)[N][4]) {
+  const uint32_t b_addr = b_tile + ((lane & 7) + ((lane >> 3) & 1) * 8) * ROWB + (lane >> 4) * 16;
+#pragma unroll
+  for (int i = 0; i < N; i += 2) {
+    uint32_t b[4];
+    ldsm_x4_t(b, b_addr + (nt0 + i) * 16);
+    mma16816(acc[i], a, b[0], b[1]);
+    mma16816(acc[i + 1], a, b[2], b[3]);
+  }
+}
+// accumulator tiles -> bf16 tile in shared memory (rows g / g+8, columns nt*8 + 2t, +1), scaled per row
+template <int N>
+__device__ __forceinline__ void acc_to_tile(uint32_t tile, int lane, int nt0, const float (&acc)[N][4], float s0, float s1) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int i = 0; i < N; ++i) {
+    const uint32_t c = (nt0 + i) * 16 + t * 4;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + g * ROWB + c), "r"(pack2(acc[i][0] * s0, acc[i][1] * s0)) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + (g + 8) * ROWB + c), "r"(pack2(acc[i][2] * s1, acc[i][3] * s1)) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward: CTA = 4 warps = 4 consecutive heads of one work item
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ lse) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hgroups = a.heads >> 2;
+  const int4 w = a.work[blockIdx.x / hgroups];
+  const int h = (blockIdx.x % hgroups) * 4 + warp, col0 = h * a.hd, nwords = a.hd >> 1;
+  const long long seg0 = w.x;
+  const int L = w.y, q0 = w.z, nq = min(16, L - q0);
+  const uint32_t Qs = smem_addr(smem) + warp * 3 * TILE_B, Ks = Qs + TILE_B, Vs = Ks + TILE_B;
+  zero_pad(Qs, nwords, lane); zero_pad(Ks, nwords, lane); zero_pad(Vs, nwords, lane);
+  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane);
+
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  for (int k0 = 0; k0 < L; k0 += 16) {
+    const int nk = min(16, L - k0);
+    if (k0 > 0) __syncwarp();
+    load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane);
+    load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    qk_product(Qs, Ks, lane, s);
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = n * 8 + 2 * t + (c & 1);
+        s[n][c] = key < nk ? s[n][c] * a.scale : -INFINITY;
+        if (c < 2) mx0 = fmaxf(mx0, s[n][c]); else mx1 = fmaxf(mx1, s[n][c]);
+      }
+    const float mn0 = fmaxf(m0, quad_max(mx0)), mn1 = fmaxf(m1, quad_max(mx1));
+    const float corr0 = __expf(m0 - mn0), corr1 = __expf(m1 - mn1);   // first tile: exp(-inf) = 0
+    m0 = mn0; m1 = mn1;
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+      s[n][0] = __expf(s[n][0] - mn0); s[n][1] = __expf(s[n][1] - mn0);
+      s[n][2] = __expf(s[n][2] - mn1); s[n][3] = __expf(s[n][3] - mn1);
+      ps0 += s[n][0] + s[n][1]; ps1 += s[n][2] + s[n][3];
+    }
+    l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;     // per-thread partial row sums; combined over the quad at the end
+    if (k0 > 0) {
+#pragma unroll
+      for (int i = 0; i < NT; ++i) { acc[i][0] *= corr0; acc[i][1] *= corr0; acc[i][2] *= corr1; acc[i][3] *= corr1; }
+    }
+    const uint32_t pa[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
+    pv_product<NT>(pa, Vs, lane, 0, acc);
+  }
+  l0 = quad_sum(l0); l1 = quad_sum(l1);
+  __syncwarp();
+  acc_to_tile<NT>(Qs, lane, 0, acc, 1.f / l0, 1.f / l1);   // the Q tile is dead: reuse it to transpose the output for row-contiguous stores
+  __syncwarp();
+  store_rows(Qs, o + col0, ldo, seg0 + q0, nq, nwords, lane);
+  if (lse != nullptr && t == 0) {
+    if (g < nq) lse[(seg0 + q0 + g) * a.heads + h] = m0 + __logf(l0);
+    if (g + 8 < nq) lse[(seg0 + q0 + g + 8) * a.heads + h] = m1 + __logf(l1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, query side: CTA = 2 warps = 2 consecutive heads of one work item; tiles Q, dO (fixed) and K, V (streamed)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+attn_bwd_dq_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const float* __restrict__ lse, float* __restrict__ delta,
+                       bf16* __restrict__ dq, int lddq) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int hgroups = a.heads >> 1;
+  const int4 w = a.work[blockIdx.x / hgroups];
+  const int h = (blockIdx.x % hgroups) * 2 + warp, col0 = h * a.hd, nwords = a.hd >> 1;
+  const long long seg0 = w.x;
+  const int L = w.y, q0 = w.z, nq = min(16, L - q0);
+  const uint32_t Qs = smem_addr(smem) + warp * 4 * TILE_B, Gs = Qs + TILE_B, Ks = Gs + TILE_B, Vs = Ks + TILE_B;
+  zero_pad(Qs, nwords, lane); zero_pad(Gs, nwords, lane); zero_pad(Ks, nwords, lane); zero_pad(Vs, nwords, lane);
+  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane);
+  load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, 0, 16, nwords, lane);
+  const long long r0 = seg0 + q0 + g, r1 = r0 + 8;
+  const float ls0 = g < nq ? lse[r0 * a.heads + h] : 0.f, ls1 = g + 8 < nq ? lse[r1 * a.heads + h] : 0.f;
+
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  // delta_i = sum_j P_ij dP_ij (= dO_i . O_i).  One key tile (the common case): computed on the fly; longer segments take
+  // a first pass over the key tiles for delta and a second one for dQ.
+  const bool single = L <= 16;
+  float dl0 = 0.f, dl1 = 0.f;
+  bool first_load = true;
+  for (int pass = single ? 1 : 0; pass < 2; ++pass) {
+    float e0 = 0.f, e1 = 0.f;
+    for (int k0 = 0; k0 < L; k0 += 16) {
+      const int nk = min(16, L - k0);
+      if (!first_load) __syncwarp();
+      first_load = false;
+      load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane);
+      load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane);
+      cp_async_wait_all();
+      __syncwarp();
+      float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+      qk_product(Qs, Ks, lane, s);
+      qk_product(Gs, Vs, lane, dp);
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int key = n * 8 + 2 * t + (c & 1);
+          s[n][c] = key < nk ? __expf(s[n][c] * a.scale - (c < 2 ? ls0 : ls1)) : 0.f;      // P
+          if (c < 2) e0 = fmaf(s[n][c], dp[n][c], e0); else e1 = fmaf(s[n][c], dp[n][c], e1);
+        }
+      if (pass == 0) continue;
+      if (single) { dl0 = quad_sum(e0); dl1 = quad_sum(e1); }
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[n][c] *= dp[n][c] - (c < 2 ? dl0 : dl1);               // dS
+      const uint32_t da[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
+      pv_product<NT>(da, Ks, lane, 0, acc);
+    }
+    if (pass == 0) { dl0 = quad_sum(e0); dl1 = quad_sum(e1); }
+  }
+  if (t == 0) {
+    if (g < nq) delta[r0 * a.heads + h] = dl0;
+    if (g + 8 < nq) delta[r1 * a.heads + h] = dl1;
+  }
+  __syncwarp();
+  acc_to_tile<NT>(Qs, lane, 0, acc, a.scale, a.scale);
+  __syncwarp();
+  store_rows(Qs, dq + col0, lddq, seg0 + q0, nq, nwords, lane);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, key side: CTA = 2 warps on ONE (work item, head): the item's 16 rows are KEYS; both warps share the K, V tiles
+// (fixed) and the streamed Q, dO tiles, compute S^T / dP^T redundantly, and own one half of the head columns of dK, dV.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+attn_bwd_dkv_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const float* __restrict__ lse, const float* __restrict__ delta,
+                        bf16* __restrict__ dk, int lddk, bf16* __restrict__ dv, int lddv) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float lse_s[16], dl_s[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int4 w = a.work[blockIdx.x / a.heads];
+  const int h = blockIdx.x % a.heads, col0 = h * a.hd, nwords = a.hd >> 1;
+  const long long seg0 = w.x;
+  const int L = w.y, k0 = w.z, nkeys = min(16, L - k0);
+  const uint32_t Ks = smem_addr(smem), Vs = Ks + TILE_B, Qs = Vs + TILE_B, Gs = Qs + TILE_B;
+  // each warp prepares / loads 8 rows of every tile
+  if (warp == 0) { zero_pad(Ks, nwords, lane); zero_pad(Qs, nwords, lane); } else { zero_pad(Vs, nwords, lane); zero_pad(Gs, nwords, lane); }
+  load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nkeys, warp * 8, 8, nwords, lane);
+  load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nkeys, warp * 8, 8, nwords, lane);
+
+  constexpr int NH = NT / 2;
+  const int nt0 = warp * NH;
+  float accK[NH][4], accV[NH][4];
+#pragma unroll
+  for (int i = 0; i < NH; ++i) { accK[i][0] = accK[i][1] = accK[i][2] = accK[i][3] = 0.f; accV[i][0] = accV[i][1] = accV[i][2] = accV[i][3] = 0.f; }
+  for (int q0 = 0; q0 < L; q0 += 16) {
+    const int nq = min(16, L - q0);
+    if (q0 > 0) __syncthreads();                      // both warps are done with the previous Q / dO tiles
+    load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, warp * 8, 8, nwords, lane);
+    load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, warp * 8, 8, nwords, lane);
+    if (threadIdx.x < 16) {
+      const bool ok = (int)threadIdx.x < nq;
+      lse_s[threadIdx.x] = ok ? lse[(seg0 + q0 + threadIdx.x) * a.heads + h] : 0.f;
+      dl_s[threadIdx.x] = ok ? delta[(seg0 + q0 + threadIdx.x) * a.heads + h] : 0.f;
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    qk_product(Ks, Qs, lane, s);      // S^T : rows = keys (g, g+8), columns = queries
+    qk_product(Vs, Gs, lane, dp);     // dP^T
+    float pt[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int qi = n * 8 + 2 * t + (c & 1);
+        const int key = g + (c >> 1) * 8;
+        const float p = (qi < nq && key < nkeys) ? __expf(s[n][c] * a.scale - lse_s[qi]) : 0.f;
+        pt[n][c] = p;
+        s[n][c] = p * (dp[n][c] - dl_s[qi]);
+      }
+    const uint32_t pa[4] = {pack2(pt[0][0], pt[0][1]), pack2(pt[0][2], pt[0][3]), pack2(pt[1][0], pt[1][1]), pack2(pt[1][2], pt[1][3])};
+    const uint32_t da[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
+    pv_product<NH>(pa, Gs, lane, nt0, accV);
+    pv_product<NH>(da, Qs, lane, nt0, accK);
+  }
+  __syncthreads();
+  acc_to_tile<NH>(Qs, lane, nt0, accK, a.scale, a.scale);   // Q / dO tiles are dead: transpose dK / dV through them
+  acc_to_tile<NH>(Gs, lane, nt0, accV, 1.f, 1.f);
+  __syncthreads();
+  store_rows(Qs, dk + col0, lddk, seg0 + k0, nkeys, nwords, lane, warp, 2);
+  store_rows(Gs, dv + col0, lddv, seg0 + k0, nkeys, nwords, lane, warp, 2);
+}
+
+template <typename K> int opt_in_smem(K kern, size_t bytes) {
+  if (bytes > 48 * 1024) NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return NLV_OK;
+}
+
+}  // namespace
+
+bool attn_mma_supported(int hd, int heads, int ld_or) {
+  // 4-byte copies need even strides / head widths; 256-column tiles; heads in groups of 4 for the forward CTA
+  return hd >= 16 && hd <= 256 && (hd & 1) == 0 && (heads & 3) == 0 && (ld_or & 1) == 0;
+}
+
+int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
+                        const void* work, int n_work, void* o, int ldo, float* lse, cudaStream_t s) {
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+  const size_t smem = 4 * 3 * TILE_B;
+  int rc = opt_in_smem(attn_fwd_mma_kernel, smem);
+  if (rc != NLV_OK) return rc;
+  attn_fwd_mma_kernel<<<(unsigned)n_work * (heads / 4), 128, smem, s>>>(a, (bf16*)o, ldo, lse);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
+                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, cudaStream_t s) {
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+  const size_t s1 = 2 * 4 * TILE_B, s2 = 4 * TILE_B;
+  int rc = opt_in_smem(attn_bwd_dq_mma_kernel, s1);
+  if (rc != NLV_OK) return rc;
+  attn_bwd_dq_mma_kernel<<<(unsigned)n_work * (heads / 2), 64, s1, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dq, lddq);
+  NLV_CHECK_LAUNCH();
+  attn_bwd_dkv_mma_kernel<<<(unsigned)n_work * heads, 64, s2, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dk, lddk, (bf16*)dv, lddv);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+}  // namespace nlv

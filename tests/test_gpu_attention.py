@@ -16,9 +16,11 @@ def _ref(q, k, v, segs, hd, heads):
     return out
 
 
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)])
-def test_attention_fwd_bwd_ragged(cuda_lib, dtype, tol):
+@pytest.mark.parametrize("dtype,tol,simt", [(torch.float32, 2e-5, True), (torch.bfloat16, 2e-2, True), (torch.bfloat16, 2e-2, False)])
+def test_attention_fwd_bwd_ragged(cuda_lib, monkeypatch, dtype, tol, simt):
+    """simt=True: the register-resident SIMT kernels (attn.cu); simt=False: the mma.sync tensor-core kernels for bf16 I/O (attn_mma.cu)."""
     from nlvsgg_b200 import ops
+    monkeypatch.setenv("NLV_ATTN_SIMT", "1" if simt else "0")
     from nlvsgg_b200.plan import work_items
     hd, heads = 242, 8
     lens = [1, 2, 3, 5, 7, 8, 9, 12, 15, 16, 17, 24, 31, 32, 33, 38, 47, 64, 65, 100]

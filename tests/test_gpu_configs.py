@@ -157,7 +157,7 @@ def test_c5_recall_over_a_test_split_shape(cuda_lib):
             # the split is a tiling of those 40 videos: every later copy repeats the same per-frame values
             period = ev.result_dict[name][k][:first]
             full = ev.result_dict[name][k]
-            assert full[first:2 * first] == period and full[42 * first:] == period[:len(full) - 42 * first]
+            assert full[first:2 * first] == period and full[43 * first:] == period[:len(full) - 43 * first]
     # order invariance: reversing the videos reverses the per-video blocks, the dataset mean is the same float
     ev2 = make_cuda_eval("sgdet")
     ev2.evaluate_videos([(base[j][1], to_cuda(base[j][0])) for j in reversed(order)])
