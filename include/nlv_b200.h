@@ -103,7 +103,7 @@ int nlv_im2col_3x3(const void* x, int x_dtype, int r, int h, int w, int c, void*
 int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, float* dx, void* stream);
 /* MaxPool2d(3,2,1) (lib/sttran.py:341) on NHWC [r,14,14,c] -> [r,7,7,c]; argmax u8 per output */
 int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dtype, uint8_t* argmax, void* stream);
-int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, float* dx, void* stream);
+int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, void* dx, int dx_dtype, void* stream);
 /* dst[i,:] = src[idx[i],:] (+ add[add_idx[i],:]); idx null = identity, idx<0 = zero row; optional 2nd output.
  * Builds the sliding-window token stream + frame position embedding (lib/transformer_wk.py:163-171) and the
  * DSG-DETR class sequences + sinusoidal encoding (lib/dsg_detr.py:545-559). */
@@ -141,7 +141,7 @@ int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, l
 int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const float* mean, const float* var,
                  const float* w, const float* b, float eps, int relu, long long rows, int c, void* y, int y_dtype, int ldy,
                  void* y2, int y2_dtype, int ldy2, void* stream);
-int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
+int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
                const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx,
                float* dw, float* db, void* stream);

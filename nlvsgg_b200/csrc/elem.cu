@@ -8,7 +8,7 @@ int launch_convert8(const void* src, int sdt, void* dst, int ddt, long long n, c
 int launch_im2col_3x3_v8(const void* x, int xdt, int r, int h, int w, int c, void* dst, int ddt, cudaStream_t s);
 int launch_col2im_3x3_v8(const void* dcol, int cdt, int r, int h, int w, int c, float* dx, cudaStream_t s);
 int launch_maxpool_fwd_v8(const void* x, int xdt, int r, int c, void* y, int ydt, uint8_t* arg, cudaStream_t s);
-int launch_maxpool_bwd_v8(const float* dy, const uint8_t* arg, int r, int c, float* dx, cudaStream_t s);
+int launch_maxpool_bwd_v8(const float* dy, const uint8_t* arg, int r, int c, void* dx, int dxdt, cudaStream_t s);
 int launch_im2col_mask_v8(const float* m, int r, void* dst, int ddt, int ld, cudaStream_t s);
 int launch_colsum_v8(const void* x, int xdt, int ld, long long rows, int cols, const int* row_class, int n_class, float* out,
                      cudaStream_t s);
@@ -189,7 +189,7 @@ __global__ void maxpool_fwd_kernel(const void* __restrict__ x, int xdt, int C, l
 
 // dx[r,iy,ix,c] = sum over the (<=4) pooling windows that contain (iy,ix) and selected it
 __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg, int C, long long total,
-                                   float* __restrict__ dx) {
+                                   void* __restrict__ dx, int dxdt) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -213,7 +213,7 @@ __global__ void maxpool_bwd_kernel(const float* __restrict__ dy, const uint8_t* 
       if (arg[o] == ky * 3 + kx) acc += dy[o];
     }
   }
-  dx[i] = acc;
+  st_from_float(dx, dxdt, (size_t)i, acc);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -442,12 +442,12 @@ int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dty
   return NLV_OK;
 }
 
-int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, float* dx, void* stream) {
+int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, void* dx, int dx_dtype, void* stream) {
   NLV_CHECK_ARG(r >= 0 && c > 0, "maxpool_bwd: bad sizes");
   if (r == 0) return NLV_OK;
-  if ((c & 7) == 0 && al16(dy) && al16(dx) && al16(argmax)) return launch_maxpool_bwd_v8(dy, argmax, r, c, dx, STREAM);
+  if ((c & 7) == 0 && al16(dy) && al16(dx) && al16(argmax)) return launch_maxpool_bwd_v8(dy, argmax, r, c, dx, dx_dtype, STREAM);
   const long long total = (long long)r * 196 * c;
-  maxpool_bwd_kernel<<<GRID1D(total)>>>(dy, argmax, c, total, dx);
+  maxpool_bwd_kernel<<<GRID1D(total)>>>(dy, argmax, c, total, dx, dx_dtype);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -63,14 +63,15 @@ __global__ void im2col_3x3_v8_kernel(const void* __restrict__ x, int xdt, int H,
 }
 
 // adjoint: dx[r,y,x,c] = sum_taps dcol[(r, y+1-ky, x+1-kx), tap*C + c]
+template <typename IT>
 __global__ void col2im_3x3_v8_kernel(const void* __restrict__ dcol, int cdt, int H, int W, int C8, long long total,
                                      float* __restrict__ dx) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pos = i / C8;
-  const int x = (int)(pos % W), y = (int)((pos / W) % H);
-  const long long r = pos / ((long long)H * W);
+  const IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (IT)total) return;
+  const int c8 = (int)(i % (IT)C8);
+  const IT pos = i / (IT)C8;
+  const int x = (int)(pos % (IT)W), y = (int)((pos / (IT)W) % (IT)H);
+  const IT r = pos / (IT)(H * W);
   V8 acc;
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
@@ -86,14 +87,15 @@ __global__ void col2im_3x3_v8_kernel(const void* __restrict__ dcol, int cdt, int
   st8(dx, NLV_F32, (size_t)i * 8, acc);
 }
 
+template <typename IT>
 __global__ void maxpool_fwd_v8_kernel(const void* __restrict__ x, int xdt, int C8, long long total, void* __restrict__ y, int ydt,
                                       uint8_t* __restrict__ arg) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pos = i / C8;
+  const IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (IT)total) return;
+  const int c8 = (int)(i % (IT)C8);
+  const IT pos = i / (IT)C8;
   const int ox = (int)(pos % 7), oy = (int)((pos / 7) % 7);
-  const long long r = pos / 49;
+  const IT r = pos / 49;
   V8 best;
   int bi[8];
 #pragma unroll
@@ -115,14 +117,15 @@ __global__ void maxpool_fwd_v8_kernel(const void* __restrict__ x, int xdt, int C
   *reinterpret_cast<uint2*>(arg + (size_t)i * 8) = packed;
 }
 
+template <typename IT>
 __global__ void maxpool_bwd_v8_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ arg, int C8, long long total,
-                                      float* __restrict__ dx) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  const long long pos = i / C8;
+                                      void* __restrict__ dx, int dxdt) {
+  const IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (IT)total) return;
+  const int c8 = (int)(i % (IT)C8);
+  const IT pos = i / (IT)C8;
   const int ix = (int)(pos % 14), iy = (int)((pos / 14) % 14);
-  const long long r = pos / 196;
+  const IT r = pos / 196;
   V8 acc;
 #pragma unroll
   for (int q = 0; q < 8; ++q) acc.v[q] = 0.f;
@@ -145,7 +148,7 @@ __global__ void maxpool_bwd_v8_kernel(const float* __restrict__ dy, const uint8_
       }
     }
   }
-  st8(dx, NLV_F32, (size_t)i * 8, acc);
+  st8(dx, dxdt, (size_t)i * 8, acc);
 }
 
 // im2col of the 2x27x27 masks, 8 output columns per thread (ld % 8 == 0)
@@ -169,6 +172,60 @@ __global__ void im2col_mask_v8_kernel(const float* __restrict__ m, long long tot
     v.v[q] = t;
   }
   st8(dst, ddt, (size_t)i * 8, v);
+}
+
+// Per-pair variants of the two im2col kernels for the shapes of the mask conv stack (bf16 output): the pair's input map is
+// parked in shared memory, every thread then writes consecutive 16-byte pieces of the pair's output rows, with 32-bit
+// constant-divisor index arithmetic only (the generic kernels above spend their time in 64-bit divisions).
+__global__ void __launch_bounds__(256)
+im2col_3x3_pair_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ dst) {
+  constexpr int HW = 49, C16 = 16, ROW16 = 9 * C16;            // 128 channels = 16 uint4; 1152 columns = 144 uint4
+  __shared__ uint4 tile[HW * C16];
+  const long long r = blockIdx.x;
+  const uint4* src = reinterpret_cast<const uint4*>(x) + r * (HW * C16);
+  for (int i = threadIdx.x; i < HW * C16; i += 256) tile[i] = src[i];
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(dst) + r * (HW * ROW16);
+  for (int e = threadIdx.x; e < HW * ROW16; e += 256) {
+    const int row = e / ROW16, q = e - row * ROW16;
+    const int tap = q >> 4, c16 = q & 15;
+    const int oy = row / 7, ox = row - oy * 7;
+    const int iy = oy - 1 + tap / 3, ix = ox - 1 + tap % 3;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (iy >= 0 && iy < 7 && ix >= 0 && ix < 7) v = tile[(iy * 7 + ix) * C16 + c16];
+    out[e] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+im2col_mask_pair_kernel(const float* __restrict__ m, __nv_bfloat16* __restrict__ dst) {
+  constexpr int LD8 = 13;                                      // 104 columns = 13 uint4 (98 used, 6 zero)
+  __shared__ float tile[2 * 27 * 27];
+  const long long r = blockIdx.x;
+  const float* src = m + r * (2 * 27 * 27);
+  for (int i = threadIdx.x; i < 2 * 27 * 27; i += 256) tile[i] = src[i];
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(dst) + r * (196 * LD8);
+  for (int e = threadIdx.x; e < 196 * LD8; e += 256) {
+    const int row = e / LD8, cb = (e - row * LD8) * 8;
+    const int oy = row / 14, ox = row - oy * 14;
+    float t[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int col = cb + q;
+      t[q] = 0.f;
+      if (col < 98) {
+        const int c = col / 49, rem = col - c * 49, ky = rem / 7, kx = rem - ky * 7;
+        const int iy = oy * 2 - 3 + ky, ix = ox * 2 - 3 + kx;
+        if (iy >= 0 && iy < 27 && ix >= 0 && ix < 27) t[q] = tile[(c * 27 + iy) * 27 + ix];
+      }
+    }
+    uint4 v;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(t[2 * q], t[2 * q + 1]);
+    out[e] = v;
+  }
 }
 
 // column sums with 8 channels per thread: block (C8x, 256/C8x) ; grid (ceil(C8/bx), row splits)
@@ -208,16 +265,16 @@ __global__ void colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, lo
 __global__ void gather_rows_v4_kernel(const float* __restrict__ src, int lds, const int* __restrict__ idx,
                                       const float* __restrict__ add, const int* __restrict__ add_idx, int ld_add, long long n_out,
                                       int cols4, float* __restrict__ dst, int ldd, void* __restrict__ dst2, int d2dt, int ldd2) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_out * cols4) return;
-  const long long r = i / cols4;
-  const int c = (int)(i - r * cols4) * 4;
+  // one row per CTA (no index division); the row's source indices are read once
+  const long long r = blockIdx.x;
   const int s = idx ? idx[r] : (int)r;
+  const int sa = add != nullptr ? (add_idx ? add_idx[r] : (int)r) : 0;
+  for (int c = threadIdx.x * 4; c < cols4 * 4; c += blockDim.x * 4) {
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s >= 0) {
     v = *reinterpret_cast<const float4*>(src + (size_t)s * lds + c);
     if (add != nullptr) {
-      const float4 a = *reinterpret_cast<const float4*>(add + (size_t)(add_idx ? add_idx[r] : (int)r) * ld_add + c);
+      const float4 a = *reinterpret_cast<const float4*>(add + (size_t)sa * ld_add + c);
       v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
     }
   }
@@ -231,6 +288,7 @@ __global__ void gather_rows_v4_kernel(const float* __restrict__ src, int lds, co
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(dst2) + (size_t)r * ldd2 + c) = v;
     }
   }
+  }
 }
 
 }  // namespace
@@ -243,6 +301,11 @@ int launch_convert8(const void* src, int sdt, void* dst, int ddt, long long n, c
   return NLV_OK;
 }
 int launch_im2col_3x3_v8(const void* x, int xdt, int r, int h, int w, int c, void* dst, int ddt, cudaStream_t s) {
+  if (xdt == NLV_BF16 && ddt == NLV_BF16 && h == 7 && w == 7 && c == 128) {
+    im2col_3x3_pair_kernel<<<r, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)dst);
+    NLV_CHECK_LAUNCH();
+    return NLV_OK;
+  }
   const long long total = (long long)r * h * w * 9 * (c / 8);
   im2col_3x3_v8_kernel<<<GRIDV(total)>>>(x, xdt, h, w, c / 8, total, dst, ddt);
   NLV_CHECK_LAUNCH();
@@ -250,23 +313,31 @@ int launch_im2col_3x3_v8(const void* x, int xdt, int r, int h, int w, int c, voi
 }
 int launch_col2im_3x3_v8(const void* dcol, int cdt, int r, int h, int w, int c, float* dx, cudaStream_t s) {
   const long long total = (long long)r * h * w * (c / 8);
-  col2im_3x3_v8_kernel<<<GRIDV(total)>>>(dcol, cdt, h, w, c / 8, total, dx);
+  if (total < (1ll << 31)) col2im_3x3_v8_kernel<unsigned><<<GRIDV(total)>>>(dcol, cdt, h, w, c / 8, total, dx);
+  else col2im_3x3_v8_kernel<long long><<<GRIDV(total)>>>(dcol, cdt, h, w, c / 8, total, dx);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 int launch_maxpool_fwd_v8(const void* x, int xdt, int r, int c, void* y, int ydt, uint8_t* arg, cudaStream_t s) {
   const long long total = (long long)r * 49 * (c / 8);
-  maxpool_fwd_v8_kernel<<<GRIDV(total)>>>(x, xdt, c / 8, total, y, ydt, arg);
+  if (total < (1ll << 31)) maxpool_fwd_v8_kernel<unsigned><<<GRIDV(total)>>>(x, xdt, c / 8, total, y, ydt, arg);
+  else maxpool_fwd_v8_kernel<long long><<<GRIDV(total)>>>(x, xdt, c / 8, total, y, ydt, arg);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
-int launch_maxpool_bwd_v8(const float* dy, const uint8_t* arg, int r, int c, float* dx, cudaStream_t s) {
+int launch_maxpool_bwd_v8(const float* dy, const uint8_t* arg, int r, int c, void* dx, int dxdt, cudaStream_t s) {
   const long long total = (long long)r * 196 * (c / 8);
-  maxpool_bwd_v8_kernel<<<GRIDV(total)>>>(dy, arg, c / 8, total, dx);
+  if (total < (1ll << 31)) maxpool_bwd_v8_kernel<unsigned><<<GRIDV(total)>>>(dy, arg, c / 8, total, dx, dxdt);
+  else maxpool_bwd_v8_kernel<long long><<<GRIDV(total)>>>(dy, arg, c / 8, total, dx, dxdt);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 int launch_im2col_mask_v8(const float* m, int r, void* dst, int ddt, int ld, cudaStream_t s) {
+  if (ddt == NLV_BF16 && ld == 104) {
+    im2col_mask_pair_kernel<<<r, 256, 0, s>>>(m, (__nv_bfloat16*)dst);
+    NLV_CHECK_LAUNCH();
+    return NLV_OK;
+  }
   const long long total = (long long)r * 196 * (ld / 8);
   im2col_mask_v8_kernel<<<GRIDV(total)>>>(m, total, dst, ddt, ld / 8);
   NLV_CHECK_LAUNCH();
@@ -287,8 +358,7 @@ int launch_colsum_v8(const void* x, int xdt, int ld, long long rows, int cols, c
 }
 int launch_gather_rows_v4(const float* src, int lds, const int* idx, const float* add, const int* add_idx, int ld_add,
                           long long n_out, int cols, float* dst, int ldd, void* dst2, int d2dt, int ldd2, cudaStream_t s) {
-  const long long total = n_out * (cols / 4);
-  gather_rows_v4_kernel<<<GRIDV(total)>>>(src, lds, idx, add, add_idx, ld_add, n_out, cols / 4, dst, ldd, dst2, d2dt, ldd2);
+  gather_rows_v4_kernel<<<(unsigned)n_out, 128, 0, s>>>(src, lds, idx, add, add_idx, ld_add, n_out, cols / 4, dst, ldd, dst2, d2dt, ldd2);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

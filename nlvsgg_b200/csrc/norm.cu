@@ -197,7 +197,7 @@ __global__ void bn_apply_kernel(const void* __restrict__ x, int xdt, int ldx, co
 }
 
 // backward pass 1: per (segment, channel) sum(dy) and sum(dy * xhat), with the optional ReLU mask (y_out > 0)
-__global__ void bn_bwd_stats_kernel(const float* __restrict__ dy, int lddy, const void* __restrict__ x, int xdt, int ldx,
+__global__ void bn_bwd_stats_kernel(const void* __restrict__ dy, int dydt, int lddy, const void* __restrict__ x, int xdt, int ldx,
                                     const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ seg,
                                     const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
                                     double* __restrict__ sums /*[nseg,2,C]*/) {
@@ -210,7 +210,7 @@ __global__ void bn_bwd_stats_kernel(const float* __restrict__ dy, int lddy, cons
   if (c < C) {
     const float m = mean[(size_t)s * C + c], rs = rsqrtf(var[(size_t)s * C + c] + eps);
     for (long long r = r0 + threadIdx.y; r < r1; r += 8) {
-      float d = dy[(size_t)r * lddy + c];
+      float d = ld_as_float(dy, dydt, (size_t)r * lddy + c);
       if (yout != nullptr && !(ld_as_float(yout, ydt, (size_t)r * ldy + c) > 0.f)) d = 0.f;
       const float xh = (ld_as_float(x, xdt, (size_t)r * ldx + c) - m) * rs;
       s1 += (double)d; s2 += (double)d * (double)xh;
@@ -231,7 +231,7 @@ __global__ void bn_bwd_stats_kernel(const float* __restrict__ dy, int lddy, cons
 
 // backward pass 2 (training statistics): dx = w*rstd*(dy - sum_dy/n - xhat*sum_dy_xhat/n)
 // eval statistics (use_batch_stats=0): dx = w*rstd*dy.  Output dtype selectable (operand for the next GEMM).
-__global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, const void* __restrict__ x, int xdt, int ldx,
+__global__ void bn_bwd_apply_kernel(const void* __restrict__ dy, int dydt, int lddy, const void* __restrict__ x, int xdt, int ldx,
                                     const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
                                     const int* __restrict__ seg, const float* __restrict__ mean,
                                     const float* __restrict__ var, const float* __restrict__ w, float eps,
@@ -243,7 +243,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, int lddy, cons
   const int c = (int)(i - r * C);
   const int s = row_seg ? row_seg[r] : 0;
   const float m = mean[(size_t)s * C + c], rs = rsqrtf(var[(size_t)s * C + c] + eps);
-  float d = dy[(size_t)r * lddy + c];
+  float d = ld_as_float(dy, dydt, (size_t)r * lddy + c);
   if (yout != nullptr && !(ld_as_float(yout, ydt, (size_t)r * ldy + c) > 0.f)) d = 0.f;
   float o;
   if (use_batch_stats) {
@@ -282,12 +282,12 @@ int bn_splits(const int* /*seg device*/, long long rows, int nseg) {
 
 // 16-byte vectorised variants (norm_vec.cu), used when C % 8 == 0 and everything is 16-byte aligned
 int launch_bn_sums_fwd_v8(const void* x, int xdt, int ld, const int* seg, int nseg, long long rows, int C, double* sums, cudaStream_t s);
-int launch_bn_sums_bwd_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
+int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
                           int nseg, const float* mean, const float* var, float eps, long long rows, int C, double* sums, cudaStream_t s);
 int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
                        const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
                        int ldy2, cudaStream_t s);
-int launch_bn_bwd_apply_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
+int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
                            const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s);
@@ -377,9 +377,9 @@ int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const 
   return NLV_OK;
 }
 
-/* Backward.  yout (optional) = the ReLU'd forward output, masks dy (Linear -> BN -> ReLU).  gate_by_x: zero dx where x <= 0
+/* Backward.  dy: fp32 or bf16.  yout (optional) = the ReLU'd forward output, masks dy (Linear -> BN -> ReLU).  gate_by_x: zero dx where x <= 0
  * (conv -> ReLU -> BN: x is the ReLU output, so this is the ReLU backward fused in).  dw/db accumulated.  sums_ws as in bn_stats. */
-int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
+int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
                const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
                float* db, void* stream) {
@@ -391,16 +391,16 @@ int nlv_bn_bwd(const float* dy, int lddy, const void* x, int x_dtype, int ldx, c
   const bool vec = (c & 7) == 0 && (lddy & 7) == 0 && (ldx & 7) == 0 && (ldy & 7) == 0 && (lddx & 7) == 0 && al16(dy) && al16(x) &&
                    al16(yout) && al16(dx) && al16(mean) && al16(var) && al16(w);
   if (vec) {
-    int rc = launch_bn_sums_bwd_v8(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, nseg, mean, var, eps, rows, c, sums_ws, STREAM);
+    int rc = launch_bn_sums_bwd_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, nseg, mean, var, eps, rows, c, sums_ws, STREAM);
     if (rc != NLV_OK) return rc;
-    rc = launch_bn_bwd_apply_v8(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean, var, w, eps, sums_ws, use_batch_stats,
+    rc = launch_bn_bwd_apply_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean, var, w, eps, sums_ws, use_batch_stats,
                                 gate_by_x, rows, c, dx, dx_dtype, lddx, STREAM);
     if (rc != NLV_OK) return rc;
   } else {
     dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
-    bn_bwd_stats_kernel<<<grid, block, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, mean, var, eps, c, sums_ws);
+    bn_bwd_stats_kernel<<<grid, block, 0, STREAM>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, mean, var, eps, c, sums_ws);
     NLV_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean,
+    bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean,
                                                                 var, w, eps, sums_ws, use_batch_stats, gate_by_x, rows, c, dx, dx_dtype,
                                                                 lddx);
     NLV_CHECK_LAUNCH();

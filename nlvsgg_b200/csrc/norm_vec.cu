@@ -36,7 +36,7 @@ namespace {
 // per (segment, channel) sums: block (bx = min(C8,32) channel groups, by rows); grid (ceil(C8/bx), nseg, splits).
 // MODE 0: sum x, sum x^2 (forward statistics).  MODE 1: sum dy, sum dy*xhat (backward), optional ReLU mask by yout.
 template <int MODE>
-__global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const float* __restrict__ dy, int lddy,
+__global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const void* __restrict__ dy, int dydt, int lddy,
                                   const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ seg,
                                   const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
                                   double* __restrict__ sums) {
@@ -66,7 +66,7 @@ __global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, 
 #pragma unroll
       for (int q = 0; q < 8; ++q) { f1[q] += xv.v[q]; f2[q] = fmaf(xv.v[q], xv.v[q], f2[q]); }
     } else {
-      V8 g = nv_ld8(dy, NLV_F32, (size_t)r * lddy + (size_t)c8 * 8);
+      V8 g = nv_ld8(dy, dydt, (size_t)r * lddy + (size_t)c8 * 8);
       if (yout != nullptr) {
         const V8 yo = nv_ld8(yout, ydt, (size_t)r * ldy + (size_t)c8 * 8);
 #pragma unroll
@@ -175,7 +175,7 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __re
 // yout on dy, optional ReLU gate by `x > 0` on the RESULT (ReLU that precedes the BN: conv -> ReLU -> BN).
 template <int U>
 __global__ void __launch_bounds__(128)
-bn_bwd_apply_v8_kernel(const float* __restrict__ dy, int lddy, const void* __restrict__ x, int xdt, int ldx,
+bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt, int lddy, const void* __restrict__ x, int xdt, int ldx,
                        const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
                        const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
@@ -195,7 +195,7 @@ bn_bwd_apply_v8_kernel(const float* __restrict__ dy, int lddy, const void* __res
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
         xv[u] = nv_ld8(x, xdt, (size_t)rr * ldx + c0);
-        g[u] = nv_ld8(dy, NLV_F32, (size_t)rr * lddy + c0);
+        g[u] = nv_ld8(dy, dydt, (size_t)rr * lddy + c0);
         if (yout != nullptr) yo[u] = nv_ld8(yout, ydt, (size_t)rr * ldy + c0);
         sg[u] = row_seg ? row_seg[rr] : 0;
       }
@@ -250,15 +250,15 @@ void sums_geometry(int C, long long rows, int nseg, dim3& grid, dim3& block) {
 int launch_bn_sums_fwd_v8(const void* x, int xdt, int ld, const int* seg, int nseg, long long rows, int C, double* sums, cudaStream_t s) {
   dim3 grid, block;
   sums_geometry(C, rows, nseg, grid, block);
-  bn_sums_v8_kernel<0><<<grid, block, 0, s>>>(x, xdt, ld, nullptr, 0, nullptr, 0, 0, seg, nullptr, nullptr, 0.f, C, sums);
+  bn_sums_v8_kernel<0><<<grid, block, 0, s>>>(x, xdt, ld, nullptr, 0, 0, nullptr, 0, 0, seg, nullptr, nullptr, 0.f, C, sums);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
-int launch_bn_sums_bwd_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
+int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
                           int nseg, const float* mean, const float* var, float eps, long long rows, int C, double* sums, cudaStream_t s) {
   dim3 grid, block;
   sums_geometry(C, rows, nseg, grid, block);
-  bn_sums_v8_kernel<1><<<grid, block, 0, s>>>(x, xdt, ldx, dy, lddy, yout, ydt, ldy, seg, mean, var, eps, C, sums);
+  bn_sums_v8_kernel<1><<<grid, block, 0, s>>>(x, xdt, ldx, dy, dydt, lddy, yout, ydt, ldy, seg, mean, var, eps, C, sums);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
@@ -271,12 +271,12 @@ int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, cons
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
-int launch_bn_bwd_apply_v8(const float* dy, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
+int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
                            const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s) {
   const ApplyGeom g = apply_geometry(C, rows, 2);
-  bn_bwd_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(dy, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+  bn_bwd_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
                                                       use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
   NLV_CHECK_LAUNCH();
   return NLV_OK;

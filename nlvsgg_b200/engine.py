@@ -355,7 +355,7 @@ def pair_tokens_bwd(k: Kernels, P: dict, plan: Plan, c: dict, drel, grads: dict)
     grads["vr_fc.weight"] = _unperm_vr(k.mm(dvr, vr_in2d, a_major=MN_, b_major=MN_))
     grads["vr_fc.bias"] = ops.colsum(drel[:, 1024:1536]).reshape(-1)
     w_vr = k.weight("vr_fc.weight", P["vr_fc.weight"], _perm_vr)
-    dvr_in = k.mm(dvr, w_vr, b_major=MN_).view(R * 49, 256)                          # fp32
+    dvr_in = k.mm(dvr, w_vr, b_major=MN_, out_dtype=k.AD).view(R * 49, 256)          # activation dtype: feeds a GEMM, a column sum and BN backward
     dvr_op = k.opnd(dvr_in)
     grads["union_func1.weight"] = k.mm(dvr_op, c["uf_op"], a_major=MN_, b_major=MN_).view(256, 2048, 1, 1)
     grads["union_func1.bias"] = ops.colsum(dvr_in).reshape(-1)
@@ -367,7 +367,7 @@ def pair_tokens_bwd(k: Kernels, P: dict, plan: Plan, c: dict, drel, grads: dict)
     w_c4 = k.weight("conv.4.weight.taps", P["conv.4.weight"], _perm_c4)
     dcol2 = k.mm(dc2, w_c4, b_major=MN_, out_dtype=k.AD)
     dp1 = ops.col2im_3x3(dcol2, R, 7, 7, 128)
-    db1 = ops.maxpool_bwd(dp1, c["arg"], R, 128)
+    db1 = ops.maxpool_bwd(dp1, c["arg"], R, 128, k.AD)
     dc1, dw, db = ops.bn_bwd(db1, c["c1"], None, plan.seg196, plan.row196, plan.nv, c["mean2"], c["var2"],
                              P["conv.2.weight"], tr, dx_dtype=k.AD, gate_by_x=True)
     grads["conv.2.weight"], grads["conv.2.bias"] = dw, db

@@ -200,9 +200,10 @@ def maxpool_fwd(x: torch.Tensor, r: int, c: int, dtype: torch.dtype):
     return y, arg
 
 
-def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, r: int, c: int) -> torch.Tensor:
-    dx = torch.empty(r * 196, c, device=dy.device, dtype=torch.float32)
-    _call("nlv_maxpool_bwd", _ptr(dy), _ptr(arg), r, c, _ptr(dx))
+def maxpool_bwd(dy: torch.Tensor, arg: torch.Tensor, r: int, c: int, out_dtype=torch.float32) -> torch.Tensor:
+    assert dy.dtype == torch.float32
+    dx = torch.empty(r * 196, c, device=dy.device, dtype=out_dtype)
+    _call("nlv_maxpool_bwd", _ptr(dy), _ptr(arg), r, c, _ptr(dx), _dt(dx))
     return dx
 
 
@@ -312,7 +313,7 @@ def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dt
     dx = torch.empty(rows, c, device=x.device, dtype=dx_dtype)
     dw = torch.zeros(c, device=x.device, dtype=torch.float32)
     db = torch.zeros(c, device=x.device, dtype=torch.float32)
-    _call("nlv_bn_bwd", _ptr(dy), dy.stride(0), _ptr(x), _dt(x), x.stride(0), _ptr(yout),
+    _call("nlv_bn_bwd", _ptr(dy), _dt(dy), dy.stride(0), _ptr(x), _dt(x), x.stride(0), _ptr(yout),
           _dt(yout) if yout is not None else 0, yout.stride(0) if yout is not None else 0, _ptr(seg), _ptr(row_seg), nseg,
           _ptr(mean), _ptr(var), _ptr(w), _F(eps), 1 if use_batch_stats else 0, 1 if gate_by_x else 0, _LL(rows), c, _ptr(ws), _ptr(dx),
           _dt(dx), c,
