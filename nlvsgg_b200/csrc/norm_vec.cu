@@ -31,6 +31,33 @@ __device__ __forceinline__ void nv_st8(void* p, int dt, size_t i, const V8& r) {
   }
 }
 
+// raw (still packed) 8-element load: 16 bytes for bf16, 32 for fp32; unpacked at the point of use so that several rows
+// can be in flight per thread without holding their fp32 expansions in registers
+struct R8 { uint4 a, b; };
+__device__ __forceinline__ R8 nv_ld8_raw(const void* p, int dt, size_t i) {
+  R8 r;
+  if (dt == NLV_BF16) {
+    r.a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p) + i);
+    r.b = make_uint4(0u, 0u, 0u, 0u);
+  } else {
+    r.a = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p) + i);
+    r.b = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(p) + i + 4);
+  }
+  return r;
+}
+__device__ __forceinline__ V8 nv_unpack(const R8& r, int dt) {
+  V8 o;
+  if (dt == NLV_BF16) {
+    const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { o.v[2 * q] = __uint_as_float(w[q] << 16); o.v[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+  } else {
+    o.v[0] = __uint_as_float(r.a.x); o.v[1] = __uint_as_float(r.a.y); o.v[2] = __uint_as_float(r.a.z); o.v[3] = __uint_as_float(r.a.w);
+    o.v[4] = __uint_as_float(r.b.x); o.v[5] = __uint_as_float(r.b.y); o.v[6] = __uint_as_float(r.b.z); o.v[7] = __uint_as_float(r.b.w);
+  }
+  return o;
+}
+
 namespace {
 
 // per (segment, channel) sums: block (bx = min(C8,32) channel groups, by rows); grid (ceil(C8/bx), nseg, splits).
@@ -125,12 +152,13 @@ ApplyGeom apply_geometry(int C, long long rows, int unroll) {
   return g;
 }
 
-template <int U>
+template <int U, bool BF>   // BF: x is bf16 (known at compile time: the raw row buffers shrink to 16 bytes)
 __global__ void __launch_bounds__(128)
-bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __restrict__ row_seg,
+bn_apply_v8_kernel(const void* __restrict__ x, int xdt_rt, int ldx, const int* __restrict__ row_seg,
                    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ w,
                    const float* __restrict__ b, float eps, int relu, long long rows, long long rows_per_block, int C,
                    void* __restrict__ y, int ydt, int ldy, void* __restrict__ y2, int y2dt, int ldy2) {
+  const int xdt = BF ? NLV_BF16 : xdt_rt;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 >= (C >> 3)) return;
   const int c0 = c8 * 8;
@@ -139,13 +167,13 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __re
   int cur = -1;
   float m[8], k[8];
   for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
-    V8 xv[U];
+    R8 xr[U];
     int sg[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
-        xv[u] = nv_ld8(x, xdt, (size_t)rr * ldx + c0);
+        xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + c0);
         sg[u] = row_seg ? row_seg[rr] : 0;
       }
     }
@@ -159,10 +187,11 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __re
 #pragma unroll
         for (int q = 0; q < 8; ++q) { m[q] = mm.v[q]; k[q] = rsqrtf(vv.v[q] + eps) * ww.v[q]; }
       }
+      const V8 xv1 = nv_unpack(xr[u], xdt);
       V8 o;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        o.v[q] = fmaf(xv[u].v[q] - m[q], k[q], bb.v[q]);
+        o.v[q] = fmaf(xv1.v[q] - m[q], k[q], bb.v[q]);
         if (relu) o.v[q] = fmaxf(o.v[q], 0.f);
       }
       if (y) nv_st8(y, ydt, (size_t)rr * ldy + c0, o);
@@ -173,13 +202,14 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __re
 
 // dx = w*rstd*(dy - sum_dy/n - xhat*sum_dy_xhat/n) [batch stats] or w*rstd*dy [running stats]; optional ReLU mask by
 // yout on dy, optional ReLU gate by `x > 0` on the RESULT (ReLU that precedes the BN: conv -> ReLU -> BN).
-template <int U>
+template <int U, bool BF>   // BF: dy, x and yout are all bf16
 __global__ void __launch_bounds__(128)
-bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt, int lddy, const void* __restrict__ x, int xdt, int ldx,
-                       const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
+bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const void* __restrict__ x, int xdt_rt, int ldx,
+                       const void* __restrict__ yout, int ydt_rt, int ldy, const int* __restrict__ row_seg,
                        const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
                        int gate_by_x, long long rows, long long rows_per_block, int C, void* __restrict__ dx, int dxdt, int lddx) {
+  const int dydt = BF ? NLV_BF16 : dydt_rt, xdt = BF ? NLV_BF16 : xdt_rt, ydt = BF ? NLV_BF16 : ydt_rt;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   if (c8 >= (C >> 3)) return;
   const int c0 = c8 * 8;
@@ -188,15 +218,15 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt, int lddy, const vo
   int cur = -1;
   float m[8], k[8], s1[8], t2[8];   // k = w*rstd, s1 = sum_dy/n, t2 = rstd*sum_dy_xhat/n
   for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
-    V8 xv[U], g[U], yo[U];
+    R8 xr[U], gr[U], yr[U];
     int sg[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
-        xv[u] = nv_ld8(x, xdt, (size_t)rr * ldx + c0);
-        g[u] = nv_ld8(dy, dydt, (size_t)rr * lddy + c0);
-        if (yout != nullptr) yo[u] = nv_ld8(yout, ydt, (size_t)rr * ldy + c0);
+        xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + c0);
+        gr[u] = nv_ld8_raw(dy, dydt, (size_t)rr * lddy + c0);
+        if (yout != nullptr) yr[u] = nv_ld8_raw(yout, ydt, (size_t)rr * ldy + c0);
         sg[u] = row_seg ? row_seg[rr] : 0;
       }
     }
@@ -219,13 +249,16 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt, int lddy, const vo
           } else { s1[q] = 0.f; t2[q] = 0.f; }
         }
       }
+      const V8 xv1 = nv_unpack(xr[u], xdt), g1 = nv_unpack(gr[u], dydt);
+      V8 yo1;
+      if (yout != nullptr) yo1 = nv_unpack(yr[u], ydt);
       V8 o;
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        float gq = g[u].v[q];
-        if (yout != nullptr && !(yo[u].v[q] > 0.f)) gq = 0.f;
-        o.v[q] = k[q] * (gq - s1[q] - (xv[u].v[q] - m[q]) * t2[q]);
-        if (gate_by_x && !(xv[u].v[q] > 0.f)) o.v[q] = 0.f;
+        float gq = g1.v[q];
+        if (yout != nullptr && !(yo1.v[q] > 0.f)) gq = 0.f;
+        o.v[q] = k[q] * (gq - s1[q] - (xv1.v[q] - m[q]) * t2[q]);
+        if (gate_by_x && !(xv1.v[q] > 0.f)) o.v[q] = 0.f;
       }
       nv_st8(dx, dxdt, (size_t)rr * lddx + c0, o);
     }
@@ -265,9 +298,15 @@ int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int
 int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
                        const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
                        int ldy2, cudaStream_t s) {
-  const ApplyGeom g = apply_geometry(C, rows, 2);
-  bn_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
-                                                  ldy, y2, y2dt, ldy2);
+  if (xdt == NLV_BF16) {
+    const ApplyGeom g = apply_geometry(C, rows, 4);
+    bn_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
+                                                          ldy, y2, y2dt, ldy2);
+  } else {
+    const ApplyGeom g = apply_geometry(C, rows, 2);
+    bn_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
+                                                           ldy, y2, y2dt, ldy2);
+  }
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
@@ -275,9 +314,15 @@ int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, in
                            const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s) {
-  const ApplyGeom g = apply_geometry(C, rows, 2);
-  bn_bwd_apply_v8_kernel<2><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
-                                                      use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+  if (dydt == NLV_BF16 && xdt == NLV_BF16 && (yout == nullptr || ydt == NLV_BF16)) {
+    const ApplyGeom g = apply_geometry(C, rows, 4);
+    bn_bwd_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+                                                              use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+  } else {
+    const ApplyGeom g = apply_geometry(C, rows, 2);
+    bn_bwd_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+                                                               use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+  }
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
