@@ -149,6 +149,11 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
 /* ------------------------------------------------------------------------------------------
  * Fused variable-length attention over contiguous segments (nn.MultiheadAttention core of
  * lib/transformer.py:22,51 and nn.TransformerEncoderLayer of lib/dsg_detr.py:502-506)
+ * work: int4[n_work] = {segment first row, segment length, first row of the item inside the segment, 0}; a segment of
+ * length L is covered by ceil(L/16) items.  q/k/v: row-major [rows, >= heads*hd], head h at column h*hd, hd even, <= 256.
+ * lse: float[rows*heads] (written by fwd, read by bwd).  delta: float[rows*heads] workspace of bwd.
+ * bf16 in / bf16 out with heads % 4 == 0 runs on mma.sync tensor cores (csrc/attn_mma.cu); every other combination of
+ * fp32 / bf16 on the register-resident SIMT kernels (csrc/attn.cu; NLV_ATTN_SIMT=1 forces them).
  * ------------------------------------------------------------------------------------------ */
 int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
                  float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, void* stream);

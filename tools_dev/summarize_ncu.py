@@ -59,8 +59,10 @@ def wide_rows(path):
 def launches():
     path = os.path.join(GO, "launches_r1.csv")
     rows = long_rows(path)
-    n = len(rows) // STEPS_IN_RUN
-    last = rows[-n:]          # the last step of the run: warm code, cold data (ncu serialises and flushes between launches)
+    # the last step of the run = everything after the second-to-last AdamW launch (AdamW is the final kernel of a step)
+    ad = [i for i, d in enumerate(rows) if "adamw_kernel" in d["kernel"]]
+    last = rows[ad[-2] + 1: ad[-1] + 1] if len(ad) >= 2 else rows[-(len(rows) // STEPS_IN_RUN):]
+    n = len(last)
     agg = collections.defaultdict(lambda: [0, 0.0])
     for d in last:
         a = agg[short(d["kernel"])]
