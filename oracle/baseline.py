@@ -50,7 +50,7 @@ def cpu_train_step(sd: Dict[str, torch.Tensor], entries: List[dict], mode: str, 
         pred = fwd(sd, e, mode, training=True)
         loss = omodel.training_loss(pred, e, mode) / len(entries)
         loss.backward()
-        total += float(loss)
+        total += float(loss.detach())
     adamw_update(params, opt_state)
     return total
 
