@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError(f"nvcc failed for {s}:\n{out}")
         if verbose and out.strip():
             print(out)
-    subprocess.run(["nvcc", "-shared", "-o", SO_PATH] + objs, check=True)
+    subprocess.run(["nvcc", "-Wno-deprecated-gpu-targets", "-shared", "-o", SO_PATH] + objs, check=True)
     return SO_PATH
 
 
