@@ -92,9 +92,9 @@ int nlv_convert(const void* src, int src_dtype, int lds, void* dst, int dst_dtyp
  * pattern 0 = (hi,hi,lo) for A operands, 1 = (hi,lo,hi) for B operands */
 int nlv_split3(const float* src, int lds, long long rows, int cols, void* dst_bf16, int ldd, int block_dim, int pattern,
                void* stream);
-/* union_feat f32[r,c,7,7] (NCHW, as the reference producer hands it) -> [r*49, c] rows (operand of the
- * union_func1 1x1 conv, lib/sttran.py:336,386) */
-int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_dtype, void* stream);
+/* union_feat [r,c,7,7] (NCHW; f32 as the reference producer hands it, or bf16 from packed feature files) ->
+ * [r*49, c] rows (operand of the union_func1 1x1 conv, lib/sttran.py:336,386) */
+int nlv_nchw_to_rows(const void* src, int src_dtype, int r, int c, int hw, void* dst, int dst_dtype, void* stream);
 /* im2col of the 2x27x27 spatial masks for Conv2d(2,128,k7,s2,p3) (lib/sttran.py:338): -> [r*196, ldd], 98 cols */
 int nlv_im2col_mask(const float* masks, int r, void* dst, int dst_dtype, int ldd, void* stream);
 /* im2col / col2im of the 3x3 s1 p1 conv (lib/sttran.py:342) over NHWC [r,h,w,c]; column = (ky*3+kx)*c_total + c

@@ -60,12 +60,12 @@ __global__ void split3_kernel(const float* __restrict__ src, int lds, long long 
 // One CTA per (pair, 64-channel slab): reads 64 x HW floats contiguously, writes HW rows of 64.
 // ------------------------------------------------------------------------------------------
 template <int HW>
-__global__ void nchw_to_rows_kernel(const float* __restrict__ src, int C, void* __restrict__ dst, int ddt) {
+__global__ void nchw_to_rows_kernel(const void* __restrict__ src, int sdt, int C, void* __restrict__ dst, int ddt) {
   __shared__ float tile[64][HW + 1];
   const int r = blockIdx.y, c0 = blockIdx.x * 64;
-  const float* s = src + ((size_t)r * C + c0) * HW;
+  const size_t s0 = ((size_t)r * C + c0) * HW;
   const int nch = min(64, C - c0);
-  for (int i = threadIdx.x; i < nch * HW; i += blockDim.x) tile[i / HW][i % HW] = s[i];
+  for (int i = threadIdx.x; i < nch * HW; i += blockDim.x) tile[i / HW][i % HW] = ld_as_float(src, sdt, s0 + i);
   __syncthreads();
   for (int i = threadIdx.x; i < HW * 64; i += blockDim.x) {
     const int hw = i >> 6, c = i & 63;
@@ -99,6 +99,36 @@ nchw_to_rows_bf16_kernel(const float* __restrict__ src, int C, __nv_bfloat16* __
   for (int e = threadIdx.x; e < HW * (CS / 2); e += 256) {
     const int hw = e >> 6, c = (e & 63) * 2;
     *reinterpret_cast<__nv_bfloat162*>(d + (size_t)hw * C + c) = __floats2bfloat162_rn(tile[c * HW + hw], tile[(c + 1) * HW + hw]);
+  }
+}
+
+// same for a bf16 source (packed per-video feature files, SURVEY 8f-2: the loader hands bf16, halving the host -> device bytes)
+__global__ void __launch_bounds__(256)
+nchw_to_rows_bf16in_kernel(const __nv_bfloat16* __restrict__ src, int C, __nv_bfloat16* __restrict__ dst) {
+  constexpr int HW = 49, CS = 128, NU4 = CS * HW / 8;   // 784 uint4 per slab
+  __shared__ __align__(16) __nv_bfloat16 tile[CS * HW];
+  const int r = blockIdx.y, c0 = blockIdx.x * CS;
+  const uint4* s4 = reinterpret_cast<const uint4*>(src + ((size_t)r * C + c0) * HW);
+  uint4 v[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < NU4) v[k] = __ldcs(s4 + i);
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int i = threadIdx.x + 256 * k;
+    if (i < NU4) reinterpret_cast<uint4*>(tile)[i] = v[k];
+  }
+  __syncthreads();
+  __nv_bfloat16* d = dst + (size_t)r * HW * C + c0;
+#pragma unroll 5
+  for (int e = threadIdx.x; e < HW * (CS / 2); e += 256) {
+    const int hw = e >> 6, c = (e & 63) * 2;
+    __nv_bfloat162 o;
+    o.x = tile[c * HW + hw];
+    o.y = tile[(c + 1) * HW + hw];
+    *reinterpret_cast<__nv_bfloat162*>(d + (size_t)hw * C + c) = o;
   }
 }
 
@@ -384,7 +414,7 @@ int nlv_split3(const float* src, int lds, long long rows, int cols, void* dst, i
   return NLV_OK;
 }
 
-int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_dtype, void* stream) {
+int nlv_nchw_to_rows(const void* src, int src_dtype, int r, int c, int hw, void* dst, int dst_dtype, void* stream) {
   NLV_CHECK_ARG(r >= 0 && c > 0, "nchw_to_rows: bad sizes");
   NLV_CHECK_ARG(hw == 49, "nchw_to_rows: only 7x7 maps are supported (hw=%d)", hw);
   if (r == 0) return NLV_OK;
@@ -392,12 +422,13 @@ int nlv_nchw_to_rows(const float* src, int r, int c, int hw, void* dst, int dst_
   NLV_CHECK_ARG(r <= 65535, "nchw_to_rows: r=%d exceeds the grid limit; split the call", r);
   if (dst_dtype == NLV_BF16 && (c & 127) == 0 && al16(src) && (reinterpret_cast<uintptr_t>(dst) & 3) == 0) {
     dim3 grid(c / 128, r);
-    nchw_to_rows_bf16_kernel<<<grid, 256, 0, STREAM>>>(src, c, (__nv_bfloat16*)dst);
+    if (src_dtype == NLV_BF16) nchw_to_rows_bf16in_kernel<<<grid, 256, 0, STREAM>>>((const __nv_bfloat16*)src, c, (__nv_bfloat16*)dst);
+    else nchw_to_rows_bf16_kernel<<<grid, 256, 0, STREAM>>>((const float*)src, c, (__nv_bfloat16*)dst);
     NLV_CHECK_LAUNCH();
     return NLV_OK;
   }
   dim3 grid(cdiv(c, 64), r);
-  nchw_to_rows_kernel<49><<<grid, 256, 0, STREAM>>>(src, c, dst, dst_dtype);
+  nchw_to_rows_kernel<49><<<grid, 256, 0, STREAM>>>(src, src_dtype, c, dst, dst_dtype);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

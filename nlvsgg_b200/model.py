@@ -24,9 +24,12 @@ class Batch:
 TENSOR_KEYS = ("features", "boxes", "labels", "scores", "distribution", "union_feat", "pair_idx", "spatial_masks")
 
 
-def collate(entries: List[dict], mode: str, pin: bool = False) -> Batch:
+def collate(entries: List[dict], mode: str, pin: bool = False, feat_dtype: torch.dtype = F32) -> Batch:
     """Concatenate per-video entries (wherever their tensors live) into one Batch of the same residency.
-    Host-side metadata (frame ids, per-video counts, label lists) is extracted once here."""
+    Host-side metadata (frame ids, per-video counts, label lists) is extracted once here.
+    feat_dtype: storage type of the two feature tensors (`features`, `union_feat`).  fp32 is the reference's entry
+    contract; bf16 is the packed-feature-file format of SURVEY 8f-2 (half the host -> device bytes; in the bf16 compute
+    mode the results are bit-identical, the same round-to-nearest just happens in the loader instead of on the device)."""
     b = Batch()
     b.n_boxes = [int(e["boxes"].shape[0]) for e in entries]
     b.frame_ids = [e["im_idx"].detach().cpu().numpy() for e in entries]
@@ -40,15 +43,25 @@ def collate(entries: List[dict], mode: str, pin: bool = False) -> Batch:
         t = t.to(dtype).contiguous() if t.dtype != dtype else t.contiguous()
         return t.pin_memory() if (pin and not t.is_cuda) else t
 
-    b.features, b.boxes = cat("features", F32), cat("boxes", F32)
+    b.features, b.boxes = cat("features", feat_dtype), cat("boxes", F32)
     b.labels, b.scores = cat("labels", torch.int64), cat("scores", F32)
     b.distribution = cat("distribution", F32) if mode != "predcls" else None
-    b.union_feat = cat("union_feat", F32)
+    b.union_feat = cat("union_feat", feat_dtype)
     pi = [e["pair_idx"].to(torch.int64) + int(o) for e, o in zip(entries, off)]
     b.pair_idx = (pi[0] if len(pi) == 1 else torch.cat(pi, 0)).contiguous()
     if pin and not b.pair_idx.is_cuda:
         b.pair_idx = b.pair_idx.pin_memory()
     b.spatial_masks = cat("spatial_masks", F32) if all("spatial_masks" in e for e in entries) else None
+    return b
+
+
+def repack(hb: Batch, feat_dtype: torch.dtype, pin: bool = True) -> Batch:
+    """Host batch with the two feature tensors stored as `feat_dtype` (what a loader of packed feature files hands over)."""
+    b = Batch()
+    b.__dict__.update(hb.__dict__)
+    for key in ("features", "union_feat"):
+        t = getattr(hb, key).to(feat_dtype)
+        setattr(b, key, t.pin_memory() if (pin and not t.is_cuda) else t)
     return b
 
 

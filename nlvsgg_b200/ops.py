@@ -170,7 +170,7 @@ def nchw_to_rows(x: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     step = 32768
     for s in range(0, r, step):  # grid.y limit
         n = min(step, r - s)
-        _call("nlv_nchw_to_rows", _ptr(x[s:s + n]), n, c, h * w, _ptr(out[s * h * w:(s + n) * h * w]), _dt(out))
+        _call("nlv_nchw_to_rows", _ptr(x[s:s + n]), _dt(x), n, c, h * w, _ptr(out[s * h * w:(s + n) * h * w]), _dt(out))
     return out
 
 

@@ -163,3 +163,23 @@ def test_c5_recall_over_a_test_split_shape(cuda_lib):
     ev2.evaluate_videos([(base[j][1], to_cuda(base[j][0])) for j in reversed(order)])
     for k in (10, 20, 50):
         assert np.mean(sorted(ev2.result_dict[key][k])) == np.mean(sorted(ev.result_dict[key][k]))
+
+
+def test_packed_bf16_feature_format_is_bit_identical_in_bf16_mode(cuda_lib):
+    """a loader that stores `features` / `union_feat` as bf16 halves the host -> device bytes; in the bf16
+    compute mode the device rounds those tensors to bf16 first anyway, so logits and loss must not change by one bit."""
+    from nlvsgg_b200 import engine as E, model as M
+    entries = [synth.synth_video(700 + i, 6 + i, 5, "sgdet", with_gt=False)[0] for i in range(3)]
+    sd = synth.make_state_dict(G.sttran_template(), 7)
+    outs = []
+    for dt in (torch.float32, torch.bfloat16):
+        P = {k: v.cuda() for k, v in sd.items()}
+        hb = M.collate(entries, "sgdet", pin=True, feat_dtype=dt)
+        assert hb.union_feat.dtype == dt and hb.features.dtype == dt
+        plan = M.make_plan(hb, "cuda", "sgdet")
+        batch = M.upload(hb, "cuda")
+        out, _ = M.sttran_forward(E.Kernels("bf16"), P, batch, plan, "sgdet", True, False)
+        outs.append(out)
+    assert M.input_bytes(M.collate(entries, "sgdet", feat_dtype=torch.bfloat16)) < 0.51 * M.input_bytes(M.collate(entries, "sgdet"))
+    assert torch.equal(outs[0]["logits26"], outs[1]["logits26"])
+    assert torch.equal(outs[0]["distribution"], outs[1]["distribution"])
