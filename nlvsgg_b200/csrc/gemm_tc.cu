@@ -302,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9) =====================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may access
     const int chunk0 = ((warp - 2) >> 2) * 32;   // first 32-column chunk of this warp
     int iter = 0;
