@@ -8,6 +8,8 @@ import torch.nn as nn
 
 from .. import autograd as A
 from .. import engine as E
+from .. import ops
+from .roi_layers import ROIAlign, nms
 from .transformer_wk import transformer_wk
 from .word_vectors import obj_edge_vectors
 
@@ -26,6 +28,78 @@ class ObjectClassifier(nn.Module):
         self.obj_dim = 2048
         self.decoder_lin = nn.Sequential(nn.Linear(self.obj_dim + 200 + 128, 1024), nn.BatchNorm1d(1024), nn.ReLU(),
                                          nn.Linear(1024, len(self.classes)))
+        self.RCNN_roi_align = ROIAlign((7, 7), 1.0 / 16.0, 0)          # lib/sttran.py:37
+        self.nms_strict = True     # reference CUDA rule (IoU > 0.6 suppresses, nms.cu); False = its CPU rule (>=, nms_cpu.cpp)
+
+    # ---- non-weakly-supervised sgdet, eval mode: lib/sttran.py:185-283 ------------------------------------------
+    @staticmethod
+    def _clean_class(boxes, dist, feats, labels, class_idx):
+        """lib/sttran.py:53-81 without the per-frame loop: every frame keeps its detections and gets, right after them, a second
+        copy of those labelled `class_idx` with that class's score zeroed and the label re-decided."""
+        sel = labels == class_idx
+        nd = dist[sel].clone()
+        nd[:, class_idx - 1] = 0
+        nl = nd.argmax(1) + 1 if nd.shape[0] else labels[:0]
+        frame = torch.cat((boxes[:, 0], boxes[sel, 0]))
+        key = frame * 2 + torch.cat((torch.zeros_like(boxes[:, 0]), torch.ones_like(boxes[sel, 0])))
+        order = torch.sort(key, stable=True)[1]
+        return (torch.cat((boxes, boxes[sel]))[order], torch.cat((dist, nd))[order], torch.cat((feats, feats[sel]))[order],
+                torch.cat((labels, nl))[order])
+
+    @torch.no_grad()
+    def sgdet_test_branch(self, entry):
+        """Detector output -> (NMS-filtered boxes, labels, human per frame, pairs, union features, spatial masks); mutates and
+        returns `entry` with the keys the reference writes.  Index logic is torch on the device; NMS, RoIAlign and the mask
+        rasteriser are the nlv_b200 kernels.  One host sync (group sizes) replaces the reference's per-frame / per-class syncs."""
+        boxes, dist = entry["boxes"].float(), entry["distribution"].float()
+        feats, labels = entry["features"], entry["pred_labels"].long()
+        dev = boxes.device
+        b = int(boxes[-1, 0].item()) + 1                                                        # :190
+        for c in (5, 8, 17):                                                                    # :196-198
+            boxes, dist, feats, labels = self._clean_class(boxes, dist, feats, labels, c)
+        # per (frame, arg-max class) groups, score-descending inside a group (:204-232)
+        am = dist.argmax(1)
+        cls_score = dist.gather(1, am[:, None])[:, 0]
+        o1 = torch.sort(cls_score, descending=True, stable=True)[1]
+        group = (boxes[:, 0].long() * (len(self.classes) - 1) + am)[o1]
+        o2 = torch.sort(group, stable=True)[1]
+        order = o1[o2]
+        group = group[o2]
+        boxes, dist, feats, cls_score = boxes[order], dist[order], feats[order], cls_score[order]
+        sizes = torch.unique_consecutive(group, return_counts=True)[1].tolist()              # the one host sync
+        keep, start = [], 0
+        for n in sizes:
+            k = nms(boxes[start:start + n, 1:], cls_score[start:start + n], 0.6, strict=self.nms_strict)
+            keep.append(k + start)
+            start += n
+        keep = torch.cat(keep)
+        boxes, dist, feats = boxes[keep], dist[keep], feats[keep]
+        box_idx = boxes[:, 0].long()
+        n_box = boxes.shape[0]
+        pred_scores, pred_labels = torch.max(dist[:, 1:], dim=1)                                # :240-241
+        pred_labels = pred_labels + 2
+        # human of a frame = its detection with the highest person score, first one on ties (:244-252); frames without
+        # detections keep index 0, exactly as the reference's zero-initialised HUMAN_IDX does
+        hs = torch.sort(dist[:, 0], descending=True, stable=True)[1]
+        hs = hs[torch.sort(box_idx[hs], stable=True)[1]]
+        first = torch.ones(n_box, dtype=torch.bool, device=dev)
+        first[1:] = box_idx[hs][1:] != box_idx[hs][:-1]
+        human = torch.zeros(b, dtype=torch.int64, device=dev)
+        human[box_idx[hs][first]] = hs[first]
+        pred_labels[human] = 1                                                                   # :254-255
+        pred_scores[human] = dist[human, 0]
+        objs = torch.nonzero(pred_labels != 1)[:, 0]                                            # :257-263 (boxes are frame-sorted)
+        pair = torch.stack((human[box_idx[objs]], objs), 1)
+        im_idx = box_idx[objs].float()
+        union_boxes = torch.cat((im_idx[:, None], torch.min(boxes[pair[:, 0], 1:3], boxes[pair[:, 1], 1:3]),
+                                 torch.max(boxes[pair[:, 0], 3:5], boxes[pair[:, 1], 3:5])), 1)  # :270-273
+        entry["boxes"], entry["distribution"], entry["features"] = boxes, dist, feats
+        entry["pred_scores"], entry["pred_labels"] = pred_scores, pred_labels
+        entry["pair_idx"], entry["im_idx"], entry["human_idx"] = pair, im_idx, human[:, None]
+        entry["union_feat"] = self.RCNN_roi_align(entry["fmaps"], union_boxes)                   # :275
+        entry["union_box"] = union_boxes
+        entry["spatial_masks"] = ops.union_mask_pairs(boxes, pair, 27, -0.5)                     # :279-281
+        return entry
 
 
 class STTran(nn.Module):
@@ -38,8 +112,8 @@ class STTran(nn.Module):
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = \
             attention_class_num, spatial_class_num, contact_class_num
         self.transformer_mode, self.motifs_path = transformer_mode, motifs_path
-        if mode == "sgcls" or (mode == "sgdet" and not is_wks):
-            raise NotImplementedError("only the predcls and sgdet/is_wks branches of lib/sttran.py are built (SURVEY.md §8f-3)")
+        if mode == "sgcls":
+            raise NotImplementedError("the sgcls branches of lib/sttran.py are not built (SURVEY.md §8f-3)")
         assert (attention_class_num, spatial_class_num, contact_class_num) == (3, 6, 17) and feat_dim == 2048
         self.object_classifier = ObjectClassifier(mode=mode, obj_classes=obj_classes, is_wks=is_wks)
         self.union_func1 = nn.Conv2d(feat_dim, 256, 1, 1)
@@ -63,6 +137,15 @@ class STTran(nn.Module):
 
     def forward(self, entry):
         """lib/sttran.py:375-411: mutates and returns ``entry``."""
+        if self.mode == "sgdet" and not self.is_wks and not self.training:
+            # :185-283 — detections are filtered and paired here; the object classifier head is NOT applied (the detector's
+            # distribution is kept), so the relation path runs exactly like predcls on the inferred labels
+            entry = self.object_classifier.sgdet_test_branch(entry)
+            view = dict(entry)
+            view["labels"], view["scores"] = entry["pred_labels"], entry["pred_scores"]
+            _, att, spa, con, _ = A.run_module(self, self.kernels, [view], "predcls", "sttran")
+            entry["attention_distribution"], entry["spatial_distribution"], entry["contacting_distribution"] = att, spa, con
+            return entry
         obj, att, spa, con, batch = A.run_module(self, self.kernels, [entry], self.mode, "sttran")
         entry["pred_labels"] = entry["labels"]                      # :91 / :183
         if self.mode != "predcls":

@@ -149,3 +149,37 @@ def make_state_dict(template: dict, seed: int = 0) -> dict:
             fan_in = int(np.prod(shape[1:]))
             out[name] = torch.randn(shape, generator=g) * (1.0 / np.sqrt(fan_in))
     return out
+
+
+def synth_detections(seed: int, frames: int = 6, mean_boxes: int = 9, fmap_channels: int = 2048, fmap_hw=(17, 30)):
+    """Raw detector output for the non-weakly-supervised sgdet TEST branch of lib/sttran.py:185-283 (before the per-class
+    NMS): clusters of overlapping boxes that share an arg-max class, one strong person box per frame, class-distribution
+    rows that sum to one, detector labels = arg-max + 1, and per-frame backbone maps for the union-box RoIAlign."""
+    g = torch.Generator().manual_seed(int(seed))
+    boxes, dists, labels = [], [], []
+    for f in range(frames):
+        k = int(torch.randint(max(3, mean_boxes - 3), mean_boxes + 4, (1,), generator=g))
+        n_clusters = max(2, k // 2)
+        centres = torch.rand(n_clusters, 2, generator=g) * torch.tensor([0.6 * IMG_W, 0.6 * IMG_H]) + 10.0
+        sizes = 30.0 + torch.rand(n_clusters, 2, generator=g) * torch.tensor([0.3 * IMG_W, 0.3 * IMG_H])
+        cls = torch.randint(1, 36, (n_clusters,), generator=g)          # column index in the 36-way distribution (0 = person)
+        cls[0] = 0                                                       # the first cluster of every frame is the person
+        for j in range(k):
+            c = j % n_clusters
+            jit = (torch.rand(4, generator=g) - 0.5) * 16.0              # +-8 px: IoU within a cluster straddles 0.6
+            x1, y1 = float(centres[c, 0] + jit[0]), float(centres[c, 1] + jit[1])
+            x2, y2 = x1 + float(sizes[c, 0] + jit[2]), y1 + float(sizes[c, 1] + jit[3])
+            boxes.append([float(f), max(x1, 0.0), max(y1, 0.0), min(x2, IMG_W - 1.0), min(y2, IMG_H - 1.0)])
+            logit = torch.randn(36, generator=g)
+            logit[int(cls[c])] += 3.0 + 2.0 * float(torch.rand(1, generator=g))
+            d = torch.softmax(logit, 0)
+            dists.append(d)
+            labels.append(int(torch.argmax(d)) + 1)
+    N = len(boxes)
+    return {
+        "boxes": torch.tensor(boxes, dtype=torch.float32),
+        "distribution": torch.stack(dists),
+        "pred_labels": torch.tensor(labels, dtype=torch.int64),
+        "features": torch.relu(torch.randn(N, 2048, generator=g)),
+        "fmaps": torch.relu(torch.randn(frames, fmap_channels, fmap_hw[0], fmap_hw[1], generator=g)),
+    }
