@@ -114,6 +114,29 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_cores(local: int):
+    """Best effort: run this rank (and therefore first-touch its pinned staging buffers) on the cores NVML reports as local to
+    its GPU.  The e2e leg moves 4.9 GB per step over PCIe; pinned memory on the far NUMA node halves that bandwidth."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            h = pynvml.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(local).uuid))
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        allowed = os.sched_getaffinity(0)
+        pick = sorted(near & allowed)
+        if pick and len(pick) < len(allowed):
+            os.sched_setaffinity(0, pick)
+            return f"bound to {len(pick)} GPU-local cores of {len(allowed)}"
+        return f"all {len(allowed)} visible cores are GPU-local" if pick else "no GPU-local core visible"
+    except Exception as e:  # NVML missing / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -125,6 +148,10 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_cores(local)
+    # one process per GPU: keep the host-side torch ops of N ranks from oversubscribing the cores (the reference pins 4
+    # threads itself, tools/train_STTran.py:40); the CPU-baseline leg raises this again for its own measurement
+    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 4) // max(world, 1))))
     if world > 1:
         import datetime
         torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -197,7 +224,7 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         e2e = {"value": total_frames / (float(t.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": float(t.item()), "last_loss": lv, "input_pipelining": "H2D of step i+1 overlaps compute of step i (side stream)",
-               "host_feature_dtype": "fp32 (the reference's entry contract)"}
+               "host_feature_dtype": "fp32 (the reference's entry contract)", "cpu_binding": numa}
         if a.precision == "bf16" and not a.no_packed_e2e:
             # Extra, NOT the headline: the same loop fed from the packed bf16 feature format.  In the bf16 compute
             # mode the step is bit-identical (the round-to-nearest moves from the device into the loader); the copy is half as long.
