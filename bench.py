@@ -225,7 +225,7 @@ def main():
         e2e = {"value": total_frames / (float(t.item()) / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": float(t.item()), "last_loss": lv, "input_pipelining": "H2D of step i+1 overlaps compute of step i (side stream)",
                "host_feature_dtype": "fp32 (the reference's entry contract)", "cpu_binding": numa}
-        if a.precision == "bf16" and not a.no_packed_e2e:
+        if a.precision == "bf16" and not a.no_packed_e2e and world == 1:   # informational leg: single-GPU runs only
             # Extra, NOT the headline: the same loop fed from the packed bf16 feature format.  In the bf16 compute
             # mode the step is bit-identical (the round-to-nearest moves from the device into the loader); the copy is half as long.
             host16 = M.repack(host, torch.bfloat16)
