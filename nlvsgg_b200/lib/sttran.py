@@ -15,7 +15,8 @@ from .word_vectors import obj_edge_vectors
 
 
 class ObjectClassifier(nn.Module):
-    """Parameter container of lib/sttran.py:20-51 (predcls pass-through :90-92, sgdet/wks head :173-184)."""
+    """Parameter container of lib/sttran.py:20-51 (predcls pass-through :90-92, sgdet/wks head :173-184) and the
+    detection-filtering / pairing logic of the non-wks sgdet TEST branch (:185-283)."""
 
     def __init__(self, mode="sgdet", obj_classes=None, is_wks=True):
         super().__init__()
