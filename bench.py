@@ -97,7 +97,7 @@ def run_reference(a):
         return
     from nlvsgg_b200 import shapes, synth
     from oracle import baseline, cref
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(len(os.sched_getaffinity(0)) or 1)    # every core this process may run on
     n = a.cpu_sample_videos
     entries = make_videos(a, 0, n, draw_fn=cref.draw_union_boxes)
     tmpl = shapes.sttran_template() if a.arch == "sttran" else shapes.dsg_template()
@@ -130,6 +130,7 @@ def bind_to_gpu_cores(local: int):
         allowed = os.sched_getaffinity(0)
         pick = sorted(near & allowed)
         if pick and len(pick) < len(allowed):
+            bind_to_gpu_cores.original = allowed          # restored before the CPU-baseline leg
             os.sched_setaffinity(0, pick)
             return f"bound to {len(pick)} GPU-local cores of {len(allowed)}"
         return f"all {len(allowed)} visible cores are GPU-local" if pick else "no GPU-local core visible"
@@ -151,7 +152,7 @@ def main():
     numa = bind_to_gpu_cores(local)
     # one process per GPU: keep the host-side torch ops of N ranks from oversubscribing the cores (the reference pins 4
     # threads itself, tools/train_STTran.py:40); the CPU-baseline leg raises this again for its own measurement
-    torch.set_num_threads(max(1, min(4, (os.cpu_count() or 4) // max(world, 1))))
+    torch.set_num_threads(max(1, min(4, len(os.sched_getaffinity(0)) // max(world, 1))))
     if world > 1:
         import datetime
         torch.distributed.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
@@ -302,7 +303,9 @@ def main():
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         from oracle import baseline, cref
-        torch.set_num_threads(os.cpu_count() or 1)
+        if getattr(bind_to_gpu_cores, "original", None):   # the CPU baseline may use every core the process was given
+            os.sched_setaffinity(0, bind_to_gpu_cores.original)
+        torch.set_num_threads(len(os.sched_getaffinity(0)) or 1)
         n = a.cpu_sample_videos
         ce = make_videos(a, 0, n, draw_fn=cref.draw_union_boxes)
         sec, cfr = baseline.time_cpu_steps(synth.make_state_dict(tmpl, 0), ce, "sgdet", a.arch, 1, 1)
