@@ -174,6 +174,18 @@ int nlv_sumsq(const float* x, long long n, float* out, void* stream);
 int nlv_adamw_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                    float weight_decay, int step, const float* total_sq, float max_norm, void* p_bf16, void* stream);
 
+/* The same update with the step counter on the device, so an iteration can be skipped without a host sync
+ * (lib/utils.py:3-11 check_valid_iter + the `continue` of tools/train_STTran.py:191): state[0] = steps applied (bias
+ * corrections use state[0]+1), state[1] = steps skipped.  Skipped when *skip_flag != 0 or *total_sq is not finite.
+ * grad_scale multiplies every gradient (1/world after a summing all-reduce; total_sq is the norm of the summed gradients).
+ * Call nlv_adamw_step_state on every parameter range of the step, then nlv_adamw_finish once. */
+int nlv_adamw_step_state(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, const int* state, const float* total_sq, const int* skip_flag, float grad_scale,
+                         float max_norm, void* p_bf16, void* stream);
+int nlv_adamw_finish(int* state, const float* total_sq, const int* skip_flag, void* stream);
+/* flag[0] = 1 if any of x[0:n] is NaN / Inf, else 0 (n small: the loss scalar) */
+int nlv_flag_nonfinite(const float* x, int n, int* flag, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Recall@K triplet matching (lib/evaluation_recall.py:397-467, :209-353, :630-773; bbox.pyx:21-61)
  * One launch over n_frames frames (any number of videos).  Per frame f:
@@ -208,6 +220,145 @@ int nlv_nms(const float* dets, const long long* order, int n, float thr, int str
 int nlv_track_cost(const float* det_box_xywh, const float* trk_box_xywh, const float* det_feat, const float* trk_feat, int feat_dim,
                    const float* det_dist, const float* trk_dist, int dist_dim, int n_det, int n_trk, float w_class, float w_feat,
                    float w_bbox, float w_giou, float* cost, float* cost_dist, float* cost_feat, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Small multi-segment helpers used by the model sequencer
+ * ------------------------------------------------------------------------------------------ */
+/* up to any number of independent contiguous conversions/copies dst[i][0:n[i]] = src[i][0:n[i]] (f32/bf16 either side) in
+ * ceil(count/32) launches; src/dst/n are HOST arrays of device pointers / element counts */
+int nlv_convert_multi(const void* const* src_host, void* const* dst_host, const long long* n_host, int count, int src_dtype,
+                      int dst_dtype, void* stream);
+/* dst[a, c, b] = src[a, b, c] (dtype conversion allowed): the conv / vr_fc weight re-orderings between the reference's
+ * NCHW parameter layout and the channels-last operand layout of the kernels, and back for their gradients */
+int nlv_permute_021(const void* src, int src_dtype, int a, int b, int c, void* dst, int dst_dtype, void* stream);
+int nlv_zero_bytes(void* p, long long nbytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Whole-model sequencer: one call enqueues the complete kernel sequence of
+ *   lib/sttran.py:375-411 STTran.forward (object classifier :173-184, pair tokens :381-399, lib/transformer_wk.py:130-217,
+ *   heads :404-409), lib/dsg_detr.py:514-572, the losses of tools/train_STTran.py:169-189 and the matching backward pass.
+ * The host does no per-layer work: buffers come from ONE caller-provided workspace (bump-allocated, sized by a dry run),
+ * parameters / gradients are pointer tables indexed by the NLV_P_* slots below.
+ * ------------------------------------------------------------------------------------------ */
+enum {
+  NLV_P_OC_EMBED = 0,                                              /* object_classifier.obj_embed.weight [36,200]   */
+  NLV_P_OC_BN0_W, NLV_P_OC_BN0_B, NLV_P_OC_BN0_RM, NLV_P_OC_BN0_RV, /* object_classifier.pos_embed.0 (BatchNorm1d(4))  */
+  NLV_P_OC_LIN1_W, NLV_P_OC_LIN1_B,                                /* object_classifier.pos_embed.1 [128,4]         */
+  NLV_P_OC_DEC0_W, NLV_P_OC_DEC0_B,                                /* object_classifier.decoder_lin.0 [1024,2376]   */
+  NLV_P_OC_BN1_W, NLV_P_OC_BN1_B, NLV_P_OC_BN1_RM, NLV_P_OC_BN1_RV, /* object_classifier.decoder_lin.1               */
+  NLV_P_OC_DEC3_W, NLV_P_OC_DEC3_B,                                /* object_classifier.decoder_lin.3 [37,1024]     */
+  NLV_P_UNION_W, NLV_P_UNION_B,                                    /* union_func1 [256,2048,1,1]                    */
+  NLV_P_CONV0_W, NLV_P_CONV0_B,                                    /* conv.0 [128,2,7,7]                            */
+  NLV_P_BN2_W, NLV_P_BN2_B, NLV_P_BN2_RM, NLV_P_BN2_RV,            /* conv.2 BatchNorm2d(128)                       */
+  NLV_P_CONV4_W, NLV_P_CONV4_B,                                    /* conv.4 [256,128,3,3]                          */
+  NLV_P_BN6_W, NLV_P_BN6_B, NLV_P_BN6_RM, NLV_P_BN6_RV,            /* conv.6 BatchNorm2d(256)                       */
+  NLV_P_SUBJ_W, NLV_P_SUBJ_B, NLV_P_OBJ_W, NLV_P_OBJ_B,            /* subj_fc / obj_fc [512,2048]                   */
+  NLV_P_VR_W, NLV_P_VR_B,                                          /* vr_fc [512,12544]                             */
+  NLV_P_EMB1, NLV_P_EMB2,                                          /* obj_embed / obj_embed2 [37,200]               */
+  NLV_P_A_W, NLV_P_A_B, NLV_P_S_W, NLV_P_S_B, NLV_P_C_W, NLV_P_C_B, /* a/s/c_rel_compress                            */
+  NLV_P_POS,                                                       /* STTran: glocal_transformer.position_embedding.weight [2,1936];
+                                                                      DSG-DETR: positional_encoder.pe [max_len,1936] (buffer) */
+  NLV_P_LAYER0                                                     /* first transformer layer; NLV_P_LAYER_STRIDE slots each */
+};
+enum {
+  NLV_L_INPROJ_W = 0, NLV_L_INPROJ_B, NLV_L_OUTPROJ_W, NLV_L_OUTPROJ_B, NLV_L_LIN1_W, NLV_L_LIN1_B, NLV_L_LIN2_W, NLV_L_LIN2_B,
+  NLV_L_NORMA_W, NLV_L_NORMA_B,   /* encoder: norm1; decoder: norm3 */
+  NLV_L_NORMB_W, NLV_L_NORMB_B,   /* encoder: norm2; decoder: unused */
+  NLV_P_LAYER_STRIDE
+};
+/* layer order: STTran = n_enc spatial-encoder layers, then n_dec temporal-decoder layers;
+ *              DSG-DETR = local_transformer layer, then the 3 global_transformer layers (all encoder type) */
+
+#define NLV_ARCH_STTRAN 0
+#define NLV_ARCH_DSG 1
+#define NLV_MODE_PREDCLS 0
+#define NLV_MODE_SGCLS 1
+#define NLV_MODE_SGDET 2
+#define NLV_PREC_BF16 0
+#define NLV_PREC_BF16X3 1
+#define NLV_PREC_FP32 2
+
+typedef struct nlv_model {
+  int arch, mode, precision;
+  int n_enc, n_dec;            /* STTran layer counts (DSG-DETR: 1, 3) */
+  int training;                /* BatchNorm batch statistics + running-stat update, dropout */
+  int n_slots;                 /* entries in the three tables below */
+  const float* const* params;  /* fp32 parameters / buffers per slot (device pointers; host array) */
+  const void* const* params_op;/* optional bf16 operand copies per slot kept current by the caller (trainer mirror); NULL
+                                  table or NULL entries -> converted inside the forward call */
+  float* grad_base;            /* backward: ONE fp32 gradient buffer, zeroed by the backward call ... */
+  long long grad_elems;
+  const long long* grad_offset;/* ... parameter of slot s receives its gradient at grad_base + grad_offset[s] (<0: none) */
+  float dropout_p;             /* reference 0.1 (lib/transformer.py:11-57); applied only when training != 0 */
+  unsigned long long seed;     /* Philox seed of this step's dropout masks */
+  int additive_mask;           /* 0: bool key-padding masks (lib/transformer.py:144); 1: the int mask of
+                                  lib/transformer_wk.py:154 under torch 1.10.1 (+1 added to padded keys' logits; the number of
+                                  padded keys of a frame travels in the 4th field of its local work items; inference only) */
+  int pe_rows;                 /* DSG-DETR: rows of the positional-encoding buffer */
+} nlv_model;
+
+typedef struct nlv_batch {
+  int nv;                       /* videos in the batch */
+  long long n_boxes, n_pairs, n_stream;   /* N, R, Mg (rows of the sliding-window stream) */
+  const void* features; int feat_dtype;   /* [N,2048] f32 (entry contract) or bf16 (packed feature files) */
+  const float* boxes;                     /* [N,5] */
+  const long long* labels;                /* [N] labels used for the semantic embeddings (pred_labels) */
+  const float* distribution;              /* [N,36] (sgdet / sgcls) */
+  const void* union_feat; int union_dtype;
+  int union_rows;                         /* 0: NCHW [R,2048,7,7] (entry contract); 1: channels-last rows [R*49,2048] */
+  const float* spatial_masks;             /* [R,2,27,27] or NULL -> rasterised from boxes + pair_idx */
+  const long long* pair_idx;              /* [R,2] */
+  /* host-built descriptors (nlvsgg_b200/plan.py), int32 device arrays */
+  const int *box_seg, *seg196, *seg49, *box_row, *row196, *row49;
+  const int *local_work; int n_local_work;
+  const int *glob_work; int n_glob_work;
+  const int *stream_src, *stream_slot, *inv, *out_src, *out_inv, *passthrough; int has_passthrough;
+  const int *cls_perm, *cls_iperm, *cls_pos, *cls_work; int n_cls_work;   /* DSG-DETR class sequences */
+  /* fused-loss labels (tools/train_STTran.py:143-167), NULL for inference */
+  const long long* lab_att; const float* w_att; const unsigned* spa_bits; const float* w_spa;
+  const unsigned* con_bits; const float* w_con; const float* w_obj;
+} nlv_batch;
+
+typedef struct nlv_outputs {
+  float* obj_logits;      /* [N,37] (NULL in predcls) */
+  float* logits26;        /* [R,26] attention logits | spatial logits | contacting logits */
+  float* att; float* spa; float* con;   /* [R,3] logits, [R,6] / [R,17] sigmoid (NLV_RUN_ACTIVATIONS) */
+  float* loss;            /* [1] (NLV_RUN_LOSS) */
+  float* masks;           /* [R,2,27,27] spatial masks used (the caller's, or the rasterised ones) */
+  float* rel_tokens;      /* [R,1936] pair tokens (lib/sttran.py:399) */
+  float* rel_out;         /* [R,1936] transformer output (lib/sttran.py:401) */
+  float* d26; float* dobj;/* loss gradients w.r.t. logits26 / obj_logits (NLV_RUN_LOSS) */
+} nlv_outputs;
+
+#define NLV_RUN_CTX 1          /* keep activations for nlv_session_backward */
+#define NLV_RUN_LOSS 2         /* fused CE / CE / BCE / BCE loss from the batch labels (+ its gradients when NLV_RUN_CTX) */
+#define NLV_RUN_BACKWARD 4     /* (plan only) size the workspace for a backward pass too */
+#define NLV_RUN_ACTIVATIONS 8  /* att / spa / con outputs (lib/sttran.py:404-409) */
+
+/* out[0..3] = sizeof(nlv_model), sizeof(nlv_batch), sizeof(nlv_outputs), sizeof(nlv_gemm_args); returns 4 */
+int nlv_struct_sizes(int* out, int n);
+
+typedef struct nlv_session nlv_session;
+nlv_session* nlv_session_create(void);
+void nlv_session_destroy(nlv_session* s);
+/* dry run: workspace bytes needed by forward (+ backward with NLV_RUN_BACKWARD) for this model / batch; < 0 on error */
+long long nlv_session_plan(nlv_session* s, const nlv_model* model, const nlv_batch* batch, int flags);
+int nlv_session_forward(nlv_session* s, const nlv_model* model, const nlv_batch* batch, void* workspace,
+                        long long workspace_bytes, int flags, nlv_outputs* out, void* stream);
+/* where the next backward writes (replaces model->grad_base / grad_elems / grad_offset given at forward time) */
+int nlv_session_set_gradients(nlv_session* s, float* grad_base, long long grad_elems, const long long* grad_offset, int n_slots);
+/* gradients of every parameter into model->grad_base; d26 / dobj NULL -> the loss's own gradients (NLV_RUN_LOSS) */
+int nlv_session_backward(nlv_session* s, const float* d26, const float* dobj, void* stream);
+/* standalone spatio-temporal transformer (lib/transformer_wk.py:130-217 forward(features, im_idx)) over the same
+ * session machinery: only the layer slots and NLV_P_POS of `model` are read; x f32[R,1936] -> *out f32[R,1936] (in the
+ * workspace).  workspace == NULL: dry run, returns the workspace bytes needed (with NLV_RUN_BACKWARD: backward included) */
+long long nlv_session_transformer_forward(nlv_session* s, const nlv_model* model, const nlv_batch* batch, const float* x,
+                                          void* workspace, long long workspace_bytes, int flags, float** out, void* stream);
+int nlv_session_transformer_backward(nlv_session* s, const float* dout, float** dx, void* stream);
+/* d26[r, 0:3|3:9|9:26] = datt | dspa * spa(1-spa) | dcon * con(1-con): chain rule of lib/sttran.py:404-409 for callers that
+ * differentiate the activated outputs (any of datt / dspa / dcon may be NULL = zero) */
+int nlv_heads_activation_bwd(const float* datt, const float* dspa, const float* dcon, const float* spa, const float* con,
+                             long long r, float* d26, void* stream);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,39 @@ class GemmArgs(ctypes.Structure):
                 ("relu", ctypes.c_int), ("gate", ctypes.c_void_p), ("ldg", ctypes.c_int), ("gate_dtype", ctypes.c_int)]
 
 
+_vp, _ip, _i, _ll, _f = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float
+
+
+class Model(ctypes.Structure):
+    """nlv_model (include/nlv_b200.h)."""
+    _fields_ = [("arch", _i), ("mode", _i), ("precision", _i), ("n_enc", _i), ("n_dec", _i), ("training", _i), ("n_slots", _i),
+                ("params", _vp), ("params_op", _vp), ("grad_base", _vp), ("grad_elems", _ll), ("grad_offset", _vp),
+                ("dropout_p", _f), ("seed", ctypes.c_ulonglong), ("additive_mask", _i), ("pe_rows", _i)]
+
+
+class BatchDesc(ctypes.Structure):
+    """nlv_batch (include/nlv_b200.h)."""
+    _fields_ = [("nv", _i), ("n_boxes", _ll), ("n_pairs", _ll), ("n_stream", _ll),
+                ("features", _vp), ("feat_dtype", _i), ("boxes", _vp), ("labels", _vp), ("distribution", _vp),
+                ("union_feat", _vp), ("union_dtype", _i), ("union_rows", _i), ("spatial_masks", _vp), ("pair_idx", _vp),
+                ("box_seg", _ip), ("seg196", _ip), ("seg49", _ip), ("box_row", _ip), ("row196", _ip), ("row49", _ip),
+                ("local_work", _ip), ("n_local_work", _i), ("glob_work", _ip), ("n_glob_work", _i),
+                ("stream_src", _ip), ("stream_slot", _ip), ("inv", _ip), ("out_src", _ip), ("out_inv", _ip), ("passthrough", _ip),
+                ("has_passthrough", _i),
+                ("cls_perm", _ip), ("cls_iperm", _ip), ("cls_pos", _ip), ("cls_work", _ip), ("n_cls_work", _i),
+                ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp)]
+
+
+class Outputs(ctypes.Structure):
+    """nlv_outputs (include/nlv_b200.h)."""
+    _fields_ = [(n, _vp) for n in ("obj_logits", "logits26", "att", "spa", "con", "loss", "masks", "rel_tokens", "rel_out", "d26", "dobj")]
+
+
+RUN_CTX, RUN_LOSS, RUN_BACKWARD, RUN_ACTIVATIONS = 1, 2, 4, 8
+ARCH = {"sttran": 0, "dsg": 1}
+MODE = {"predcls": 0, "sgcls": 1, "sgdet": 2}
+PREC = {"bf16": 0, "bf16x3": 1, "fp32": 2}
+
 _lib = None
 
 
@@ -77,6 +110,18 @@ def lib() -> ctypes.CDLL:
         _lib = ctypes.CDLL(SO_PATH)
         _lib.nlv_last_error.restype = ctypes.c_char_p
         _lib.nlv_launch_count.restype = ctypes.c_longlong
+        _lib.nlv_session_create.restype = ctypes.c_void_p
+        _lib.nlv_session_destroy.argtypes = [ctypes.c_void_p]
+        _lib.nlv_session_plan.restype = ctypes.c_longlong
+        _lib.nlv_session_plan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        _lib.nlv_session_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                             ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.nlv_session_set_gradients.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_int]
+        _lib.nlv_session_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.nlv_session_transformer_forward.restype = ctypes.c_longlong
+        _lib.nlv_session_transformer_forward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                         ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _lib.nlv_session_transformer_backward.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     return _lib
 
 

@@ -1,5 +1,9 @@
 """torch.autograd glue: one Function per whole model, so the reference training scripts
-(loss.backward(); clip_grad_norm_; optimizer.step()) drive the hand-written backward unchanged."""
+(loss.backward(); clip_grad_norm_; optimizer.step()) drive the hand-written backward unchanged.
+
+Forward and backward are ONE C call each (csrc/step.cu).  The operand (bf16) copies of the weights are re-made from the
+live fp32 parameters inside every forward call — the reference optimiser updates through `p.data` (lib/AdamW.py:69,112),
+which no version counter sees, so nothing derived from a parameter is ever cached across calls."""
 from __future__ import annotations
 
 from typing import Dict, List
@@ -22,10 +26,9 @@ class _WholeModelFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, runner, names: List[str], *params):
-        P = runner.P
         want_ctx = runner.want_ctx   # decided by the caller: grad mode is always off inside Function.forward
         out, saved = runner.fwd(want_ctx)
-        att, spa, con = ops.heads_activation(out["logits26"])
+        att, spa, con = out["att"], out["spa"], out["con"]
         obj = out.get("distribution")
         if obj is None:
             obj = torch.empty(0, device=att.device)
@@ -37,22 +40,21 @@ class _WholeModelFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dobj, datt, dspa, dcon):
         spa, con = ctx.spa, ctx.con
-        R = spa.shape[0]
-        d26 = torch.zeros(R, 26, device=spa.device, dtype=torch.float32)
-        if datt is not None:
-            d26[:, 0:3] = datt
-        if dspa is not None:
-            d26[:, 3:9] = dspa * spa * (1.0 - spa)
-        if dcon is not None:
-            d26[:, 9:26] = dcon * con * (1.0 - con)
+        d26 = ops.heads_activation_bwd(datt, dspa, dcon, spa, con, spa.shape[0])
         dobj_l = dobj.contiguous() if (ctx.has_obj and dobj is not None) else None
+        if ctx.has_obj and dobj_l is None:
+            dobj_l = torch.zeros(ctx.runner.plan.N, 37, device=spa.device)
         grads = ctx.runner.bwd(ctx.saved, d26, dobj_l)
         ctx.saved = None
+        if ctx.runner.plan.Mg == 0:
+            # a video without a sliding window never reaches the temporal decoder / position embedding: the reference leaves
+            # their .grad None (lib/AdamW.py:66 then skips them)
+            grads = {n: g for n, g in grads.items() if "global_attention" not in n and "position_embedding" not in n}
         return (None, None) + tuple(grads.get(n) for n in ctx.names)
 
 
 class Runner:
-    """Binds a parameter dict, a batch and a plan to the engine's forward/backward."""
+    """Binds a parameter dict, a batch and a plan to the sequencer's forward / backward."""
 
     def __init__(self, kernels: E.Kernels, P, batch, plan, mode: str, training: bool, arch: str = "sttran"):
         self.k, self.P, self.batch, self.plan, self.mode, self.training, self.arch = kernels, P, batch, plan, mode, training, arch
@@ -60,7 +62,8 @@ class Runner:
 
     def fwd(self, want_ctx: bool):
         f = M.sttran_forward if self.arch == "sttran" else M.dsg_forward
-        return f(self.k, self.P, self.batch, self.plan, self.mode, self.training, want_ctx)
+        return f(self.k, self.P, self.batch, self.plan, self.mode, self.training, want_ctx, activations=True, with_backward=want_ctx,
+                 fresh_ws=True)
 
     def bwd(self, saved, d26, dobj):
         f = M.sttran_backward if self.arch == "sttran" else M.dsg_backward
@@ -73,11 +76,12 @@ def run_module(module: torch.nn.Module, kernels: E.Kernels, entries, mode: str, 
     if dev.type != "cuda":
         raise RuntimeError("nlvsgg_b200 models run on CUDA only (sm_100a kernels); there is no CPU fallback")
     batch, plan = M.make_batch(entries, dev, mode, dsg=(arch == "dsg"))
-    P = {k: v for k, v in module_tensors(module).items()}
+    P = {k: v.detach() for k, v in module_tensors(module).items()}
     runner = Runner(kernels, P, batch, plan, mode, module.training, arch)
     names = [n for n, p in module.named_parameters()]
     params = [p for n, p in module.named_parameters()]
     runner.want_ctx = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    kernels.seed += 1
     obj, att, spa, con = _WholeModelFn.apply(runner, names, *params)
     if module.training:   # BatchNorm bookkeeping the kernels do not touch
         for n, buf in module.named_buffers():

@@ -108,6 +108,48 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
   }
 }
 
+// Same update driven by device-side state, so a step can be skipped without a host sync (tools/train_STTran.py:191
+// check_valid_iter: NaN loss / NaN outputs -> `continue` before backward and optimizer.step()):
+//   state[0] = optimiser steps applied so far (bias corrections use state[0] + 1), state[1] = steps skipped;
+//   skipped when *skip_flag != 0 or the gradient norm is not finite; grad_scale folds the 1/world of the gradient
+//   all-reduce (total_sq is the squared norm of the SUMMED gradients).
+__global__ void adamw_state_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                   long long n, float lr, float b1, float b2, float eps, float wd, const int* __restrict__ state,
+                                   const float* __restrict__ total_sq, const int* __restrict__ skip_flag, float grad_scale,
+                                   float max_norm, __nv_bfloat16* __restrict__ p_bf16) {
+  const float tsq = total_sq != nullptr ? *total_sq : 0.f;
+  if ((skip_flag != nullptr && *skip_flag != 0) || !isfinite(tsq)) return;
+  float coef = grad_scale;
+  if (total_sq != nullptr && max_norm > 0.f) coef *= fminf(1.f, max_norm / (sqrtf(tsq) * grad_scale + 1e-6f));
+  const int step = state[0] + 1;
+  const float bc1 = (float)(1.0 - pow((double)b1, (double)step));
+  const float bc2s = (float)sqrt(1.0 - pow((double)b2, (double)step));
+  const float step_size = lr * bc2s / bc1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] * coef;
+    float pi = p[i] * (1.f - lr * wd);
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) + eps;
+    pi += -step_size * (mi / denom);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+    if (p_bf16) p_bf16[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+__global__ void adamw_finish_kernel(int* state, const float* total_sq, const int* skip_flag) {
+  const float tsq = total_sq != nullptr ? *total_sq : 0.f;
+  if ((skip_flag != nullptr && *skip_flag != 0) || !isfinite(tsq)) state[1] += 1;
+  else state[0] += 1;
+}
+
+__global__ void flag_nonfinite_kernel(const float* x, int n, int* flag) {
+  int bad = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) bad |= !isfinite(x[i]);
+  bad = __syncthreads_or(bad);
+  if (threadIdx.x == 0) flag[0] = bad ? 1 : 0;
+}
+
 }  // namespace
 }  // namespace nlv
 
@@ -170,6 +212,35 @@ int nlv_adamw_step(float* p, const float* g, float* m, float* v, long long n, fl
   if (blocks > cap) blocks = cap;
   adamw_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s, total_sq, max_norm,
                                           (__nv_bfloat16*)p_bf16);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_adamw_step_state(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                         float weight_decay, const int* state, const float* total_sq, const int* skip_flag, float grad_scale,
+                         float max_norm, void* p_bf16, void* stream) {
+  NLV_CHECK_ARG(n >= 0, "adamw_state: bad arguments");
+  if (n == 0) return NLV_OK;
+  NLV_CHECK_ARG(p && g && m && v && state, "adamw_state: null pointer");
+  int blocks = cdiv(n, 256 * 4);
+  const int cap = 16 * sm_count();
+  if (blocks > cap) blocks = cap;
+  adamw_state_kernel<<<blocks, 256, 0, STREAM>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, state, total_sq, skip_flag,
+                                                grad_scale, max_norm, (__nv_bfloat16*)p_bf16);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_adamw_finish(int* state, const float* total_sq, const int* skip_flag, void* stream) {
+  NLV_CHECK_ARG(state != nullptr, "adamw_finish: null state");
+  adamw_finish_kernel<<<1, 1, 0, STREAM>>>(state, total_sq, skip_flag);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_flag_nonfinite(const float* x, int n, int* flag, void* stream) {
+  NLV_CHECK_ARG(x && flag && n >= 0, "flag_nonfinite: bad arguments");
+  flag_nonfinite_kernel<<<1, 128, 0, STREAM>>>(x, n, flag);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

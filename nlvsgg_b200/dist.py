@@ -35,6 +35,20 @@ def allreduce_mean_(flat: torch.Tensor, bucket_elems: int = 32 * 1024 * 1024) ->
     return flat
 
 
+def allreduce_sum_(flat: torch.Tensor, flag: torch.Tensor = None, bucket_elems: int = 32 * 1024 * 1024) -> torch.Tensor:
+    """In-place SUM over ranks of the flat gradient buffer in independent async buckets (128 MB of fp32 each); the 1/world
+    of the mean is folded into the optimiser kernel.  `flag` (int32[1], the skip-this-step flag of lib/utils.py:3-11) is
+    max-reduced alongside so that all ranks skip together."""
+    if world() == 1:
+        return flat
+    works = [dist.all_reduce(flat[i:i + bucket_elems], async_op=True) for i in range(0, flat.numel(), bucket_elems)]
+    if flag is not None:
+        works.append(dist.all_reduce(flag, op=dist.ReduceOp.MAX, async_op=True))
+    for wk in works:
+        wk.wait()
+    return flat
+
+
 def gather_frame_results(local_ids: torch.Tensor, local_masks: torch.Tensor):
     """all_gather of (global frame id, u32[3,3,8] match sets) with ragged sizes; returns (ids, masks) sorted by id
     on every rank.  local_ids: int64[F_local]; local_masks: int32[F_local,3,3,8]."""

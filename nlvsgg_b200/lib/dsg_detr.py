@@ -46,7 +46,9 @@ class STTran(nn.Module):
         super().__init__()
         assert mode in ("sgdet", "sgcls", "predcls")
         if mode == "sgcls":
-            raise NotImplementedError("DSG-DETR sgcls (Hungarian object tracks) is a next-row item (SURVEY.md §8f-4)")
+            # lib/dsg_detr.py:185-275 feeds 2376-d object-track rows into subj_fc = Linear(2048, 512) (:181, :486): the
+            # reference itself raises a shape error on this path
+            raise NotImplementedError("DSG-DETR sgcls is unreachable in the reference (lib/dsg_detr.py:181 vs :486)")
         self.obj_classes, self.mode = obj_classes, mode
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = \
             attention_class_num, spatial_class_num, contact_class_num
@@ -73,7 +75,7 @@ class STTran(nn.Module):
         self.a_rel_compress = nn.Linear(d_model, attention_class_num)
         self.s_rel_compress = nn.Linear(d_model, spatial_class_num)
         self.c_rel_compress = nn.Linear(d_model, contact_class_num)
-        self.kernels = E.Kernels(precision or os.environ.get("NLV_PRECISION", "bf16"))
+        self.kernels = E.Kernels(precision or os.environ.get("NLV_PRECISION", "bf16"), dropout=0.1)
 
     def forward(self, entry):
         """lib/dsg_detr.py:514-572: mutates ``entry`` and returns it."""

@@ -113,8 +113,6 @@ class STTran(nn.Module):
         self.attention_class_num, self.spatial_class_num, self.contact_class_num = \
             attention_class_num, spatial_class_num, contact_class_num
         self.transformer_mode, self.motifs_path = transformer_mode, motifs_path
-        if mode == "sgcls":
-            raise NotImplementedError("the sgcls branches of lib/sttran.py are not built (SURVEY.md §8f-3)")
         assert (attention_class_num, spatial_class_num, contact_class_num) == (3, 6, 17) and feat_dim == 2048
         self.object_classifier = ObjectClassifier(mode=mode, obj_classes=obj_classes, is_wks=is_wks)
         self.union_func1 = nn.Conv2d(feat_dim, 256, 1, 1)
@@ -134,10 +132,14 @@ class STTran(nn.Module):
         self.a_rel_compress = nn.Linear(1936, attention_class_num)
         self.s_rel_compress = nn.Linear(1936, spatial_class_num)
         self.c_rel_compress = nn.Linear(1936, contact_class_num)
-        self.kernels = E.Kernels(precision or os.environ.get("NLV_PRECISION", "bf16"))
+        self.kernels = E.Kernels(precision or os.environ.get("NLV_PRECISION", "bf16"), dropout=0.1)
 
     def forward(self, entry):
         """lib/sttran.py:375-411: mutates and returns ``entry``."""
+        if self.mode == "sgcls" and not self.training:
+            # lib/sttran.py:105-170 re-extracts union features with VinVL (`extract_feature_given_bbox_base_feat_torch`, an
+            # un-vendored dependency, SURVEY.md §8c): there is no reference to run it against
+            raise NotImplementedError("sgcls evaluation needs the un-vendored VinVL feature extractor (lib/sttran.py:159)")
         if self.mode == "sgdet" and not self.is_wks and not self.training:
             # :185-283 — detections are filtered and paired here; the object classifier head is NOT applied (the detector's
             # distribution is kept), so the relation path runs exactly like predcls on the inferred labels

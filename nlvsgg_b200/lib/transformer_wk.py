@@ -41,18 +41,19 @@ class _Stack(nn.Module):
 
 class _TransformerFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, kernels, plan, P, names, want, features, *params):
-        Pg = {"glocal_transformer." + n: t for n, t in P.items()}
-        out, saved = E.sttran_transformer_fwd(kernels, Pg, plan, features.contiguous().float(), want)
-        ctx.k, ctx.plan, ctx.Pg, ctx.saved, ctx.names = kernels, plan, Pg, saved, names
+    def forward(ctx, kernels, desc, plan, P, names, want, training, features, *params):
+        x = features.detach().contiguous().float()
+        out, sess = E.run_transformer_forward(kernels, desc, P, plan, x, training, want)
+        ctx.desc, ctx.sess, ctx.P, ctx.names, ctx.plan = desc, sess, P, names, plan
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        grads = {}
-        dx = E.sttran_transformer_bwd(ctx.k, ctx.Pg, ctx.plan, ctx.saved, dout.contiguous(), grads)
-        ctx.saved = None
-        return (None, None, None, None, None, dx) + tuple(grads.get("glocal_transformer." + n) for n in ctx.names)
+        dx, grads = E.run_transformer_backward(ctx.sess, ctx.desc, dout.contiguous().float(), ctx.P)
+        ctx.sess = None
+        if ctx.plan.Mg == 0:   # single-frame input: the temporal decoder is never reached (lib/transformer_wk.py:187-188)
+            grads = {n: g for n, g in grads.items() if "global_attention" not in n and "position_embedding" not in n}
+        return (None, None, None, None, None, None, None, dx) + tuple(grads.get(n) for n in ctx.names)
 
 
 class transformer_wk(nn.Module):
@@ -72,6 +73,7 @@ class transformer_wk(nn.Module):
         nn.init.uniform_(self.position_embedding.weight)
         self._precision = precision
         self._kernels = None
+        self._desc = None
 
     def forward(self, features, im_idx):
         if not features.is_cuda:
@@ -80,10 +82,14 @@ class transformer_wk(nn.Module):
             self._kernels = E.Kernels(self._precision or os.environ.get("NLV_PRECISION", "bf16"))
         fid = im_idx.detach().cpu().numpy()
         plan = E.Plan([0], [fid], features.device)
-        P = dict(self.named_parameters())
-        names = list(P.keys())
-        want = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in P.values()))
-        out = _TransformerFn.apply(self._kernels, plan, P, names, want, features, *P.values())
+        params = dict(self.named_parameters())
+        P = {n: t.detach() for n, t in params.items()}
+        if self._desc is None:
+            self._desc = E.ModelDesc(self._kernels, P, "sttran", "predcls", transformer_prefix="")
+        names = list(params.keys())
+        want = torch.is_grad_enabled() and (features.requires_grad or any(p.requires_grad for p in params.values()))
+        self._kernels.seed += 1
+        out = _TransformerFn.apply(self._kernels, self._desc, plan, P, names, want, self.training, features, *params.values())
         return out, None, None
 
 

@@ -94,14 +94,15 @@ def input_bytes(hb: Batch) -> int:
     return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in TENSOR_KEYS if getattr(hb, k) is not None))
 
 
-def make_plan(b: Batch, device, mode: str, dsg: bool = False, with_labels: bool = False, consumer_stream=None) -> "E.Plan":
+def make_plan(b: Batch, device, mode: str, dsg: bool = False, with_labels: bool = False, consumer_stream=None,
+              label_rng=None) -> "E.Plan":
     """Descriptors (+ optionally the loss labels) -> one pinned async upload.  plan.labels is set when with_labels."""
     obj_class = subj_box = None
     if dsg:
         lab = b.labels.cpu().numpy()
         pi = b.pair_idx.cpu().numpy()
         obj_class, subj_box = lab[pi[:, 1]], pi[:, 0]
-    extra = label_arrays(b) if with_labels else None
+    extra = label_arrays(b, label_rng) if with_labels else None
     plan = E.Plan(b.n_boxes, b.frame_ids, torch.device(device), obj_class=obj_class, subj_box=subj_box, dsg=dsg,
                   dsg_pos_by_rank=(mode == "sgdet"), extra=extra, consumer_stream=consumer_stream)
     if with_labels:
@@ -116,95 +117,61 @@ def make_batch(entries: List[dict], device, mode: str, dsg: bool = False):
     """collate + upload + plan; returns (Batch on device, Plan)."""
     hb = collate(entries, mode)
     plan = make_plan(hb, device, mode, dsg)
-    return upload(hb, device), plan
+    return upload(hb, device, rasterise=False), plan      # masks the producer did not supply are rasterised inside the forward call
 
 
 # ================================================================================================
-# STTran
+# whole-model forward / backward: one C call each (csrc/step.cu)
 # ================================================================================================
+def _desc(k: E.Kernels, P, arch: str, mode: str) -> E.ModelDesc:
+    cache = k.__dict__.setdefault("_desc_cache", {})
+    key = (arch, mode, len(P))
+    d = cache.get(key)
+    if d is None:
+        d = cache[key] = E.ModelDesc(k, P, arch, mode)
+    return d
+
+
+def _forward(arch: str, k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, training: bool, want_ctx: bool, **kw):
+    desc = _desc(k, P, arch, mode)
+    kw.setdefault("fresh_ws", True)     # the outputs are views of the call's workspace: callers of this API own them
+    out, sess = E.run_forward(k, desc, P, batch, plan, training, want_ctx, **kw)
+    if batch.spatial_masks is None:
+        batch.spatial_masks = out["spatial_masks"]      # rasterised inside the call (a3)
+    return out, ((sess, desc) if want_ctx else None)
+
+
+def _backward(k: E.Kernels, P, ctx, d26, dobj, grads=None):
+    """Returns {name: gradient} — views of ONE flat fp32 buffer (zeroed by the call, so parameters the batch does not
+    reach come back as exact zeros)."""
+    sess, desc = ctx
+    flat = torch.empty(desc.grad_elems, device=d26.device, dtype=F32)
+    E.set_gradients(sess, desc, flat)
+    E.run_backward(sess, d26.contiguous(), dobj.contiguous() if dobj is not None else None)
+    grads = {} if grads is None else grads
+    for n in desc.grad_names:
+        o = desc.grad_off[n]
+        grads[n] = flat[o:o + P[n].numel()].view(P[n].shape)
+    return grads
+
+
 def sttran_forward(k: E.Kernels, P: Dict[str, torch.Tensor], batch: Batch, plan: E.Plan, mode: str, training: bool,
-                   want_ctx: bool):
+                   want_ctx: bool, **kw):
     """lib/sttran.py:375-411.  Returns (outputs dict, ctx)."""
-    ctx = {}
-    out = {}
-    if mode == "predcls":
-        feat_op = k.opnd(batch.features)
-        ctx["oc"] = None
-    else:
-        logits, objfeat, ctx["oc"] = E.object_classifier_fwd(k, P, plan, batch.features, batch.distribution, batch.boxes,
-                                                            training, want_ctx)
-        out["distribution"] = logits
-        feat_op = objfeat[:, :2048]
-    rel, ctx["pt"] = E.pair_tokens_fwd(k, P, plan, feat_op, batch.union_feat, batch.spatial_masks, batch.pair_idx,
-                                       batch.labels, training, want_ctx)
-    glob, ctx["tr"] = E.sttran_transformer_fwd(k, P, plan, rel, want_ctx)
-    logits26 = E.heads_fwd(k, P, glob)
-    ctx["glob"], ctx["logits26"] = glob, logits26
-    out["logits26"] = logits26
-    return out, (ctx if want_ctx else None)
+    return _forward("sttran", k, P, batch, plan, mode, training, want_ctx, **kw)
 
 
-def sttran_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits, grads=None):
-    """`grads`: any mapping that accepts grads[name] = tensor (a dict, or the trainer's flat-buffer sink)."""
-    grads = {} if grads is None else grads
-    dglob = E.heads_bwd(k, P, ctx["glob"], dlogits26, grads)
-    drel = E.sttran_transformer_bwd(k, P, plan, ctx["tr"], dglob, grads)
-    E.pair_tokens_bwd(k, P, plan, ctx["pt"], drel, grads)
-    if mode != "predcls" and dobj_logits is not None:
-        E.object_classifier_bwd(k, P, plan, ctx["oc"], dobj_logits, grads)
-    return grads
+def sttran_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx, dlogits26, dobj_logits, grads=None):
+    return _backward(k, P, ctx, dlogits26, dobj_logits if mode != "predcls" else None, grads)
 
 
-# ================================================================================================
-# DSG-DETR (sgdet): lib/dsg_detr.py:514-572
-# ================================================================================================
-def dsg_forward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, training: bool, want_ctx: bool):
-    ctx = {}
-    out = {}
-    if mode == "predcls":
-        feat_op = k.opnd(batch.features)
-        ctx["oc"] = None
-    else:
-        logits, objfeat, ctx["oc"] = E.object_classifier_fwd(k, P, plan, batch.features, batch.distribution, batch.boxes,
-                                                            training, want_ctx)
-        out["distribution"] = logits
-        feat_op = objfeat[:, :2048]
-    rel, ctx["pt"] = E.pair_tokens_fwd(k, P, plan, feat_op, batch.union_feat, batch.spatial_masks, batch.pair_idx,
-                                       batch.labels, training, want_ctx)
-    x, _, ctx["loc"] = E.encoder_fwd(k, P, "local_transformer.layers.0.", "self_attn", rel, k.opnd(rel), plan.local_work,
-                                     plan.n_local_work, want_ctx, out_op=False)
-    pe = P["positional_encoder.pe"].reshape(-1, E.D_MODEL)
-    # class-sorted stream + sinusoidal encoding of the frame rank (dsg_detr.py:545-559)
-    g, gop = ops.gather_rows(x, plan.cls_perm, plan.R, out_dtype=F32, add=pe, add_idx=plan.cls_pos,
-                             out2_dtype=torch.bfloat16 if k.AD == torch.bfloat16 else None)
-    if gop is None:
-        gop = g
-    ctx["glob"] = []
-    for i in range(3):
-        g, gop, c = E.encoder_fwd(k, P, f"global_transformer.layers.{i}.", "self_attn", g, gop, plan.cls_work,
-                                  plan.n_cls_work, want_ctx, out_op=(i < 2))
-        ctx["glob"].append(c)
-    glob, _ = ops.gather_rows(g, plan.cls_iperm, plan.R, out_dtype=F32)
-    logits26 = E.heads_fwd(k, P, glob)
-    ctx["globout"], ctx["logits26"] = glob, logits26
-    out["logits26"] = logits26
-    return out, (ctx if want_ctx else None)
+def dsg_forward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, training: bool, want_ctx: bool, **kw):
+    """DSG-DETR (sgdet): lib/dsg_detr.py:514-572."""
+    return _forward("dsg", k, P, batch, plan, mode, training, want_ctx, **kw)
 
 
-def dsg_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx: dict, dlogits26, dobj_logits, grads=None):
-    grads = {} if grads is None else grads
-    dglob = E.heads_bwd(k, P, ctx["globout"], dlogits26, grads)
-    dg, _ = ops.gather_rows(dglob, plan.cls_perm, plan.R, out_dtype=F32)
-    for i in reversed(range(3)):
-        dg = E.encoder_bwd(k, P, f"global_transformer.layers.{i}.", "self_attn", ctx["glob"][i], dg, plan.cls_work,
-                           plan.n_cls_work, grads)
-    dx, _ = ops.gather_rows(dg, plan.cls_iperm, plan.R, out_dtype=F32)   # the encoding is a constant buffer
-    drel = E.encoder_bwd(k, P, "local_transformer.layers.0.", "self_attn", ctx["loc"], dx, plan.local_work,
-                         plan.n_local_work, grads)
-    E.pair_tokens_bwd(k, P, plan, ctx["pt"], drel, grads)
-    if mode != "predcls" and dobj_logits is not None:
-        E.object_classifier_bwd(k, P, plan, ctx["oc"], dobj_logits, grads)
-    return grads
+def dsg_backward(k: E.Kernels, P, batch: Batch, plan: E.Plan, mode: str, ctx, dlogits26, dobj_logits, grads=None):
+    return _backward(k, P, ctx, dlogits26, dobj_logits if mode != "predcls" else None, grads)
 
 
 # ================================================================================================
@@ -214,39 +181,56 @@ class Labels:
     pass
 
 
-def _bits_of(lists) -> np.ndarray:
-    """uint32 multi-hot mask per row from a list of index lists (vectorised)."""
+def _flat_lists(lists):
+    """(values int64[total], row int64[total], lens int64[n]) of a list of index lists."""
     n = len(lists)
     lens = np.fromiter((len(x) for x in lists), dtype=np.int64, count=n)
-    out = np.zeros(n, dtype=np.uint32)
-    if lens.sum() == 0:
-        return out
-    flat = np.fromiter((int(j) for x in lists for j in x), dtype=np.int64, count=int(lens.sum()))
-    rows = np.repeat(np.arange(n), lens)
-    np.bitwise_or.at(out, rows, (np.uint32(1) << flat.astype(np.uint32)))
+    total = int(lens.sum())
+    vals = np.fromiter((j for x in lists for j in x), dtype=np.int64, count=total) if total else np.zeros(0, dtype=np.int64)
+    return vals, np.repeat(np.arange(n), lens), lens
+
+
+def _bits_of(lists) -> np.ndarray:
+    """uint32 multi-hot mask per row from a list of index lists (vectorised)."""
+    vals, rows, lens = _flat_lists(lists)
+    out = np.zeros(len(lists), dtype=np.uint32)
+    if len(vals):
+        np.bitwise_or.at(out, rows, (np.uint32(1) << vals.astype(np.uint32)))
     return out
 
 
-def label_arrays(batch: Batch) -> dict:
+def label_arrays(batch: Batch, rng: Optional[np.random.Generator] = None) -> dict:
     """Label tensors + per-row loss weights from the python label lists of the entries (train_STTran.py:143-167).
-    Weight = 1 / (rows of that video entering the mean) / (classes, for BCE) / videos."""
+    Weight = 1 / (rows of that video entering the mean) / (classes, for BCE) / videos.  A pair with several attention
+    labels contributes ONE of them per step: the reference draws it with np.random.choice (:148-150) — pass `rng` for that;
+    without it the first label is taken (deterministic; what the parity fixtures use).  All videos in one numpy pass."""
     nv = len(batch.n_boxes)
-    att, w_att, spa_bits, w_spa, con_bits, w_con, w_obj = [], [], [], [], [], [], []
-    for (a_gt, s_gt, c_gt), nb in zip(batch.gt_lists, batch.n_boxes):
-        n = len(a_gt)
-        a = np.fromiter((int(x[0]) if len(x) else -1 for x in a_gt), dtype=np.int64, count=n)
-        na = int((a >= 0).sum())
-        att.append(a)
-        w_att.append(np.where(a >= 0, 1.0 / (max(na, 1) * nv), 0.0).astype(np.float32))
-        sb, cb = _bits_of(s_gt), _bits_of(c_gt)
-        ns, nc = int((sb != 0).sum()), int((cb != 0).sum())
-        spa_bits.append(sb); con_bits.append(cb)
-        w_spa.append(np.where(sb != 0, 1.0 / (max(ns, 1) * 6 * nv), 0.0).astype(np.float32))
-        w_con.append(np.where(cb != 0, 1.0 / (max(nc, 1) * 17 * nv), 0.0).astype(np.float32))
-        w_obj.append(np.full(nb, 1.0 / (max(nb, 1) * nv), dtype=np.float32))
-    c = np.concatenate
-    return {"lab_att": c(att), "lab_w_att": c(w_att), "lab_spa_bits": c(spa_bits), "lab_w_spa": c(w_spa),
-            "lab_con_bits": c(con_bits), "lab_w_con": c(w_con), "lab_w_obj": c(w_obj)}
+    n_pairs = np.asarray(batch.n_pairs, dtype=np.int64)
+    a_all = [x for g in batch.gt_lists for x in g[0]]
+    s_all = [x for g in batch.gt_lists for x in g[1]]
+    c_all = [x for g in batch.gt_lists for x in g[2]]
+    R = len(a_all)
+    vid = np.repeat(np.arange(nv), n_pairs)
+    avals, arows, alens = _flat_lists(a_all)
+    first = np.cumsum(alens) - alens
+    pick = first.copy()
+    if rng is not None and len(avals):
+        multi = alens >= 2
+        pick[multi] += (rng.random(int(multi.sum())) * alens[multi]).astype(np.int64)
+    att = np.full(R, -1, dtype=np.int64)
+    has = alens > 0
+    att[has] = avals[pick[has]]
+    sb, cb = _bits_of(s_all), _bits_of(c_all)
+
+    def weights(mask, classes):
+        cnt = np.bincount(vid[mask], minlength=nv).astype(np.float64)
+        w = 1.0 / (np.maximum(cnt, 1.0) * classes * nv)
+        return np.where(mask, w[vid], 0.0).astype(np.float32)
+
+    nb = np.asarray(batch.n_boxes, dtype=np.int64)
+    w_obj = np.repeat((1.0 / (np.maximum(nb, 1) * nv)).astype(np.float32), nb)
+    return {"lab_att": att, "lab_w_att": weights(att >= 0, 1), "lab_spa_bits": sb, "lab_w_spa": weights(sb != 0, 6),
+            "lab_con_bits": cb, "lab_w_con": weights(cb != 0, 17), "lab_w_obj": w_obj}
 
 
 def make_labels(batch: Batch, device, mode: str) -> Labels:

@@ -358,6 +358,20 @@ def bce_sigmoid_loss(logits, c, bits, row_weight, loss, dlogits):
           _ptr(loss), _ptr(dlogits), dlogits.stride(0) if dlogits is not None else 0)
 
 
+def zero_(t: torch.Tensor) -> torch.Tensor:
+    assert t.is_contiguous()
+    _call("nlv_zero_bytes", _ptr(t), _LL(t.numel() * t.element_size()))
+    return t
+
+
+def heads_activation_bwd(datt, dspa, dcon, spa, con, r):
+    d26 = torch.empty(r, 26, device=spa.device, dtype=torch.float32)
+    c = lambda t: t.contiguous() if t is not None else None
+    datt, dspa, dcon = c(datt), c(dspa), c(dcon)
+    _call("nlv_heads_activation_bwd", _ptr(datt), _ptr(dspa), _ptr(dcon), _ptr(spa), _ptr(con), _LL(r), _ptr(d26))
+    return d26
+
+
 def sumsq(x, out):
     _call("nlv_sumsq", _ptr(x), _LL(x.numel()), _ptr(out))
 

@@ -1,12 +1,26 @@
-"""Fused training step: forward, fused losses, hand-written backward, (NCCL gradient allreduce), global-norm clip and
-AdamW over flat fp32 parameter / gradient / moment buffers — the kernel-level equivalent of one iteration of
-tools/train_STTran.py:129-195 for a batch of videos (loss = mean over videos of the per-video loss)."""
+"""Fused training step: forward, fused losses, hand-written backward (ONE C call each, csrc/step.cu), NCCL gradient
+all-reduce, global-norm clip and AdamW over flat fp32 parameter / gradient / moment buffers — the kernel-level equivalent
+of one iteration of tools/train_STTran.py:129-195 for a batch of videos (loss = mean over videos of the per-video loss).
+
+Reference behaviours kept:
+  * `check_valid_iter` (lib/utils.py:3-11, train_STTran.py:191): a step whose loss or gradient norm is not finite is
+    skipped — decided ON THE DEVICE (no host sync), agreed across ranks (the flag is max-reduced; NaN gradients poison
+    the all-reduced norm on every rank alike); `Trainer.steps_applied()` / `steps_skipped()` read the counters back.
+  * lib/AdamW.py:66 skips parameters without a gradient: parameters the mode never reaches are not in the flat buffers
+    (object classifier in predcls); when a batch has no sliding window at all (every video a single frame) the temporal
+    decoder and the frame position embedding are left untouched for that step.
+  * tools/train_STTran.py:148-150: a pair with several attention labels trains on one drawn at random per step
+    (`label_rng`; None = the first label, deterministic).
+"""
 from __future__ import annotations
 
-from typing import Dict, List
+import ctypes
+from typing import Dict, Optional
 
+import numpy as np
 import torch
 
+from . import _C
 from . import dist as D
 from . import engine as E
 from . import model as M
@@ -14,52 +28,29 @@ from . import ops
 
 F32 = torch.float32
 
-
-class GradSink(dict):
-    """grads[name] = tensor  ->  copied into the parameter's slice of the flat gradient buffer."""
-
-    def __init__(self, views: Dict[str, torch.Tensor]):
-        super().__init__()
-        self.views = views
-        self.seen = set()
-
-    def __setitem__(self, name, value):
-        v = self.views[name]
-        assert value.numel() == v.numel(), name
-        ops.convert(value.contiguous().reshape(1, -1), F32, out=v.reshape(1, -1))
-        self.seen.add(name)
+_OP_SUFFIX = ("in_proj_weight", "out_proj.weight", "linear1.weight", "linear2.weight")
+_OP_NAMES = ("object_classifier.decoder_lin.0.weight", "union_func1.weight", "subj_fc.weight", "obj_fc.weight")
 
 
 class Trainer:
     def __init__(self, state: Dict[str, torch.Tensor], mode: str = "sgdet", arch: str = "sttran", precision: str = "bf16",
                  lr: float = 1e-5, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2, max_norm: float = 5.0,
-                 device="cuda"):
+                 device="cuda", dropout: float = 0.0, label_seed: Optional[int] = None):
         dev = torch.device(device)
         self.mode, self.arch, self.dev = mode, arch, dev
-        self.k = E.Kernels(precision)
+        self.k = E.Kernels(precision, dropout=dropout)
         self.lr, self.betas, self.eps, self.wd, self.max_norm = lr, betas, eps, weight_decay, max_norm
-        is_param = lambda n: not (n.endswith("running_mean") or n.endswith("running_var") or n.endswith("num_batches_tracked")
-                                  or n.endswith(".pe"))
-        names = [n for n in state if is_param(n) and "encoder_tran" not in n]
-        # groups that the kernels consume as ONE matrix are laid out adjacently so a single view serves them
-        groups = [["subj_fc.weight", "obj_fc.weight"], ["subj_fc.bias", "obj_fc.bias"],
-                  ["a_rel_compress.weight", "s_rel_compress.weight", "c_rel_compress.weight"],
-                  ["a_rel_compress.bias", "s_rel_compress.bias", "c_rel_compress.bias"]]
-        grouped = {n for g in groups for n in g}
-        self.param_names = [n for g in groups for n in g] + [n for n in names if n not in grouped]
-        self.offsets: Dict[str, int] = {}
-        off = 0
-        for n in self.param_names:
-            if state[n].dim() >= 2:
-                off += (-off) % 8             # 16-byte aligned rows for the bf16 mirror (TMA)
-            self.offsets[n] = off
-            off += state[n].numel()
-        total, pad = off, (-off) % 8
-        self.flat_p = torch.zeros(total + pad, device=dev, dtype=F32)
-        self.flat_g = torch.zeros(total + pad, device=dev, dtype=F32)
-        self.flat_m = torch.zeros(total + pad, device=dev, dtype=F32)
-        self.flat_v = torch.zeros(total + pad, device=dev, dtype=F32)
-        self.flat_pb = torch.zeros(total + pad, device=dev, dtype=torch.bfloat16) if precision == "bf16" else None
+        self.label_rng = np.random.default_rng(label_seed) if label_seed is not None else None
+        state = {n: t for n, t in state.items() if "encoder_tran" not in n and not n.startswith("object_classifier.positional_encoder")}
+        probe = E.ModelDesc(self.k, state, arch, mode)
+        self.param_names = list(probe.grad_names)
+        self.offsets: Dict[str, int] = dict(probe.grad_off)
+        total = probe.grad_elems
+        self.flat_p = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_g = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_m = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_v = torch.zeros(total, device=dev, dtype=F32)
+        self.flat_pb = torch.zeros(total, device=dev, dtype=torch.bfloat16) if precision == "bf16" else None
         self.P: Dict[str, torch.Tensor] = {}
         self.gviews: Dict[str, torch.Tensor] = {}
         for n in self.param_names:
@@ -67,63 +58,91 @@ class Trainer:
             self.P[n] = self.flat_p[off:off + t.numel()].view(t.shape)
             self.P[n].copy_(t)
             self.gviews[n] = self.flat_g[off:off + t.numel()].view(t.shape)
-        for n, t in state.items():
-            if n not in self.P and "encoder_tran" not in n:
-                self.P[n] = t.to(dev).clone()
+        for n, t in state.items():      # buffers (BN running statistics, positional encoding) and unreached parameters
+            if n not in self.P:
+                self.P[n] = t.to(dev).clone().contiguous()
         self._install_mirror()
+        self.desc = E.ModelDesc(self.k, self.P, arch, mode, static=True)
+        assert self.desc.grad_off == self.offsets
+        self._goff = self.desc.grad_offsets()
         self.total_sq = torch.zeros(1, device=dev, dtype=F32)
-        self.step_count = 0
+        self.state = torch.zeros(2, device=dev, dtype=torch.int32)     # [steps applied, steps skipped]
+        self.skip_flag = torch.zeros(1, device=dev, dtype=torch.int32)
         self.n_params = self.flat_p.numel()
-        self.last_sink = None
+        # the parameters a window-less batch does not reach: position embedding + temporal decoder (contiguous slot ranges)
+        self._tail_ranges = None
+        if arch == "sttran":
+            pos = "glocal_transformer.position_embedding.weight"
+            dec0 = [n for n in self.param_names if n.startswith("glocal_transformer.global_attention.")]
+            if dec0:
+                self._tail_ranges = ((self.offsets[pos], self.offsets[pos] + (self.P[pos].numel() + 7) // 8 * 8), (self.offsets[dec0[0]], total))
+        self.last = None
+        self._loss_ring, self._loss_i = torch.zeros(8, device=dev, dtype=F32), 0
 
     def _install_mirror(self):
-        """Operand views the kernels can use without per-step conversion: the bf16 mirror of the flat parameter buffer
-        (rewritten by the AdamW kernel) and fp32 views of parameter groups that are consumed as one matrix."""
-        mir = self.k.mirror
-        o = self.offsets
-        f32view = lambda first, rows, cols: self.flat_p[o[first]:o[first] + rows * cols].view(rows, cols)
-        mir["heads.weight"] = f32view("a_rel_compress.weight", 26, 1936)
-        mir["heads.bias"] = self.flat_p[o["a_rel_compress.bias"]:o["a_rel_compress.bias"] + 26]
-        mir["subjobj.bias"] = self.flat_p[o["subj_fc.bias"]:o["subj_fc.bias"] + 1024]
+        """bf16 operand mirror of the flat parameter buffer (rewritten by the AdamW kernel): the GEMM weights are used from
+        it without a per-step conversion."""
         if self.flat_pb is None:
-            mir["subjobj.weight"] = f32view("subj_fc.weight", 1024, 2048)
             return
-        from . import ops as _ops
-        _ops.convert(self.flat_p.view(1, -1), torch.bfloat16, out=self.flat_pb.view(1, -1))
-        bview = lambda n, shape: self.flat_pb[o[n]:o[n] + int(__import__('math').prod(shape))].view(shape)
-        mir["subjobj.weight"] = bview("subj_fc.weight", (1024, 2048))
+        ops.convert(self.flat_p.view(1, -1), torch.bfloat16, out=self.flat_pb.view(1, -1))
         for n in self.param_names:
-            t = self.P[n]
-            if t.dim() == 2 and t.shape[1] % 8 == 0 and t.shape[0] >= 64 and not n.endswith("_rel_compress.weight") \
-                    and n not in ("vr_fc.weight", "subj_fc.weight", "obj_fc.weight", "obj_embed.weight", "obj_embed2.weight",
-                                  "object_classifier.obj_embed.weight", "object_classifier.pos_embed.1.weight",
-                                  "object_classifier.decoder_lin.3.weight"):
-                mir[n] = bview(n, tuple(t.shape))
-        mir["union_func1.weight"] = bview("union_func1.weight", (256, 2048))
+            if n in _OP_NAMES or (n.endswith(_OP_SUFFIX) and ("attention" in n or "transformer" in n)):
+                o = self.offsets[n]
+                self.k.mirror[n] = self.flat_pb[o:o + self.P[n].numel()].view(self.P[n].shape[0], -1)
 
+    # ---- one step ------------------------------------------------------------------------------------------------
     def forward_backward(self, batch: M.Batch, plan=None):
         """batch: device-resident collated batch.  Plan + labels are (re)built from its host metadata every call —
         they replace the reference's per-frame python loops and are part of the step."""
         dsg = self.arch == "dsg"
         if plan is None:
-            plan = M.make_plan(batch, self.dev, self.mode, dsg, with_labels=True)
-        labels = plan.labels
-        fwd = M.dsg_forward if dsg else M.sttran_forward
-        bwd = M.dsg_backward if dsg else M.sttran_backward
-        out, ctx = fwd(self.k, self.P, batch, plan, self.mode, True, True)
-        loss, d26, dobj = M.fused_loss(out, batch, labels, self.mode)
-        self.last_sink = GradSink(self.gviews)
-        bwd(self.k, self.P, batch, plan, self.mode, ctx, d26, dobj, grads=self.last_sink)
-        return loss, out
+            plan = M.make_plan(batch, self.dev, self.mode, dsg, with_labels=True, label_rng=self.label_rng)
+        self.k.seed += 1
+        out, sess = E.run_forward(self.k, self.desc, self.P, batch, plan, True, True, labels=plan.labels, with_loss=True,
+                                  with_backward=True, grad_base=self.flat_g, grad_offsets=self._goff)
+        E.run_backward(sess)
+        self.last = (out, plan)
+        # the workspace is reused by the next step: the loss a caller may hold on to goes to a small ring of its own
+        slot = self._loss_ring[self._loss_i % 8:self._loss_i % 8 + 1]
+        self._loss_i += 1
+        ops.convert(out["loss"].view(1, 1), F32, out=slot.view(1, 1))
+        return slot, out
 
     def optimizer_step(self):
-        D.allreduce_mean_(self.flat_g)      # no-op on one rank
-        self.step_count += 1
-        self.total_sq.zero_()
+        lib = _C.lib()
+        st = ops._stream()
+        out, plan = self.last if self.last is not None else (None, None)
+        w = D.world()
+        if out is not None:
+            _C.check(lib.nlv_flag_nonfinite(ops._ptr(out["loss"]), 1, ops._ptr(self.skip_flag), st), "flag_nonfinite")
+        D.allreduce_sum_(self.flat_g, flag=self.skip_flag)      # no-op on one rank; the mean's 1/world is folded into AdamW
+        ops.zero_(self.total_sq)
         ops.sumsq(self.flat_g, self.total_sq)
-        ops.adamw_step(self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.lr, self.betas[0], self.betas[1], self.eps,
-                       self.wd, self.step_count, self.total_sq, self.max_norm, p_bf16=self.flat_pb)
-        self.k._wcache.clear()   # derived operand copies (permuted / padded weights) are stale now; mirrored ones are not
+        ranges = [(0, self.n_params)]
+        if self._tail_ranges is not None and plan is not None and plan.Mg == 0:
+            (p0, p1), (d0, _) = self._tail_ranges
+            ranges = [(0, p0), (p1, d0)]
+        for a, b in ranges:
+            if b <= a:
+                continue
+            pb = ctypes.c_void_p(self.flat_pb.data_ptr() + 2 * a) if self.flat_pb is not None else None
+            _C.check(lib.nlv_adamw_step_state(
+                ctypes.c_void_p(self.flat_p.data_ptr() + 4 * a), ctypes.c_void_p(self.flat_g.data_ptr() + 4 * a),
+                ctypes.c_void_p(self.flat_m.data_ptr() + 4 * a), ctypes.c_void_p(self.flat_v.data_ptr() + 4 * a),
+                ctypes.c_longlong(b - a), ctypes.c_float(self.lr), ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]),
+                ctypes.c_float(self.eps), ctypes.c_float(self.wd), ops._ptr(self.state), ops._ptr(self.total_sq), ops._ptr(self.skip_flag),
+                ctypes.c_float(1.0 / w), ctypes.c_float(self.max_norm), pb, st), "adamw_step_state")
+        _C.check(lib.nlv_adamw_finish(ops._ptr(self.state), ops._ptr(self.total_sq), ops._ptr(self.skip_flag), st), "adamw_finish")
+
+    def steps_applied(self) -> int:
+        return int(self.state[0].item())
+
+    def steps_skipped(self) -> int:
+        return int(self.state[1].item())
+
+    @property
+    def step_count(self) -> int:
+        return self.steps_applied()
 
     def step(self, batch: M.Batch):
         loss, _ = self.forward_backward(batch)
@@ -132,7 +151,7 @@ class Trainer:
 
     def step_from_host(self, host_batch: M.Batch):
         """End-to-end step: pinned host buffers -> device inside the step (copies on the compute stream)."""
-        return self.step(M.upload(host_batch, self.dev))
+        return self.step(M.upload(host_batch, self.dev, rasterise=False))
 
     # ---- input pipelining: the next batch's H2D copies run on a side stream while this batch computes ----
     def prefetch(self, host_batch: M.Batch):
@@ -143,7 +162,8 @@ class Trainer:
             self.copy_stream = torch.cuda.Stream(device=self.dev)
         main = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_stream):
-            plan = M.make_plan(host_batch, self.dev, self.mode, self.arch == "dsg", with_labels=True, consumer_stream=main)
+            plan = M.make_plan(host_batch, self.dev, self.mode, self.arch == "dsg", with_labels=True, consumer_stream=main,
+                               label_rng=self.label_rng)
             b = M.upload(host_batch, self.dev, rasterise=False, consumer_stream=main)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)
@@ -155,6 +175,6 @@ class Trainer:
         b, plan, ev = handle
         nxt = self.prefetch(next_host) if next_host is not None else None
         torch.cuda.current_stream(self.dev).wait_event(ev)
-        loss, _ = self.forward_backward(M.ensure_masks(b), plan)
+        loss, _ = self.forward_backward(b, plan)
         self.optimizer_step()
         return loss, nxt

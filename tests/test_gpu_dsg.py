@@ -16,6 +16,7 @@ def _build(case, precision, training):
     m.load_state_dict(synth.make_state_dict(G.dsg_template(), case["seed"]))
     m = m.cuda()
     m.train(training)
+    m.kernels.dropout = 0.0      # parity runs with the dropout probability forced to 0 (masks cannot be RNG-matched)
     return m
 
 
