@@ -138,11 +138,13 @@ int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
                       long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, void* stream);
 int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, long long rows, int c, float momentum,
                  double* sums_ws, float* mean, float* var, float* running_mean, float* running_var, void* stream);
-int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const float* mean, const float* var,
+/* row_seg[r / row_div] = statistics segment (video) of row r (row_seg NULL: segment 0); row_div = rows per indexed unit
+ * (1 for per-box arrays, 49 / 196 for the per-pair conv maps) */
+int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, int row_div, const float* mean, const float* var,
                  const float* w, const float* b, float eps, int relu, long long rows, int c, void* y, int y_dtype, int ldy,
                  void* y2, int y2_dtype, int ldy2, void* stream);
 int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
-               const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
+               const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx,
                float* dw, float* db, void* stream);
 
@@ -232,6 +234,14 @@ int nlv_convert_multi(const void* const* src_host, void* const* dst_host, const 
  * NCHW parameter layout and the channels-last operand layout of the kernels, and back for their gradients */
 int nlv_permute_021(const void* src, int src_dtype, int a, int b, int c, void* dst, int dst_dtype, void* stream);
 int nlv_zero_bytes(void* p, long long nbytes, void* stream);
+/* Packed per-video feature files (nlvsgg_b200/featfile.py; replaces the per-frame dets.npy / feat.npy of
+ * lib/assign_pseudo_label.py:27-45): zero-suppressed channels-last union features -> dense bf16 rows [rows, 2048].
+ * bitmap u64[rows,32] (bit c of word w = channel 64 w + c is stored), off u32[rows+1] = first value of each row, vals bf16
+ * (16-byte aligned, padded by 16 bytes). */
+int nlv_union_unpack(const void* bitmap, const unsigned* off, const void* vals, long long rows, void* dst_bf16, void* stream);
+/* lib/assign_pseudo_label.py:934-938 create_dis on device: out f32[n,36] = conf at idx, `other` elsewhere (and at idx when
+ * conf == 0); other NULL -> (1 - conf) / 35 in fp32 arithmetic */
+int nlv_create_dis(const float* conf, const float* other, const int* idx, long long n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Whole-model sequencer: one call enqueues the complete kernel sequence of
@@ -305,15 +315,21 @@ typedef struct nlv_batch {
   const long long* labels;                /* [N] labels used for the semantic embeddings (pred_labels) */
   const float* distribution;              /* [N,36] (sgdet / sgcls) */
   const void* union_feat; int union_dtype;
-  int union_rows;                         /* 0: NCHW [R,2048,7,7] (entry contract); 1: channels-last rows [R*49,2048] */
+  int union_rows;                         /* 0: NCHW [R,2048,7,7] (entry contract); 1: channels-last rows [R*49,2048];
+                                             2: zero-suppressed rows: union_feat = bf16 values, + union_bitmap / union_off */
   const float* spatial_masks;             /* [R,2,27,27] or NULL -> rasterised from boxes + pair_idx */
   const long long* pair_idx;              /* [R,2] */
   /* host-built descriptors (nlvsgg_b200/plan.py), int32 device arrays */
-  const int *box_seg, *seg196, *seg49, *box_row, *row196, *row49;
+  const int *box_seg, *seg196, *seg49;    /* [nv+1] row offsets of every video in the box / 196-per-pair / 49-per-pair arrays */
+  const int *box_row, *pair_row;          /* [N], [R]: video of a box / pair (NULL when nv == 1) */
   const int *local_work; int n_local_work;
   const int *glob_work; int n_glob_work;
   const int *stream_src, *stream_slot, *inv, *out_src, *out_inv, *passthrough; int has_passthrough;
   const int *cls_perm, *cls_iperm, *cls_pos, *cls_work; int n_cls_work;   /* DSG-DETR class sequences */
+  /* packed-file inputs (nlvsgg_b200/featfile.py): occupancy words + row offsets of zero-suppressed union features;
+   * (confidence, class) per box from which `distribution` is rebuilt on device when distribution == NULL */
+  const void* union_bitmap; const unsigned* union_off;
+  const float* dist_conf; const float* dist_other; const int* dist_idx;
   /* fused-loss labels (tools/train_STTran.py:143-167), NULL for inference */
   const long long* lab_att; const float* w_att; const unsigned* spa_bits; const float* w_spa;
   const unsigned* con_bits; const float* w_con; const float* w_obj;
@@ -337,6 +353,12 @@ typedef struct nlv_outputs {
 
 /* out[0..3] = sizeof(nlv_model), sizeof(nlv_batch), sizeof(nlv_outputs), sizeof(nlv_gemm_args); returns 4 */
 int nlv_struct_sizes(int* out, int n);
+
+/* diagnostic per-call timing of the sequencer (bench.py roofline legs): nlv_profile(1) records CUDA events around every
+ * kernel entry; nlv_profile_read synchronises, writes "name\tms\tflops\tunits\tm\tn\tk\tdtype\n" lines into buf (NULL: size only),
+ * clears the records and returns the bytes needed */
+int nlv_profile(int on);
+long long nlv_profile_read(char* buf, long long cap);
 
 typedef struct nlv_session nlv_session;
 nlv_session* nlv_session_create(void);

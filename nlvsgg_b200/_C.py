@@ -80,11 +80,12 @@ class BatchDesc(ctypes.Structure):
     _fields_ = [("nv", _i), ("n_boxes", _ll), ("n_pairs", _ll), ("n_stream", _ll),
                 ("features", _vp), ("feat_dtype", _i), ("boxes", _vp), ("labels", _vp), ("distribution", _vp),
                 ("union_feat", _vp), ("union_dtype", _i), ("union_rows", _i), ("spatial_masks", _vp), ("pair_idx", _vp),
-                ("box_seg", _ip), ("seg196", _ip), ("seg49", _ip), ("box_row", _ip), ("row196", _ip), ("row49", _ip),
+                ("box_seg", _ip), ("seg196", _ip), ("seg49", _ip), ("box_row", _ip), ("pair_row", _ip),
                 ("local_work", _ip), ("n_local_work", _i), ("glob_work", _ip), ("n_glob_work", _i),
                 ("stream_src", _ip), ("stream_slot", _ip), ("inv", _ip), ("out_src", _ip), ("out_inv", _ip), ("passthrough", _ip),
                 ("has_passthrough", _i),
                 ("cls_perm", _ip), ("cls_iperm", _ip), ("cls_pos", _ip), ("cls_work", _ip), ("n_cls_work", _i),
+                ("union_bitmap", _vp), ("union_off", _vp), ("dist_conf", _vp), ("dist_other", _vp), ("dist_idx", _vp),
                 ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp)]
 
 

@@ -228,9 +228,68 @@ im2col_mask_pair_kernel(const float* __restrict__ m, __nv_bfloat16* __restrict__
   }
 }
 
-// column sums with 8 channels per thread: block (C8x, 256/C8x) ; grid (ceil(C8/bx), row splits)
-__global__ void colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, long long rows, int C8,
-                                 const int* __restrict__ row_class, int n_class, float* __restrict__ out, int cols) {
+// column sums with 8 channels per thread: block (C8x, 256/C8x) ; grid (ceil(C8/bx), row splits).
+// NC = 1 or 2 row classes accumulated in ONE pass (the decoder's per-slot sums); four rows in flight per thread so that
+// enough bytes are outstanding per SM to cover the DRAM latency (the loop is a pure stream: ~40 KB in flight per SM needed).
+template <int NC>
+__global__ void __launch_bounds__(256)
+colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, long long rows, int C8,
+                 const int* __restrict__ row_class, float* __restrict__ out, int cols) {
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  const long long per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = (long long)blockIdx.y * per, r1 = min(rows, r0 + per);
+  float acc[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[c][q] = 0.f;
+  constexpr int U = 4;
+  if (c8 < C8) {
+    for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
+      V8 v[U];
+      int cl[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long rr = r + (long long)u * blockDim.y;
+        cl[u] = -1;
+        if (rr < r1) {
+          v[u] = ld8(x, xdt, (size_t)rr * ld + (size_t)c8 * 8);
+          cl[u] = (NC > 1 && row_class != nullptr) ? row_class[rr] : 0;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+          if (cl[u] == c) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[c][q] += v[u].v[q];
+          }
+    }
+  }
+  // reduce over threadIdx.y in shared memory, then one atomic per column per block
+  __shared__ float red[256 * 8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    float* mine = red + (threadIdx.y * blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mine[q] = acc[c][q];
+    __syncthreads();
+    if (threadIdx.y == 0 && c8 < C8) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float t = 0.f;
+        for (int yy = 0; yy < blockDim.y; ++yy) t += red[(yy * blockDim.x + threadIdx.x) * 8 + q];
+        atomicAdd(out + (size_t)c * cols + c8 * 8 + q, t);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// any number of classes: one pass per class
+__global__ void colsum_v8_multi_kernel(const void* __restrict__ x, int xdt, int ld, long long rows, int C8,
+                                       const int* __restrict__ row_class, int n_class, float* __restrict__ out, int cols) {
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
   const long long r0 = (long long)blockIdx.y * per, r1 = min(rows, r0 + per);
@@ -243,7 +302,6 @@ __global__ void colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, lo
 #pragma unroll
           for (int q = 0; q < 8; ++q) acc[q] += v.v[q];
         }
-    // reduce over threadIdx.y in shared memory, then one atomic per column per block
     __shared__ float red[256 * 8];
     float* mine = red + (threadIdx.y * blockDim.x + threadIdx.x) * 8;
 #pragma unroll
@@ -349,10 +407,17 @@ int launch_colsum_v8(const void* x, int xdt, int ld, long long rows, int cols, c
   int bx = 1;
   while (bx < C8 && bx < 32) bx <<= 1;
   const int by = 256 / bx;
-  int splits = (int)((rows + 64 * by - 1) / (64 * by));
+  const int gx = cdiv(C8, bx);
+  // ~4 blocks per SM, but at least 4 * by rows per block (one unrolled iteration per thread)
+  long long splits = (4ll * sm_count() + gx - 1) / gx;
+  const long long max_splits = (rows + 4 * by - 1) / (4 * by);
+  if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
-  if (splits > 2048) splits = 2048;
-  colsum_v8_kernel<<<dim3(cdiv(C8, bx), splits), dim3(bx, by), 0, s>>>(x, xdt, ld, rows, C8, row_class, n_class, out, cols);
+  if (splits > 65535) splits = 65535;
+  dim3 grid(gx, (unsigned)splits), block(bx, by);
+  if (n_class == 1 || row_class == nullptr) colsum_v8_kernel<1><<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, nullptr, out, cols);
+  else if (n_class == 2) colsum_v8_kernel<2><<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, row_class, out, cols);
+  else colsum_v8_multi_kernel<<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, row_class, n_class, out, cols);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -180,7 +180,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, const int* _
 }
 
 // apply: y = (x - mean[s,c]) * rsqrt(var[s,c] + eps) * w[c] + b[c]  (optional ReLU); up to two outputs
-__global__ void bn_apply_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __restrict__ row_seg,
+__global__ void bn_apply_kernel(const void* __restrict__ x, int xdt, int ldx, const int* __restrict__ row_seg, int row_div,
                                 const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ w,
                                 const float* __restrict__ b, float eps, int relu, long long rows, int C,
                                 void* __restrict__ y, int ydt, int ldy, void* __restrict__ y2, int y2dt, int ldy2) {
@@ -188,7 +188,7 @@ __global__ void bn_apply_kernel(const void* __restrict__ x, int xdt, int ldx, co
   if (i >= rows * C) return;
   const long long r = i / C;
   const int c = (int)(i - r * C);
-  const int s = row_seg ? row_seg[r] : 0;
+  const int s = row_seg ? row_seg[r / row_div] : 0;
   const float m = mean[(size_t)s * C + c], v = var[(size_t)s * C + c];
   float o = (ld_as_float(x, xdt, (size_t)r * ldx + c) - m) * rsqrtf(v + eps) * w[c] + b[c];
   if (relu) o = fmaxf(o, 0.f);
@@ -232,7 +232,7 @@ __global__ void bn_bwd_stats_kernel(const void* __restrict__ dy, int dydt, int l
 // backward pass 2 (training statistics): dx = w*rstd*(dy - sum_dy/n - xhat*sum_dy_xhat/n)
 // eval statistics (use_batch_stats=0): dx = w*rstd*dy.  Output dtype selectable (operand for the next GEMM).
 __global__ void bn_bwd_apply_kernel(const void* __restrict__ dy, int dydt, int lddy, const void* __restrict__ x, int xdt, int ldx,
-                                    const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg,
+                                    const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ row_seg, int row_div,
                                     const int* __restrict__ seg, const float* __restrict__ mean,
                                     const float* __restrict__ var, const float* __restrict__ w, float eps,
                                     const double* __restrict__ sums, int use_batch_stats, int gate_by_x, long long rows, int C,
@@ -241,7 +241,7 @@ __global__ void bn_bwd_apply_kernel(const void* __restrict__ dy, int dydt, int l
   if (i >= rows * C) return;
   const long long r = i / C;
   const int c = (int)(i - r * C);
-  const int s = row_seg ? row_seg[r] : 0;
+  const int s = row_seg ? row_seg[r / row_div] : 0;
   const float m = mean[(size_t)s * C + c], rs = rsqrtf(var[(size_t)s * C + c] + eps);
   float d = ld_as_float(dy, dydt, (size_t)r * lddy + c);
   if (yout != nullptr && !(ld_as_float(yout, ydt, (size_t)r * ldy + c) > 0.f)) d = 0.f;
@@ -284,11 +284,11 @@ int bn_splits(const int* /*seg device*/, long long rows, int nseg) {
 int launch_bn_sums_fwd_v8(const void* x, int xdt, int ld, const int* seg, int nseg, long long rows, int C, double* sums, cudaStream_t s);
 int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
                           int nseg, const float* mean, const float* var, float eps, long long rows, int C, double* sums, cudaStream_t s);
-int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
+int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, int row_div, const float* mean, const float* var, const float* w,
                        const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
                        int ldy2, cudaStream_t s);
 int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
-                           const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
+                           const int* row_seg, int row_div, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s);
 int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
@@ -362,16 +362,17 @@ int nlv_bn_stats(const void* x, int x_dtype, int ld, const int* seg, int nseg, l
 }
 
 /* mean/var are [nseg,C] (training: from nlv_bn_stats with row_seg; eval: running stats with row_seg = null). */
-int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const float* mean, const float* var,
+int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, int row_div, const float* mean, const float* var,
                  const float* w, const float* b, float eps, int relu, long long rows, int c, void* y, int y_dtype, int ldy,
                  void* y2, int y2_dtype, int ldy2, void* stream) {
   NLV_CHECK_ARG(rows >= 0 && c > 0, "bn_apply: bad sizes");
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(x && mean && var && w && b && (y || y2), "bn_apply: null pointer");
+  if (row_div < 1) row_div = 1;
   if ((c & 7) == 0 && (ldx & 7) == 0 && (ldy & 7) == 0 && (ldy2 & 7) == 0 && al16(x) && al16(y) && al16(y2) && al16(mean) && al16(var) &&
       al16(w) && al16(b))
-    return launch_bn_apply_v8(x, x_dtype, ldx, row_seg, mean, var, w, b, eps, relu, rows, c, y, y_dtype, ldy, y2, y2_dtype, ldy2, STREAM);
-  bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(x, x_dtype, ldx, row_seg, mean, var, w, b, eps, relu, rows, c, y,
+    return launch_bn_apply_v8(x, x_dtype, ldx, row_seg, row_div, mean, var, w, b, eps, relu, rows, c, y, y_dtype, ldy, y2, y2_dtype, ldy2, STREAM);
+  bn_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(x, x_dtype, ldx, row_seg, row_div, mean, var, w, b, eps, relu, rows, c, y,
                                                           y_dtype, ldy, y2, y2_dtype, ldy2);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
@@ -380,11 +381,12 @@ int nlv_bn_apply(const void* x, int x_dtype, int ldx, const int* row_seg, const 
 /* Backward.  dy: fp32 or bf16.  yout (optional) = the ReLU'd forward output, masks dy (Linear -> BN -> ReLU).  gate_by_x: zero dx where x <= 0
  * (conv -> ReLU -> BN: x is the ReLU output, so this is the ReLU backward fused in).  dw/db accumulated.  sums_ws as in bn_stats. */
 int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
-               const int* seg, const int* row_seg, int nseg, const float* mean, const float* var, const float* w, float eps,
+               const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
                float* db, void* stream) {
   NLV_CHECK_ARG(nseg >= 1 && c > 0 && rows >= 0, "bn_bwd: bad sizes");
   NLV_CHECK_ARG(dy && x && seg && mean && var && w && sums_ws && dx && dw && db, "bn_bwd: null pointer");
+  if (row_div < 1) row_div = 1;
   { int zrc = zero_fill(reinterpret_cast<float*>(sums_ws), 1, 4 * nseg * c, 4 * nseg * c, STREAM); if (zrc != NLV_OK) return zrc; }
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(nseg <= 65535, "bn_bwd: too many segments");
@@ -393,14 +395,14 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
   if (vec) {
     int rc = launch_bn_sums_bwd_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, nseg, mean, var, eps, rows, c, sums_ws, STREAM);
     if (rc != NLV_OK) return rc;
-    rc = launch_bn_bwd_apply_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean, var, w, eps, sums_ws, use_batch_stats,
+    rc = launch_bn_bwd_apply_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, row_div, seg, mean, var, w, eps, sums_ws, use_batch_stats,
                                 gate_by_x, rows, c, dx, dx_dtype, lddx, STREAM);
     if (rc != NLV_OK) return rc;
   } else {
     dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
     bn_bwd_stats_kernel<<<grid, block, 0, STREAM>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, mean, var, eps, c, sums_ws);
     NLV_CHECK_LAUNCH();
-    bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, seg, mean,
+    bn_bwd_apply_kernel<<<cdiv(rows * c, 256), 256, 0, STREAM>>>(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, row_div, seg, mean,
                                                                 var, w, eps, sums_ws, use_batch_stats, gate_by_x, rows, c, dx, dx_dtype,
                                                                 lddx);
     NLV_CHECK_LAUNCH();

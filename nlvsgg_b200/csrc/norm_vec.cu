@@ -154,7 +154,7 @@ ApplyGeom apply_geometry(int C, long long rows, int unroll) {
 
 template <int U, bool BF>   // BF: x is bf16 (known at compile time: the raw row buffers shrink to 16 bytes)
 __global__ void __launch_bounds__(128)
-bn_apply_v8_kernel(const void* __restrict__ x, int xdt_rt, int ldx, const int* __restrict__ row_seg,
+bn_apply_v8_kernel(const void* __restrict__ x, int xdt_rt, int ldx, const int* __restrict__ row_seg, int row_div,
                    const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ w,
                    const float* __restrict__ b, float eps, int relu, long long rows, long long rows_per_block, int C,
                    void* __restrict__ y, int ydt, int ldy, void* __restrict__ y2, int y2dt, int ldy2) {
@@ -174,7 +174,7 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt_rt, int ldx, const int* _
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
         xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + c0);
-        sg[u] = row_seg ? row_seg[rr] : 0;
+        sg[u] = row_seg ? row_seg[rr / row_div] : 0;
       }
     }
 #pragma unroll
@@ -205,7 +205,7 @@ bn_apply_v8_kernel(const void* __restrict__ x, int xdt_rt, int ldx, const int* _
 template <int U, bool BF>   // BF: dy, x and yout are all bf16
 __global__ void __launch_bounds__(128)
 bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const void* __restrict__ x, int xdt_rt, int ldx,
-                       const void* __restrict__ yout, int ydt_rt, int ldy, const int* __restrict__ row_seg,
+                       const void* __restrict__ yout, int ydt_rt, int ldy, const int* __restrict__ row_seg, int row_div,
                        const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
                        int gate_by_x, long long rows, long long rows_per_block, int C, void* __restrict__ dx, int dxdt, int lddx) {
@@ -227,7 +227,7 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const
         xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + c0);
         gr[u] = nv_ld8_raw(dy, dydt, (size_t)rr * lddy + c0);
         if (yout != nullptr) yr[u] = nv_ld8_raw(yout, ydt, (size_t)rr * ldy + c0);
-        sg[u] = row_seg ? row_seg[rr] : 0;
+        sg[u] = row_seg ? row_seg[rr / row_div] : 0;
       }
     }
 #pragma unroll
@@ -295,32 +295,32 @@ int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
-int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, const float* mean, const float* var, const float* w,
+int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, int row_div, const float* mean, const float* var, const float* w,
                        const float* b, float eps, int relu, long long rows, int C, void* y, int ydt, int ldy, void* y2, int y2dt,
                        int ldy2, cudaStream_t s) {
   if (xdt == NLV_BF16) {
     const ApplyGeom g = apply_geometry(C, rows, 4);
-    bn_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
+    bn_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, row_div, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
                                                           ldy, y2, y2dt, ldy2);
   } else {
     const ApplyGeom g = apply_geometry(C, rows, 2);
-    bn_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
+    bn_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(x, xdt, ldx, row_seg, row_div, mean, var, w, b, eps, relu, rows, g.rows_per_block, C, y, ydt,
                                                            ldy, y2, y2dt, ldy2);
   }
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
-                           const int* row_seg, const int* seg, const float* mean, const float* var, const float* w, float eps,
+                           const int* row_seg, int row_div, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
                            cudaStream_t s) {
   if (dydt == NLV_BF16 && xdt == NLV_BF16 && (yout == nullptr || ydt == NLV_BF16)) {
     const ApplyGeom g = apply_geometry(C, rows, 4);
-    bn_bwd_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+    bn_bwd_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, row_div, seg, mean, var, w, eps, sums,
                                                               use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
   } else {
     const ApplyGeom g = apply_geometry(C, rows, 2);
-    bn_bwd_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, seg, mean, var, w, eps, sums,
+    bn_bwd_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, row_div, seg, mean, var, w, eps, sums,
                                                                use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
   }
   NLV_CHECK_LAUNCH();

@@ -42,6 +42,31 @@ struct DecCtx { T xop, xpop, qkv, o, lse, y, m3, r3, top, h; };
 struct OcCtx { T objfeat, cs, pos_bn, mean0, var0, h1, h2, mean1, var1; };
 struct PtCtx { T feat_op, uf_op, col1, c1, mean2, var2, arg, col2, c2, mean6, var6, vr_in; };
 
+// ---- optional per-call timing (bench.py roofline legs): CUDA events around every kernel entry the sequencer makes --------
+struct ProfRec { char name[40]; cudaEvent_t e0, e1; double flops; double units; int m, n, k; int dt; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+double g_next_flops = 0, g_next_units = 0;
+int g_next_m = 0, g_next_n = 0, g_next_k = 0, g_next_dt = 0;
+struct ProfScope {
+  bool on; ProfRec r; cudaStream_t st;
+  ProfScope(void* stream, const char* call) : on(g_prof_on), st((cudaStream_t)stream) {
+    if (!on) return;
+    int i = 0;
+    for (; call[i] && call[i] != '(' && i < 39; ++i) r.name[i] = call[i];
+    r.name[i] = 0;
+    cudaEventCreate(&r.e0); cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, st);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, st);
+    r.flops = g_next_flops; r.units = g_next_units; r.m = g_next_m; r.n = g_next_n; r.k = g_next_k; r.dt = g_next_dt;
+    g_next_flops = g_next_units = 0; g_next_m = g_next_n = g_next_k = g_next_dt = 0;
+    g_prof.push_back(r);
+  }
+};
+
 }  // namespace
 int set_seg(int* p, int rows, cudaStream_t s);   // util.cu
 }  // namespace nlv
@@ -134,8 +159,8 @@ struct nlv_session {
     if (AD == NLV_BF16 && wop[slot].ok()) return wop[slot];
     return mk(params[slot], NLV_F32, rows, cols);
   }
-  int bn_fwd(const T& x, const int* seg, const int* row_seg, int slot_w, float momentum, bool relu, const T& y, T* mean, T* var);
-  int bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int slot_w, const T& mean, const T& var,
+  int bn_fwd(const T& x, const int* seg, const int* row_seg, int row_div, int slot_w, float momentum, bool relu, const T& y, T* mean, T* var);
+  int bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int row_div, int slot_w, const T& mean, const T& var,
              bool gate_by_x, const T& dx);
   int lin_grads(const T& dy_op, const T& x_op, const T& dy_bias, int wslot, int bslot);
   int encoder_fwd(int layer, const T& x, const T& xop, const int* work, int n_work, bool out_op, T* x2, T* x2op, EncCtx* c);
@@ -159,6 +184,7 @@ struct nlv_session {
 #define RUN(call)                                  \
   do {                                             \
     if (!dry) {                                    \
+      nlv::ProfScope _ps(st, #call);               \
       const int _rc = (call);                      \
       if (_rc != NLV_OK) return _rc;               \
     }                                              \
@@ -248,6 +274,9 @@ int nlv_session::mm(const T& a_in, int am, const T& b_in, int bm, const T& out, 
   g.relu = relu ? 1 : 0;
   if (residual != nullptr) { g.residual = residual->p; g.ldr = residual->ld; g.r_dtype = residual->dt; }
   if (gate != nullptr) { g.gate = gate->p; g.ldg = gate->ld; g.gate_dtype = gate->dt; }
+  if (g_prof_on) {   // algorithmic FLOPs of the product as the model states it (a bf16x3 product still counts 2mnk)
+    g_next_flops = 2.0 * (double)m * (double)n * (double)kdim; g_next_m = (int)m; g_next_n = (int)n; g_next_k = (int)kdim; g_next_dt = a.dt;
+  }
   RUN(nlv_gemm(&g, st));
   return NLV_OK;
 }
@@ -256,6 +285,7 @@ int nlv_session::mm(const T& a_in, int am, const T& b_in, int bm, const T& out, 
 int nlv_session::lin_grads(const T& dy_op, const T& x_op, const T& dy_bias, int wslot, int bslot) {
   const T gw = mk(G(wslot), NLV_F32, dy_op.cols, x_op.cols);
   CK(mm(dy_op, MN_, x_op, MN_, gw));
+  g_next_units = (double)dy_bias.rows * dy_bias.cols * dy_bias.esz();
   RUN(nlv_colsum(dy_bias.p, dy_bias.dt, dy_bias.ld, dy_bias.rows, dy_bias.cols, nullptr, 1, G(bslot), st));
   return NLV_OK;
 }
@@ -279,14 +309,17 @@ int nlv_session::encoder_fwd(int layer, const T& x, const T& xop, const int* wor
   T h = ctx(Mr, DFF, AD), y2 = ctx(Mr, D, NLV_F32), m2 = ctx(Mr, 1, NLV_F32), r2 = ctx(Mr, 1, NLV_F32);
   OOM_CHECK();
   CK(mm(xop, K_, W(LS(layer, NLV_L_INPROJ_W), 3 * D, D), K_, qkv, P(LS(layer, NLV_L_INPROJ_B))));
+  g_next_units = 4.0 * (double)Mr * D * qkv.esz(); g_next_dt = qkv.dt;   // algorithmic bytes: Q, K, V in, O out
   RUN(nlv_attn_fwd(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
                    HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, st));
   CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y1, P(LS(layer, NLV_L_OUTPROJ_B)), &x));
+  g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y1.f(), Mr, D, P(LS(layer, NLV_L_NORMA_W)), P(LS(layer, NLV_L_NORMA_B)), 1e-5f, x1.f(),
                         b16 ? x1op.p : nullptr, NLV_BF16, m1.f(), r1.f(), st));
   const T& x1o = b16 ? x1op : x1;
   CK(mm(x1o, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), K_, h, P(LS(layer, NLV_L_LIN1_B)), nullptr, true));
   CK(mm(h, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), K_, y2, P(LS(layer, NLV_L_LIN2_B)), &x1));
+  g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y2.f(), Mr, D, P(LS(layer, NLV_L_NORMB_W)), P(LS(layer, NLV_L_NORMB_B)), 1e-5f, x2.f(),
                         x2op.ok() ? x2op.p : nullptr, NLV_BF16, m2.f(), r2.f(), st));
   if (c != nullptr) { c->xop = xop; c->qkv = qkv; c->o = o; c->lse = lse; c->y1 = y1; c->m1 = m1; c->r1 = r1; c->x1op = x1o; c->h = h;
@@ -303,6 +336,7 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   Scope sc(this);
   T dy2 = tmp(Mr, D, NLV_F32), dy2op = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
+  g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_bwd(dx2.f(), c.y2.f(), c.m2.f(), c.r2.f(), P(LS(layer, NLV_L_NORMB_W)), Mr, D, dy2.f(), b16 ? dy2op.p : nullptr, NLV_BF16,
                         G(LS(layer, NLV_L_NORMB_W)), G(LS(layer, NLV_L_NORMB_B)), st));
   const T& dy2o = b16 ? dy2op : dy2;
@@ -314,6 +348,7 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   CK(mm(dh, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), MN_, dx1, nullptr, &dy2));
   T dy1 = tmp(Mr, D, NLV_F32), dy1op = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
+  g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_bwd(dx1.f(), c.y1.f(), c.m1.f(), c.r1.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy1.f(), b16 ? dy1op.p : nullptr, NLV_BF16,
                         G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), st));
   const T& dy1o = b16 ? dy1op : dy1;
@@ -324,6 +359,7 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   OOM_CHECK();
   const T& q = c.qkv;
   const size_t e = q.esz();
+  g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
   RUN(nlv_attn_bwd(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work,
                    c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e, dqkv.ld,
                    (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, st));
@@ -352,9 +388,11 @@ int nlv_session::decoder_fwd(int layer, const T& x, const T& xop, const T& xpop,
   const float* bin = P(LS(layer, NLV_L_INPROJ_B));
   CK(mm(xpop, K_, win.rs(0, 2 * D), K_, qkv.cs(0, 2 * D), bin));
   CK(mm(xop, K_, win.rs(2 * D, D), K_, qkv.cs(2 * D, D), bin + 2 * D));
+  g_next_units = 4.0 * (double)Mr * D * qkv.esz(); g_next_dt = qkv.dt;   // algorithmic bytes: Q, K, V in, O out
   RUN(nlv_attn_fwd(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
                    HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work, B.n_glob_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, st));
   CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y, P(LS(layer, NLV_L_OUTPROJ_B)), &x));
+  g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y.f(), Mr, D, P(LS(layer, NLV_L_NORMA_W)), P(LS(layer, NLV_L_NORMA_B)), 1e-5f, t.f(), b16 ? top.p : nullptr,
                         NLV_BF16, m3.f(), r3.f(), st));
   const T& to = b16 ? top : t;
@@ -382,6 +420,7 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   CK(mm(dh, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), MN_, dt, nullptr, &dout));
   T dy = tmp(Mr, D, NLV_F32), dyop = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
+  g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_bwd(dt.f(), c.y.f(), c.m3.f(), c.r3.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy.f(), b16 ? dyop.p : nullptr, NLV_BF16,
                         G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), st));
   const T& dyo = b16 ? dyop : dy;
@@ -392,6 +431,7 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   OOM_CHECK();
   const T& q = c.qkv;
   const size_t e = q.esz();
+  g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
   RUN(nlv_attn_bwd(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work,
                    B.n_glob_work, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e,
                    dqkv.ld, (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, st));
@@ -415,7 +455,7 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
 // object classifier + pair tokens
 // ================================================================================================================
 // Training: per-video batch statistics, running stats updated in video order.  slot_w: BN weight slot (b, rm, rv follow).
-int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int slot_w, float momentum, bool relu, const T& y, T* mean,
+int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int row_div, int slot_w, float momentum, bool relu, const T& y, T* mean,
                         T* var) {
   const int c = x.cols;
   const float *w = P(slot_w), *b = P(slot_w + 1);
@@ -425,12 +465,12 @@ int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int slot
     T ws = tmp((long long)B.nv * 2 * c, 1, NLV_F32, 2);   // double[nv*2*c]
     OOM_CHECK();
     RUN(nlv_bn_stats(x.p, x.dt, x.ld, seg, B.nv, x.rows, c, momentum, reinterpret_cast<double*>(ws.p), mu.f(), va.f(), rm, rv, st));
-    RUN(nlv_bn_apply(x.p, x.dt, x.ld, B.nv > 1 ? row_seg : nullptr, mu.f(), va.f(), w, b, 1e-5f, relu ? 1 : 0, x.rows, c, y.p, y.dt, y.ld,
+    RUN(nlv_bn_apply(x.p, x.dt, x.ld, B.nv > 1 ? row_seg : nullptr, row_div, mu.f(), va.f(), w, b, 1e-5f, relu ? 1 : 0, x.rows, c, y.p, y.dt, y.ld,
                      nullptr, 0, c, st));
     *mean = mu; *var = va;
   } else {
     OOM_CHECK();
-    RUN(nlv_bn_apply(x.p, x.dt, x.ld, nullptr, rm, rv, w, b, 1e-5f, relu ? 1 : 0, x.rows, c, y.p, y.dt, y.ld, nullptr, 0, c, st));
+    RUN(nlv_bn_apply(x.p, x.dt, x.ld, nullptr, 1, rm, rv, w, b, 1e-5f, relu ? 1 : 0, x.rows, c, y.p, y.dt, y.ld, nullptr, 0, c, st));
     *mean = mk(rm, NLV_F32, 1, c); *var = mk(rv, NLV_F32, 1, c);
   }
   return NLV_OK;
@@ -438,7 +478,7 @@ int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int slot
 
 // BatchNorm backward (+ the ReLU that follows (yout) or precedes (gate_by_x) it).  Training: per-video statistics.
 // Eval (running statistics): one segment over all rows, dx = w * rstd * dy.
-int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int slot_w, const T& mean, const T& var,
+int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int row_div, int slot_w, const T& mean, const T& var,
                         bool gate_by_x, const T& dx) {
   const int c = x.cols;
   int nseg = B.nv;
@@ -454,7 +494,7 @@ int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, 
   }
   T ws = tmp((long long)nseg * 2 * c, 1, NLV_F32, 2);   // double[nseg*2*c]
   OOM_CHECK();
-  RUN(nlv_bn_bwd(dy.p, dy.dt, dy.ld, x.p, x.dt, x.ld, yout ? yout->p : nullptr, yout ? yout->dt : 0, yout ? yout->ld : 0, seg, row_seg, nseg,
+  RUN(nlv_bn_bwd(dy.p, dy.dt, dy.ld, x.p, x.dt, x.ld, yout ? yout->p : nullptr, yout ? yout->dt : 0, yout ? yout->ld : 0, seg, row_seg, row_div, nseg,
                  mean.f(), var.f(), P(slot_w), 1e-5f, training ? 1 : 0, gate_by_x ? 1 : 0, x.rows, c, reinterpret_cast<double*>(ws.p), dx.p, dx.dt,
                  dx.ld, G(slot_w), G(slot_w + 1), st));
   return NLV_OK;
@@ -473,10 +513,10 @@ int nlv_session::object_classifier_fwd() {
   CK(mm(mk(B.distribution, NLV_F32, N, 36), K_, mk(P(NLV_P_OC_EMBED), NLV_F32, 36, 200), MN_, objfeat.cs(2048, 200), nullptr, nullptr, false,
         nullptr, true));
   RUN(nlv_center_size(B.boxes, N, cs.f(), st));
-  CK(bn_fwd(cs, B.box_seg, B.box_row, NLV_P_OC_BN0_W, 0.01f / 10.0f, false, pos_bn, &oc.mean0, &oc.var0));
+  CK(bn_fwd(cs, B.box_seg, B.box_row, 1, NLV_P_OC_BN0_W, 0.01f / 10.0f, false, pos_bn, &oc.mean0, &oc.var0));
   CK(mm(pos_bn, K_, mk(P(NLV_P_OC_LIN1_W), NLV_F32, 128, 4), K_, objfeat.cs(2248, 128), P(NLV_P_OC_LIN1_B), nullptr, true, nullptr, true));
   CK(mm(objfeat, K_, W(NLV_P_OC_DEC0_W, 1024, 2376), K_, h1, P(NLV_P_OC_DEC0_B)));
-  CK(bn_fwd(h1, B.box_seg, B.box_row, NLV_P_OC_BN1_W, 0.1f, true, h2, &oc.mean1, &oc.var1));
+  CK(bn_fwd(h1, B.box_seg, B.box_row, 1, NLV_P_OC_BN1_W, 0.1f, true, h2, &oc.mean1, &oc.var1));
   CK(mm(h2, K_, mk(P(NLV_P_OC_DEC3_W), NLV_F32, 37, 1024), K_, obj_logits, P(NLV_P_OC_DEC3_B), nullptr, false, nullptr, true));
   oc.cs = cs; oc.pos_bn = pos_bn; oc.h1 = h1; oc.h2 = h2;
   (void)b16;
@@ -490,7 +530,7 @@ int nlv_session::object_classifier_bwd(const T& dlogits) {
   T dh2 = tmp(N, 1024, NLV_F32);
   CK(mm(dlogits, K_, mk(P(NLV_P_OC_DEC3_W), NLV_F32, 37, 1024), MN_, dh2, nullptr, nullptr, false, nullptr, true));
   T dh1 = tmp(N, 1024, AD);
-  CK(bn_bwd(dh2, oc.h1, &oc.h2, B.box_seg, B.box_row, NLV_P_OC_BN1_W, oc.mean1, oc.var1, false, dh1));
+  CK(bn_bwd(dh2, oc.h1, &oc.h2, B.box_seg, B.box_row, 1, NLV_P_OC_BN1_W, oc.mean1, oc.var1, false, dh1));
   CK(lin_grads(dh1, oc.objfeat, dh1, NLV_P_OC_DEC0_W, NLV_P_OC_DEC0_B));
   const T w0 = W(NLV_P_OC_DEC0_W, 1024, 2376);
   T dtail = tmp(N, 328, NLV_F32);                                   // [N, 200 + 128]
@@ -506,7 +546,7 @@ int nlv_session::object_classifier_bwd(const T& dlogits) {
   RUN(nlv_colsum(dpos.p, dpos.dt, dpos.ld, N, 128, nullptr, 1, G(NLV_P_OC_LIN1_B), st));
   T dposbn = tmp(N, 4, NLV_F32), dcs = tmp(N, 4, NLV_F32);
   CK(mm(dpos, K_, mk(P(NLV_P_OC_LIN1_W), NLV_F32, 128, 4), MN_, dposbn, nullptr, nullptr, false, nullptr, true));
-  CK(bn_bwd(dposbn, oc.cs, nullptr, B.box_seg, B.box_row, NLV_P_OC_BN0_W, oc.mean0, oc.var0, false, dcs));
+  CK(bn_bwd(dposbn, oc.cs, nullptr, B.box_seg, B.box_row, 1, NLV_P_OC_BN0_W, oc.mean0, oc.var0, false, dcs));
   return NLV_OK;
 }
 
@@ -520,7 +560,20 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
   CK(mm(feat_op, K_, W(NLV_P_OBJ_W, 512, 2048), K_, fo.cs(512, 512), P(NLV_P_OBJ_B)));
   // union features as [R*49, 2048] rows (operand of the 1x1 conv)
   T uf;
-  if (B.union_rows) {
+  if (B.union_rows == 2) {          // zero-suppressed rows from a packed feature file
+    NLV_CHECK_ARG(B.union_bitmap != nullptr && B.union_off != nullptr, "session: sparse union features need bitmap and offsets");
+    T d = AD == NLV_BF16 ? ctx(R * 49, 2048, NLV_BF16) : tmp(R * 49, 2048, NLV_BF16);
+    OOM_CHECK();
+    g_next_units = (double)R * 49 * (256 + 4 + 4096);   // + 2 bytes per stored value (added by the reader of the profile)
+    RUN(nlv_union_unpack(B.union_bitmap, B.union_off, B.union_feat, R * 49, d.p, st));
+    uf = d;
+    if (AD != NLV_BF16) {
+      T t = ctx(R * 49, 2048, AD);
+      OOM_CHECK();
+      RUN(nlv_convert(d.p, d.dt, d.ld, t.p, t.dt, t.ld, R * 49, 2048, st));
+      uf = t;
+    }
+  } else if (B.union_rows) {
     uf = mk(B.union_feat, B.union_dtype, R * 49, 2048);
     if (uf.dt != AD) {
       T t = ctx(R * 49, 2048, AD);
@@ -534,6 +587,7 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
     const size_t in_row = (size_t)2048 * 49 * (B.union_dtype == NLV_BF16 ? 2 : 4);
     for (long long s = 0; s < R; s += 32768) {   // grid.y limit of the transposing kernel
       const int n = (int)((R - s) < 32768 ? (R - s) : 32768);
+      g_next_units = (double)n * 49 * 2048 * ((B.union_dtype == NLV_BF16 ? 2 : 4) + uf.esz());
       RUN(nlv_nchw_to_rows((const char*)B.union_feat + s * in_row, B.union_dtype, n, 2048, 49, (char*)uf.p + (size_t)s * 49 * 2048 * uf.esz(),
                            uf.dt, st));
     }
@@ -542,7 +596,7 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
   OOM_CHECK();
   RUN(nlv_im2col_mask(masks.f(), (int)R, col1.p, col1.dt, 104, st));
   CK(mm(col1, K_, w_c0, K_, c1, P(NLV_P_CONV0_B), nullptr, true));                                     // conv 7x7 s2 + ReLU
-  CK(bn_fwd(c1, B.seg196, B.row196, NLV_P_BN2_W, 0.01f, false, b1, &pt.mean2, &pt.var2));
+  CK(bn_fwd(c1, B.seg196, B.pair_row, 196, NLV_P_BN2_W, 0.01f, false, b1, &pt.mean2, &pt.var2));
   T p1 = tmp(R * 49, 128, AD), arg = ctx(R * 49, 128, NLV_BF16 /*u8 payload*/, 64);
   arg.dt = NLV_BF16;
   OOM_CHECK();
@@ -551,7 +605,7 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
   OOM_CHECK();
   RUN(nlv_im2col_3x3(p1.p, p1.dt, (int)R, 7, 7, 128, col2.p, col2.dt, st));
   CK(mm(col2, K_, w_c4, K_, c2, P(NLV_P_CONV4_B), nullptr, true));
-  CK(bn_fwd(c2, B.seg49, B.row49, NLV_P_BN6_W, 0.01f, false, b2, &pt.mean6, &pt.var6));
+  CK(bn_fwd(c2, B.seg49, B.pair_row, 49, NLV_P_BN6_W, 0.01f, false, b2, &pt.mean6, &pt.var6));
   T vr_in = ctx(R * 49, 256, AD);                                                                      // = [R, 12544] in (hw, c) order
   OOM_CHECK();
   CK(mm(uf, K_, W(NLV_P_UNION_W, 256, 2048), K_, vr_in, P(NLV_P_UNION_B), &b2));
@@ -586,7 +640,7 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   CK(mm(dvr_in, MN_, pt.uf_op, MN_, mk(G(NLV_P_UNION_W), NLV_F32, 256, 2048)));
   RUN(nlv_colsum(dvr_in.p, dvr_in.dt, dvr_in.ld, R * 49, 256, nullptr, 1, G(NLV_P_UNION_B), st));
   T dc2 = tmp(R * 49, 256, AD);
-  CK(bn_bwd(dvr_in, pt.c2, nullptr, B.seg49, B.row49, NLV_P_BN6_W, pt.mean6, pt.var6, true, dc2));   // BN backward + ReLU backward fused
+  CK(bn_bwd(dvr_in, pt.c2, nullptr, B.seg49, B.pair_row, 49, NLV_P_BN6_W, pt.mean6, pt.var6, true, dc2));   // BN backward + ReLU backward fused
   {
     Scope s2(this);
     T gtap = tmp(256, 1152, NLV_F32);
@@ -602,7 +656,7 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   RUN(nlv_col2im_3x3(dcol2.p, dcol2.dt, (int)R, 7, 7, 128, dp1.f(), st));
   RUN(nlv_maxpool_bwd(dp1.f(), reinterpret_cast<const uint8_t*>(pt.arg.p), (int)R, 128, db1.p, db1.dt, st));
   T dc1 = tmp(R * 196, 128, AD);
-  CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.row196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1));
+  CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.pair_row, 196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1));
   {
     Scope s2(this);
     T g0 = tmp(128, 104, NLV_F32);
@@ -864,7 +918,13 @@ int nlv_session::run_forward() {
       feat_op = t;
     }
   } else {
-    NLV_CHECK_ARG(B.distribution != nullptr, "session: sgdet / sgcls need entry['distribution']");
+    if (B.distribution == nullptr && B.dist_conf != nullptr && B.dist_idx != nullptr) {   // create_dis on device
+      T d = keep(N, 36, NLV_F32);
+      OOM_CHECK();
+      RUN(nlv_create_dis(B.dist_conf, B.dist_other, B.dist_idx, N, d.f(), st));
+      B.distribution = d.f();
+    }
+    NLV_CHECK_ARG(dry || B.distribution != nullptr, "session: sgdet / sgcls need entry['distribution']");
     CK(object_classifier_fwd());
     feat_op = oc.objfeat.cs(0, 2048);
   }
@@ -944,6 +1004,27 @@ int nlv_struct_sizes(int* out, int n) {
   const int v[4] = {(int)sizeof(nlv_model), (int)sizeof(nlv_batch), (int)sizeof(nlv_outputs), (int)sizeof(nlv_gemm_args)};
   for (int i = 0; i < n && i < 4; ++i) out[i] = v[i];
   return 4;
+}
+
+/* per-call timing of the sequencer's kernel entries: nlv_profile(1) starts recording (CUDA events around every entry),
+ * nlv_profile_read synchronises and writes one line per call "name\tms\tflops\tunits\tm\tn\tk\tdtype\n" into buf (returns the
+ * bytes needed; records are cleared).  Diagnostic only: adds two event records per call. */
+int nlv_profile(int on) { nlv::g_prof_on = on != 0; return NLV_OK; }
+long long nlv_profile_read(char* buf, long long cap) {
+  cudaDeviceSynchronize();
+  long long pos = 0;
+  for (nlv::ProfRec& r : nlv::g_prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.e0, r.e1);
+    char line[160];
+    const int n = snprintf(line, sizeof(line), "%s\t%.6f\t%.0f\t%.0f\t%d\t%d\t%d\t%d\n", r.name, ms, r.flops, r.units, r.m, r.n, r.k, r.dt);
+    if (buf != nullptr && pos + n < cap) memcpy(buf + pos, line, n);
+    pos += n;
+    cudaEventDestroy(r.e0); cudaEventDestroy(r.e1);
+  }
+  if (buf != nullptr && pos < cap) buf[pos] = 0;
+  nlv::g_prof.clear();
+  return pos + 1;
 }
 
 nlv_session* nlv_session_create(void) { return new nlv_session(); }
@@ -1037,6 +1118,7 @@ int nlv_session_transformer_backward(nlv_session* s, const float* dout, float** 
   NLV_CHECK_ARG(s->want_ctx && s->M.grad_base != nullptr && !s->goff.empty(), "transformer_backward: needs NLV_RUN_CTX and the gradient buffer");
   s->st = stream;
   const bool dry = false;
+  void* st = stream;
   RUN(nlv_zero_bytes(s->M.grad_base, s->M.grad_elems * 4, stream));
   T d;
   const int rc = s->sttran_transformer_bwd(mk(dout, NLV_F32, s->R, D), &d);

@@ -97,6 +97,77 @@ __global__ void heads_activation_bwd_kernel(const float* __restrict__ datt, cons
 
 __global__ void set_seg_kernel(int* p, int rows) { p[0] = 0; p[1] = rows; }
 
+// Zero-suppressed union features (packed feature files, nlvsgg_b200/featfile.py) -> dense bf16 rows [rows, 2048].
+// One warp per row.  The row's stored values (channel order, vals[off[row] .. off[row+1])) are staged in shared memory with
+// 16-byte loads (from the 16-byte boundary below off[row]; the value array is padded).  Lane l holds occupancy word l
+// (channels 64 l .. 64 l + 63); a warp scan of the word popcounts gives every word's first value.  Output is written in
+// 16-byte chunks of 8 channels, chunk j = 32 g + lane in pass g, so every store instruction covers 512 contiguous bytes;
+// channel i of a chunk is the popc(occupancy bits below it)-th stored value — independent predicated loads, no serial chain.
+__global__ void __launch_bounds__(256)
+union_unpack_kernel(const unsigned long long* __restrict__ bitmap, const unsigned* __restrict__ off,
+                    const unsigned short* __restrict__ vals, long long rows, unsigned short* __restrict__ dst) {
+  __shared__ __align__(16) unsigned short sv[8][2048 + 8];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < rows; r += nwarps) {
+    const unsigned long long bits = bitmap[r * 32 + lane];
+    const size_t b0 = off[r];
+    const int total = (int)(off[r + 1] - off[r]);
+    const size_t a0 = b0 & ~(size_t)7;
+    const int mis = (int)(b0 - a0);
+    const uint4* src = reinterpret_cast<const uint4*>(vals + a0);
+    uint4* stg = reinterpret_cast<uint4*>(sv[w]);
+    for (int c = lane; c * 8 < mis + total; c += 32) stg[c] = src[c];
+    const int cnt = __popcll(bits);
+    int pre = cnt;                                  // inclusive prefix sum over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, pre, o);
+      if (lane >= o) pre += t;
+    }
+    const int excl = pre - cnt;                     // first stored value of word `lane`
+    __syncwarp();
+    const unsigned short* v = sv[w] + mis;
+    uint4* out = reinterpret_cast<uint4*>(dst + (size_t)r * 2048);
+    const int byte = lane & 7;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const int word = (lane >> 3) + 4 * g;         // chunk j = 32 g + lane lies in word j / 8, byte j % 8
+      const unsigned long long wb = __shfl_sync(0xffffffffu, bits, word);
+      const int base = __shfl_sync(0xffffffffu, excl, word) + __popcll(wb & ((1ull << (8 * byte)) - 1ull));
+      const unsigned m = (unsigned)(wb >> (8 * byte)) & 0xffu;
+      unsigned wd[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const int i = 2 * h;
+        const int i0 = base + __popc(m & ((1u << i) - 1u));
+        const bool s0 = (m >> i) & 1u, s1 = (m >> (i + 1)) & 1u;
+        const unsigned lo = s0 ? v[i0] : 0u;
+        const unsigned hi = s1 ? v[i0 + (s0 ? 1 : 0)] : 0u;
+        wd[h] = lo | (hi << 16);
+      }
+      out[32 * g + lane] = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+    }
+    __syncwarp();
+  }
+}
+
+// lib/assign_pseudo_label.py:934-938 create_dis: d = zeros(36); d[idx] = conf; d[d == 0] = (1 - conf) / 35
+// `other`: the value of the 35 remaining entries as the producer computed it (python double or fp32 tensor arithmetic,
+// depending on the caller); NULL -> (1 - conf) / 35 in fp32
+__global__ void create_dis_kernel(const float* __restrict__ conf, const float* __restrict__ other, const int* __restrict__ idx,
+                                  long long n, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 36) return;
+  const long long r = i / 36;
+  const int c = (int)(i - r * 36);
+  const float cf = conf[r];
+  float v = (c == idx[r]) ? cf : 0.f;
+  if (v == 0.f) v = other != nullptr ? other[r] : __fdiv_rn(__fsub_rn(1.f, cf), 35.f);
+  out[i] = v;
+}
+
 }  // namespace
 
 int set_seg(int* p, int rows, cudaStream_t s) {
@@ -162,6 +233,29 @@ int nlv_zero_bytes(void* p, long long nbytes, void* stream) {
   }
   const long long tail = nbytes - h - n16 * 16;
   if (tail > 0) { zero1_kernel<<<1, 32, 0, STREAM>>>(q + h + n16 * 16, tail); NLV_CHECK_LAUNCH(); }
+  return NLV_OK;
+}
+
+int nlv_union_unpack(const void* bitmap, const unsigned* off, const void* vals, long long rows, void* dst_bf16, void* stream) {
+  NLV_CHECK_ARG(rows >= 0, "union_unpack: bad size");
+  if (rows == 0) return NLV_OK;
+  NLV_CHECK_ARG(bitmap && off && vals && dst_bf16, "union_unpack: null pointer");
+  NLV_CHECK_ARG((reinterpret_cast<uintptr_t>(dst_bf16) & 15) == 0 && (reinterpret_cast<uintptr_t>(bitmap) & 7) == 0, "union_unpack: misaligned buffer");
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  union_unpack_kernel<<<(unsigned)blocks, 256, 0, STREAM>>>(reinterpret_cast<const unsigned long long*>(bitmap), off,
+                                                           reinterpret_cast<const unsigned short*>(vals), rows,
+                                                           reinterpret_cast<unsigned short*>(dst_bf16));
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_create_dis(const float* conf, const float* other, const int* idx, long long n, float* out, void* stream) {
+  NLV_CHECK_ARG(n >= 0, "create_dis: bad size");
+  if (n == 0) return NLV_OK;
+  NLV_CHECK_ARG(conf && idx && out, "create_dis: null pointer");
+  create_dis_kernel<<<cdiv(n * 36, 256), 256, 0, STREAM>>>(conf, other, idx, n, out);
+  NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 

@@ -205,7 +205,7 @@ def plan_desc(plan: Plan, dsg: bool = False) -> "_C.BatchDesc":
     """The descriptor half of nlv_batch (sizes + the int32 index arrays of plan.py)."""
     b = _C.BatchDesc()
     b.nv, b.n_boxes, b.n_pairs, b.n_stream = plan.nv, plan.N, plan.R, plan.Mg
-    for name in ("box_seg", "seg196", "seg49", "box_row", "row196", "row49", "local_work", "glob_work", "stream_src", "stream_slot",
+    for name in ("box_seg", "seg196", "seg49", "box_row", "pair_row", "local_work", "glob_work", "stream_src", "stream_slot",
                  "inv", "out_src", "out_inv", "passthrough"):
         setattr(b, name, _ptr(getattr(plan, name, None)))
     b.n_local_work, b.n_glob_work, b.has_passthrough = plan.n_local_work, plan.n_glob_work, 1 if plan.has_passthrough else 0
@@ -228,7 +228,10 @@ def batch_desc(batch, plan: Plan, labels=None, dsg: bool = False) -> "_C.BatchDe
     b.distribution = _ptr(batch.distribution)
     u = batch.union_feat
     b.union_feat, b.union_dtype = u.data_ptr(), _C.NLV_BF16 if u.dtype == BF16 else _C.NLV_F32
-    b.union_rows = 1 if getattr(batch, "union_rows", False) else 0
+    b.union_rows = int(getattr(batch, "union_rows", 0) or 0)
+    b.union_bitmap, b.union_off = _ptr(getattr(batch, "union_bitmap", None)), _ptr(getattr(batch, "union_off", None))
+    b.dist_conf, b.dist_idx = _ptr(getattr(batch, "dist_conf", None)), _ptr(getattr(batch, "dist_idx", None))
+    b.dist_other = _ptr(getattr(batch, "dist_other", None))
     b.spatial_masks = _ptr(batch.spatial_masks)
     b.pair_idx = batch.pair_idx.data_ptr()
     if labels is not None:

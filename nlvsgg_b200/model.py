@@ -18,10 +18,17 @@ F32 = torch.float32
 
 
 class Batch:
-    pass
+    """A collated batch of videos (host or device resident).  `union_rows`: 0 = union_feat is NCHW [R,2048,7,7] (the entry
+    contract), 1 = channels-last rows [R*49,2048], 2 = zero-suppressed rows (values + union_bitmap + union_off) — the two
+    layouts of the packed feature files (featfile.py)."""
+    union_rows = 0
+    union_bitmap = union_off = dist_conf = dist_other = dist_idx = None
+    distribution = spatial_masks = None
+    lab_csr = None
 
 
-TENSOR_KEYS = ("features", "boxes", "labels", "scores", "distribution", "union_feat", "pair_idx", "spatial_masks")
+TENSOR_KEYS = ("features", "boxes", "labels", "scores", "distribution", "union_feat", "pair_idx", "spatial_masks",
+               "union_bitmap", "union_off", "dist_conf", "dist_other", "dist_idx")
 
 
 def collate(entries: List[dict], mode: str, pin: bool = False, feat_dtype: torch.dtype = F32) -> Batch:
@@ -35,6 +42,7 @@ def collate(entries: List[dict], mode: str, pin: bool = False, feat_dtype: torch
     b.frame_ids = [e["im_idx"].detach().cpu().numpy() for e in entries]
     b.n_pairs = [len(f) for f in b.frame_ids]
     b.gt_lists = [(e.get("attention_gt"), e.get("spatial_gt"), e.get("contacting_gt")) for e in entries]
+    b.lab_csr = _label_csr(b.gt_lists) if all(g[0] is not None for g in b.gt_lists) else None
     off = np.concatenate(([0], np.cumsum(b.n_boxes)))[:-1]
 
     def cat(key, dtype):
@@ -73,7 +81,7 @@ def upload(hb: Batch, device, rasterise: bool = True, consumer_stream=None) -> B
     b = Batch()
     b.__dict__.update(hb.__dict__)
     for key in TENSOR_KEYS:
-        t = getattr(hb, key)
+        t = getattr(hb, key, None)
         if t is not None:
             d = t.to(dev, non_blocking=True)
             if consumer_stream is not None and d is not t:
@@ -91,11 +99,11 @@ def ensure_masks(b: Batch) -> Batch:
 
 
 def input_bytes(hb: Batch) -> int:
-    return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in TENSOR_KEYS if getattr(hb, k) is not None))
+    return int(sum(getattr(hb, k).numel() * getattr(hb, k).element_size() for k in TENSOR_KEYS if getattr(hb, k, None) is not None))
 
 
 def make_plan(b: Batch, device, mode: str, dsg: bool = False, with_labels: bool = False, consumer_stream=None,
-              label_rng=None) -> "E.Plan":
+              label_rng=None, stager=None) -> "E.Plan":
     """Descriptors (+ optionally the loss labels) -> one pinned async upload.  plan.labels is set when with_labels."""
     obj_class = subj_box = None
     if dsg:
@@ -104,7 +112,7 @@ def make_plan(b: Batch, device, mode: str, dsg: bool = False, with_labels: bool 
         obj_class, subj_box = lab[pi[:, 1]], pi[:, 0]
     extra = label_arrays(b, label_rng) if with_labels else None
     plan = E.Plan(b.n_boxes, b.frame_ids, torch.device(device), obj_class=obj_class, subj_box=subj_box, dsg=dsg,
-                  dsg_pos_by_rank=(mode == "sgdet"), extra=extra, consumer_stream=consumer_stream)
+                  dsg_pos_by_rank=(mode == "sgdet"), extra=extra, consumer_stream=consumer_stream, stager=stager)
     if with_labels:
         L = Labels()
         L.att, L.w_att, L.spa_bits, L.w_spa = plan.lab_att, plan.lab_w_att, plan.lab_spa_bits, plan.lab_w_spa
@@ -199,28 +207,36 @@ def _bits_of(lists) -> np.ndarray:
     return out
 
 
+def _label_csr(gt_lists):
+    """The python label lists of a batch flattened once (loader-side work: it walks every list):
+    (attention values, attention list lengths, spatial bit masks, contacting bit masks)."""
+    a_all = [x for g in gt_lists for x in g[0]]
+    s_all = [x for g in gt_lists for x in g[1]]
+    c_all = [x for g in gt_lists for x in g[2]]
+    avals, _, alens = _flat_lists(a_all)
+    return avals, alens, _bits_of(s_all), _bits_of(c_all)
+
+
 def label_arrays(batch: Batch, rng: Optional[np.random.Generator] = None) -> dict:
-    """Label tensors + per-row loss weights from the python label lists of the entries (train_STTran.py:143-167).
+    """Label tensors + per-row loss weights from the label lists of the entries (train_STTran.py:143-167).
     Weight = 1 / (rows of that video entering the mean) / (classes, for BCE) / videos.  A pair with several attention
     labels contributes ONE of them per step: the reference draws it with np.random.choice (:148-150) — pass `rng` for that;
-    without it the first label is taken (deterministic; what the parity fixtures use).  All videos in one numpy pass."""
+    without it the first label is taken (deterministic; what the parity fixtures use).  One numpy pass over all videos; the
+    python lists themselves were flattened at collate time (`batch.lab_csr`)."""
     nv = len(batch.n_boxes)
     n_pairs = np.asarray(batch.n_pairs, dtype=np.int64)
-    a_all = [x for g in batch.gt_lists for x in g[0]]
-    s_all = [x for g in batch.gt_lists for x in g[1]]
-    c_all = [x for g in batch.gt_lists for x in g[2]]
-    R = len(a_all)
+    csr = getattr(batch, "lab_csr", None)
+    avals, alens, sb, cb = csr if csr is not None else _label_csr(batch.gt_lists)
+    R = len(alens)
     vid = np.repeat(np.arange(nv), n_pairs)
-    avals, arows, alens = _flat_lists(a_all)
-    first = np.cumsum(alens) - alens
-    pick = first.copy()
+    pick = np.cumsum(alens) - alens
     if rng is not None and len(avals):
         multi = alens >= 2
+        pick = pick.copy()
         pick[multi] += (rng.random(int(multi.sum())) * alens[multi]).astype(np.int64)
     att = np.full(R, -1, dtype=np.int64)
     has = alens > 0
     att[has] = avals[pick[has]]
-    sb, cb = _bits_of(s_all), _bits_of(c_all)
 
     def weights(mask, classes):
         cnt = np.bincount(vid[mask], minlength=nv).astype(np.float64)

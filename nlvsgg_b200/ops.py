@@ -296,25 +296,25 @@ def bn_stats(x, seg, nseg, c, momentum, running_mean, running_var):
     return mean, var
 
 
-def bn_apply(x, row_seg, mean, var, w, b, relu, out=None, out_dtype=None, out2_dtype=None, eps=1e-5):
+def bn_apply(x, row_seg, mean, var, w, b, relu, out=None, out_dtype=None, out2_dtype=None, eps=1e-5, row_div=1):
     rows, c = x.shape
     if out is None:
         out = torch.empty(rows, c, device=x.device, dtype=out_dtype or torch.float32)
     out2 = torch.empty(rows, c, device=x.device, dtype=out2_dtype) if out2_dtype is not None else None
-    _call("nlv_bn_apply", _ptr(x), _dt(x), x.stride(0), _ptr(row_seg), _ptr(mean), _ptr(var), _ptr(w), _ptr(b), _F(eps),
+    _call("nlv_bn_apply", _ptr(x), _dt(x), x.stride(0), _ptr(row_seg), row_div, _ptr(mean), _ptr(var), _ptr(w), _ptr(b), _F(eps),
           1 if relu else 0, _LL(rows), c, _ptr(out), _dt(out), out.stride(0), _ptr(out2),
           _dt(out2) if out2 is not None else 0, c)
     return out, out2
 
 
-def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dtype=torch.float32, eps=1e-5, gate_by_x=False):
+def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dtype=torch.float32, eps=1e-5, gate_by_x=False, row_div=1):
     rows, c = x.shape
     ws = torch.empty(nseg * 2 * c, device=x.device, dtype=torch.float64)
     dx = torch.empty(rows, c, device=x.device, dtype=dx_dtype)
     dw = torch.zeros(c, device=x.device, dtype=torch.float32)
     db = torch.zeros(c, device=x.device, dtype=torch.float32)
     _call("nlv_bn_bwd", _ptr(dy), _dt(dy), dy.stride(0), _ptr(x), _dt(x), x.stride(0), _ptr(yout),
-          _dt(yout) if yout is not None else 0, yout.stride(0) if yout is not None else 0, _ptr(seg), _ptr(row_seg), nseg,
+          _dt(yout) if yout is not None else 0, yout.stride(0) if yout is not None else 0, _ptr(seg), _ptr(row_seg), row_div, nseg,
           _ptr(mean), _ptr(var), _ptr(w), _F(eps), 1 if use_batch_stats else 0, 1 if gate_by_x else 0, _LL(rows), c, _ptr(ws), _ptr(dx),
           _dt(dx), c,
           _ptr(dw), _ptr(db))

@@ -12,28 +12,67 @@ import numpy as np
 import torch
 
 
-def pack_upload(arrays: Dict[str, np.ndarray], device, consumer_stream=None) -> Dict[str, torch.Tensor]:
-    """All arrays -> one pinned byte buffer -> one async H2D copy -> typed device views."""
+_TORCH_DT = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32,
+             np.dtype(np.uint32): torch.int32}
+
+
+class Stager:
+    """Ring of reusable (pinned host buffer, device buffer) pairs for the per-step descriptor upload.
+
+    Allocating pinned memory inside the step is what must not happen: cudaHostAlloc synchronises the device, and the
+    caching host allocator cannot recycle a block whose copy is still queued behind the previous step's kernels.  A slot
+    is reused `depth` uploads later, after its consumer (the step that read the device copy) has finished — that wait is
+    the only back-pressure on a host that runs ahead of the GPU."""
+
+    def __init__(self, device, depth: int = 4):
+        self.device, self.depth, self.i = torch.device(device), depth, 0
+        self.slots = [dict(host=None, dev=None, done=None) for _ in range(depth)]
+
+    def next(self, nbytes: int):
+        s = self.slots[self.i % self.depth]
+        self.i += 1
+        if s["done"] is not None:
+            s["done"].synchronize()
+            s["done"] = None
+        if s["host"] is None or s["host"].numel() < nbytes:
+            cap = int(nbytes * 1.5) + 4096
+            s["host"] = torch.empty(cap, dtype=torch.uint8, pin_memory=self.device.type == "cuda")
+            s["dev"] = torch.empty(cap, dtype=torch.uint8, device=self.device)
+        return s
+
+
+def pack_upload(arrays: Dict[str, np.ndarray], device, consumer_stream=None, stager: Optional[Stager] = None) -> Dict[str, torch.Tensor]:
+    """All arrays -> one pinned byte buffer -> one async H2D copy -> typed device views.  With a `stager` no memory is
+    allocated; the returned dict carries the slot under "_slot" (record slot["done"] after the consumer is enqueued)."""
     offs, total = {}, 0
     for k, a in arrays.items():
         total = (total + 15) // 16 * 16
         offs[k] = total
         total += a.nbytes
-    host = torch.empty(max(total, 16), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+    total = max(total, 16)
+    slot = None
+    if stager is not None:
+        slot = stager.next(total)
+        host, dev = slot["host"], slot["dev"]
+    else:
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
     hv = host.numpy()
     for k, a in arrays.items():
         if a.nbytes:
             hv[offs[k]:offs[k] + a.nbytes] = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-    dev = host.to(device, non_blocking=True)
-    if consumer_stream is not None and dev.is_cuda:
-        dev.record_stream(consumer_stream)   # issued on a copy stream, read on the compute stream
+    if slot is not None:
+        dev[:total].copy_(host[:total], non_blocking=True)
+    else:
+        dev = host.to(device, non_blocking=True)
+        if consumer_stream is not None and dev.is_cuda:
+            dev.record_stream(consumer_stream)   # issued on a copy stream, read on the compute stream
     out = {}
     for k, a in arrays.items():
         t = dev[offs[k]:offs[k] + a.nbytes]
-        tdt = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64, np.dtype(np.float32): torch.float32,
-               np.dtype(np.uint32): torch.int32}[a.dtype]
+        tdt = _TORCH_DT[a.dtype]
         out[k] = t.view(tdt).reshape(a.shape) if a.nbytes else torch.empty(a.shape, dtype=tdt, device=device)
     out["_pinned_keepalive"] = host
+    out["_slot"] = slot
     return out
 
 
@@ -67,7 +106,7 @@ class Plan:
 
     def __init__(self, n_boxes: List[int], frame_ids: List[np.ndarray], device, obj_class: Optional[np.ndarray] = None,
                  subj_box: Optional[np.ndarray] = None, dsg: bool = False, dsg_pos_by_rank: bool = True,
-                 extra: Optional[Dict[str, np.ndarray]] = None, consumer_stream=None):
+                 extra: Optional[Dict[str, np.ndarray]] = None, consumer_stream=None, stager: Optional[Stager] = None):
         nv = len(n_boxes)
         self.nv = nv
         n_pairs = np.asarray([len(f) for f in frame_ids], dtype=np.int64)
@@ -127,8 +166,7 @@ class Plan:
         }
         if nv > 1:
             pair_row = np.repeat(np.arange(nv, dtype=np.int32), n_pairs)
-            arrays.update(box_row=np.repeat(np.arange(nv, dtype=np.int32), n_boxes), pair_row=pair_row,
-                          row196=np.repeat(pair_row, 196), row49=np.repeat(pair_row, 49))
+            arrays.update(box_row=np.repeat(np.arange(nv, dtype=np.int32), n_boxes), pair_row=pair_row)
         self.n_local_work, self.n_glob_work = len(lw), len(gw)
 
         # ---- DSG-DETR: per-video, per-object-class sequences (lib/dsg_detr.py:545-559)
@@ -163,9 +201,17 @@ class Plan:
             self.n_cls_work = len(cw)
         if extra:
             arrays.update(extra)
-        dev = pack_upload(arrays, device, consumer_stream)
+        dev = pack_upload(arrays, device, consumer_stream, stager)
         self._keep = dev.pop("_pinned_keepalive")
+        self._slot = dev.pop("_slot")
         for k, v in dev.items():
             setattr(self, k, v)
         if nv == 1:
-            self.box_row = self.pair_row = self.row196 = self.row49 = None
+            self.box_row = self.pair_row = None
+
+    def consumed(self):
+        """Call after the last kernel that reads the descriptors has been enqueued (staged uploads only)."""
+        if self._slot is not None and torch.cuda.is_available():
+            ev = torch.cuda.Event()
+            ev.record()
+            self._slot["done"] = ev

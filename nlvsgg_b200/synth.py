@@ -183,3 +183,22 @@ def synth_detections(seed: int, frames: int = 6, mean_boxes: int = 9, fmap_chann
         "features": torch.relu(torch.randn(N, 2048, generator=g)),
         "fmaps": torch.relu(torch.randn(frames, fmap_channels, fmap_hw[0], fmap_hw[1], generator=g)),
     }
+
+
+def synth_pred(mode, seed, frames, k, empty_p, saturate):
+    """A `pred` dict as lib/sttran.py would return it (CPU tensors) + the gt annotation list: random relation logits ->
+    (logits | sigmoid | sigmoid); `saturate` produces exact ties between non-zero scores (saturated sigmoids, few distinct
+    object scores) — the case the evaluator's canonical tie order exists for."""
+    entry, gt = synth_video(seed, frames, k, mode, draw_fn=None, empty_frame_prob=empty_p, union_feat=False)
+    g = torch.Generator().manual_seed(seed + 5000)
+    R = entry["pair_idx"].shape[0]
+    scale = 40.0 if saturate else 2.0
+    pred = {k_: v for k_, v in entry.items() if torch.is_tensor(v)}
+    pred["attention_distribution"] = torch.randn(R, 3, generator=g) * 2.0
+    pred["spatial_distribution"] = torch.sigmoid(torch.randn(R, 6, generator=g) * scale)
+    pred["contacting_distribution"] = torch.sigmoid(torch.randn(R, 17, generator=g) * scale)
+    pred["pred_labels"] = entry["labels"].clone()
+    pred["pred_scores"] = entry["scores"].clone()
+    if saturate and mode != "predcls":
+        pred["pred_scores"] = torch.round(pred["pred_scores"] * 4) / 4
+    return pred, gt

@@ -77,6 +77,8 @@ class Trainer:
             if dec0:
                 self._tail_ranges = ((self.offsets[pos], self.offsets[pos] + (self.P[pos].numel() + 7) // 8 * 8), (self.offsets[dec0[0]], total))
         self.last = None
+        from .plan import Stager
+        self.stager = Stager(dev)
         self._loss_ring, self._loss_i = torch.zeros(8, device=dev, dtype=F32), 0
 
     def _install_mirror(self):
@@ -96,11 +98,12 @@ class Trainer:
         they replace the reference's per-frame python loops and are part of the step."""
         dsg = self.arch == "dsg"
         if plan is None:
-            plan = M.make_plan(batch, self.dev, self.mode, dsg, with_labels=True, label_rng=self.label_rng)
+            plan = M.make_plan(batch, self.dev, self.mode, dsg, with_labels=True, label_rng=self.label_rng, stager=self.stager)
         self.k.seed += 1
         out, sess = E.run_forward(self.k, self.desc, self.P, batch, plan, True, True, labels=plan.labels, with_loss=True,
                                   with_backward=True, grad_base=self.flat_g, grad_offsets=self._goff)
         E.run_backward(sess)
+        plan.consumed()
         self.last = (out, plan)
         # the workspace is reused by the next step: the loss a caller may hold on to goes to a small ring of its own
         slot = self._loss_ring[self._loss_i % 8:self._loss_i % 8 + 1]
@@ -163,7 +166,7 @@ class Trainer:
         main = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_stream):
             plan = M.make_plan(host_batch, self.dev, self.mode, self.arch == "dsg", with_labels=True, consumer_stream=main,
-                               label_rng=self.label_rng)
+                               label_rng=self.label_rng, stager=self.stager)
             b = M.upload(host_batch, self.dev, rasterise=False, consumer_stream=main)
             ev = torch.cuda.Event()
             ev.record(self.copy_stream)

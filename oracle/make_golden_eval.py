@@ -19,21 +19,7 @@ CASES = [("eval_predcls", "predcls", 41, 12, 6, 0.0, False), ("eval_sgdet", "sgd
          ("eval_sgdet_saturated", "sgdet", 43, 8, 5, 0.0, True), ("eval_predcls_tiny", "predcls", 44, 6, 3, 0.0, True)]
 
 
-def synth_pred(mode, seed, frames, k, empty_p, saturate):
-    """A `pred` dict as lib/sttran.py would return it (CPU tensors) + the gt annotation list."""
-    entry, gt = synth.synth_video(seed, frames, k, mode, draw_fn=None, empty_frame_prob=empty_p, union_feat=False)
-    g = torch.Generator().manual_seed(seed + 5000)
-    R = entry["pair_idx"].shape[0]
-    scale = 40.0 if saturate else 2.0      # saturated sigmoids produce exact ties between non-zero scores
-    pred = {k_: v for k_, v in entry.items() if torch.is_tensor(v)}
-    pred["attention_distribution"] = torch.randn(R, 3, generator=g) * 2.0
-    pred["spatial_distribution"] = torch.sigmoid(torch.randn(R, 6, generator=g) * scale)
-    pred["contacting_distribution"] = torch.sigmoid(torch.randn(R, 17, generator=g) * scale)
-    pred["pred_labels"] = entry["labels"].clone()
-    pred["pred_scores"] = entry["scores"].clone()
-    if saturate and mode != "predcls":
-        pred["pred_scores"] = torch.round(pred["pred_scores"] * 4) / 4   # few distinct object scores -> more ties
-    return pred, gt
+synth_pred = synth.synth_pred      # the generator lives with the other synthetic inputs (nlvsgg_b200/synth.py)
 
 
 def run_reference_eval(evmod, mode, pred, gt):
