@@ -49,6 +49,16 @@ long long nlv_launch_count(void);
  *                        aligned and lda,ldb multiples of 8.
  *   ab_dtype NLV_F32  -> exact-fp32 SIMT kernel (any shape/stride); parity mode and tiny shapes.
  * ------------------------------------------------------------------------------------------ */
+/* Counter-based dropout (Philox4x32-10; csrc/philox.cuh): replaces nn.Dropout / MultiheadAttention(dropout=0.1) of
+ * lib/transformer.py:9-29,38-57, lib/sttran.py:46, lib/dsg_detr.py:28,48.  thr16 = round(p * 65536) (0 = off), scale = 1 / (1 - p);
+ * `stream` names the dropout site, so forward and backward regenerate identical masks from (seed, stream, element). */
+typedef struct nlv_dropout {
+  unsigned thr16;
+  float scale;
+  unsigned seed_lo, seed_hi;
+  unsigned stream;
+} nlv_dropout;
+
 typedef struct nlv_gemm_args {
   const void* a;        /* A operand: [m,k] (a_major K, ld=lda) or [k,m] (a_major MN) */
   const void* b;        /* B operand: [n,k] (b_major K, ld=ldb) or [k,n] (b_major MN) */
@@ -63,6 +73,8 @@ typedef struct nlv_gemm_args {
   const void* gate;     /* optional [m,n] (row stride ldg, dtype gate_dtype): value kept where gate > 0, else 0 —
                            the ReLU backward fused into an input-gradient GEMM; applied before residual */
   int ldg, gate_dtype;
+  float gate_scale;     /* multiplies the gated value (0 is read as 1): the 1 / (1 - p) of a dropout that followed the ReLU */
+  nlv_dropout drop;     /* dropout applied after bias / ReLU, before the residual (element (row, col) of the [m,n] output) */
 } nlv_gemm_args;
 
 int nlv_gemm(const nlv_gemm_args* args, void* stream);
@@ -163,6 +175,27 @@ int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
                  float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
                  int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                  int dqkv_dtype, void* stream);
+
+/* with dropout on the attention weights (drop NULL or thr16 == 0: identical to the plain entry points).  Masks are keyed by
+ * (global row, head, key index inside the segment).  bf16 tensor-core path only (NLV_ERR_UNSUPPORTED otherwise). */
+int nlv_attn_fwd_drop(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                      float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, const nlv_dropout* drop,
+                      void* stream);
+int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                      float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
+                      int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                      int dqkv_dtype, const nlv_dropout* drop, void* stream);
+/* dst = keep(row, col) ? src * scale : 0 (dtype conversion allowed, dst may alias src); and the masks themselves as bytes
+ * (tests): matrix sites [rows, cols], attention sites [rows, heads, nkeys] */
+int nlv_dropout_apply(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows, int cols,
+                      const nlv_dropout* drop, void* stream);
+int nlv_dropout_mask(long long rows, int cols, const nlv_dropout* drop, unsigned char* out, void* stream);
+int nlv_dropout_mask_attn(long long rows, int heads, int nkeys, const nlv_dropout* drop, unsigned char* out, void* stream);
+/* nlv_layernorm_bwd whose second output dx2 is the dropout-masked, scaled copy of dx (operand of the GEMMs behind a
+ * residual dropout: d(dropout(a)) = mask * dx / (1 - p)); dx itself stays unmasked (the residual branch) */
+int nlv_layernorm_bwd_drop(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                           long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db,
+                           const nlv_dropout* drop, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Heads, losses, optimiser (lib/sttran.py:404-409; tools/train_STTran.py:169-195; lib/AdamW.py:52-114)

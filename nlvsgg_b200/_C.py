@@ -55,6 +55,21 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO_PATH
 
 
+class Dropout(ctypes.Structure):
+    """nlv_dropout (include/nlv_b200.h)."""
+    _fields_ = [("thr16", ctypes.c_uint), ("scale", ctypes.c_float), ("seed_lo", ctypes.c_uint), ("seed_hi", ctypes.c_uint),
+                ("stream", ctypes.c_uint)]
+
+    @classmethod
+    def make(cls, p: float, seed: int, stream: int) -> "Dropout":
+        d = cls()
+        if p > 0:
+            d.thr16 = min(65535, int(p * 65536.0 + 0.5))
+            d.scale = 1.0 / (1.0 - p)
+            d.seed_lo, d.seed_hi, d.stream = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stream
+        return d
+
+
 class GemmArgs(ctypes.Structure):
     _fields_ = [("a", ctypes.c_void_p), ("b", ctypes.c_void_p), ("d", ctypes.c_void_p), ("bias", ctypes.c_void_p),
                 ("residual", ctypes.c_void_p),
@@ -62,7 +77,8 @@ class GemmArgs(ctypes.Structure):
                 ("lda", ctypes.c_int), ("ldb", ctypes.c_int), ("ldd", ctypes.c_int), ("ldr", ctypes.c_int),
                 ("a_major", ctypes.c_int), ("b_major", ctypes.c_int),
                 ("ab_dtype", ctypes.c_int), ("d_dtype", ctypes.c_int), ("r_dtype", ctypes.c_int),
-                ("relu", ctypes.c_int), ("gate", ctypes.c_void_p), ("ldg", ctypes.c_int), ("gate_dtype", ctypes.c_int)]
+                ("relu", ctypes.c_int), ("gate", ctypes.c_void_p), ("ldg", ctypes.c_int), ("gate_dtype", ctypes.c_int),
+                ("gate_scale", ctypes.c_float), ("drop", Dropout)]
 
 
 _vp, _ip, _i, _ll, _f = ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float

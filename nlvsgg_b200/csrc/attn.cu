@@ -439,10 +439,10 @@ int check_common(int hd, int heads, int n_work, int ld_all_even) {
 namespace nlv {
 bool attn_mma_supported(int hd, int heads, int ld_or);
 int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
-                        const void* work, int n_work, void* o, int ldo, float* lse, cudaStream_t s);
+                        const void* work, int n_work, void* o, int ldo, float* lse, const nlv_dropout* drop, cudaStream_t s);
 int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
                         const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq,
-                        void* dk, int lddk, void* dv, int lddv, cudaStream_t s);
+                        void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s);
 static bool use_mma() {
   const char* e = getenv("NLV_ATTN_SIMT");
   return !(e != nullptr && e[0] == '1');
@@ -460,12 +460,22 @@ extern "C" {
  * q/k/v share in_dtype; base pointers must be 8-byte (f32) / 4-byte (bf16) aligned and row strides even. */
 int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
                  float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, void* stream) {
+  return nlv_attn_fwd_drop(q, ldq, k, ldk, v, ldv, in_dtype, hd, heads, scale, work, n_work, o, ldo, o_dtype, lse, nullptr, stream);
+}
+
+int nlv_attn_fwd_drop(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                      float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, const nlv_dropout* drop,
+                      void* stream) {
   int rc = check_common(hd, heads, n_work, ((ldq | ldk | ldv | ldo) & 1) == 0);
   if (rc != NLV_OK) return rc;
   if (n_work == 0) return NLV_OK;
   NLV_CHECK_ARG(q && k && v && work && o, "attn_fwd: null pointer");
   if (in_dtype == NLV_BF16 && o_dtype == NLV_BF16 && use_mma() && attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo))
-    return launch_attn_fwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, o, ldo, lse, STREAM);
+    return launch_attn_fwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, o, ldo, lse, drop, STREAM);
+  if (drop != nullptr && drop->thr16 != 0u) {
+    nlv::set_error("attn_fwd: attention-weight dropout is implemented on the bf16 tensor-core path only");
+    return NLV_ERR_UNSUPPORTED;
+  }
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define FWD(TI, TO) attn_fwd_kernel<TI, TO><<<grid, THREADS, 0, STREAM>>>(a, (TO*)o, ldo, lse)
@@ -484,6 +494,14 @@ int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
                  float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
                  int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                  int dqkv_dtype, void* stream) {
+  return nlv_attn_bwd_drop(q, ldq, k, ldk, v, ldv, in_dtype, hd, heads, scale, work, n_work, o, ldo, o_dtype, dout, lddo, do_dtype, lse, delta,
+                           dq, lddq, dk, lddk, dv, lddv, dqkv_dtype, nullptr, stream);
+}
+
+int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                      float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
+                      int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                      int dqkv_dtype, const nlv_dropout* drop, void* stream) {
   int rc = check_common(hd, heads, n_work, ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 1) == 0);
   if (rc != NLV_OK) return rc;
   if (n_work == 0) return NLV_OK;
@@ -492,7 +510,11 @@ int nlv_attn_bwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
   if (in_dtype == NLV_BF16 && do_dtype == NLV_BF16 && use_mma() &&
       attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv))
     return launch_attn_bwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv,
-                               lddv, STREAM);
+                               lddv, drop, STREAM);
+  if (drop != nullptr && drop->thr16 != 0u) {
+    nlv::set_error("attn_bwd: attention-weight dropout is implemented on the bf16 tensor-core path only");
+    return NLV_ERR_UNSUPPORTED;
+  }
   AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define BWD(TI, TG)                                                                                                         \

@@ -15,6 +15,7 @@
 // Replaces torch.nn.MultiheadAttention's core (lib/transformer.py:9-13,38-42, lib/dsg_detr.py:21-22) with
 // key_padding_mask semantics folded into the segment bounds.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nlv {
 namespace {
@@ -31,6 +32,7 @@ struct MArgs {
   int hd, heads;
   float scale;
   const int4* work;
+  DropCfg drop;     // dropout on the attention weights (nn.MultiheadAttention(dropout=0.1), lib/transformer.py:9,38)
 };
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -197,6 +199,15 @@ attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ 
       ps0 += s[n][0] + s[n][1]; ps1 += s[n][2] + s[n][3];
     }
     l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;     // per-thread partial row sums; combined over the quad at the end
+    if (a.drop.thr16 != 0u) {   // O accumulates the dropped weights; the normaliser l keeps all of them
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const uint32_t kp0 = keep8_attn(a.drop, seg0 + q0 + g, a.heads, h, (k0 >> 3) + n) >> (2 * t);
+        const uint32_t kp1 = keep8_attn(a.drop, seg0 + q0 + g + 8, a.heads, h, (k0 >> 3) + n) >> (2 * t);
+        s[n][0] = (kp0 & 1u) ? s[n][0] * a.drop.scale : 0.f; s[n][1] = (kp0 & 2u) ? s[n][1] * a.drop.scale : 0.f;
+        s[n][2] = (kp1 & 1u) ? s[n][2] * a.drop.scale : 0.f; s[n][3] = (kp1 & 2u) ? s[n][3] * a.drop.scale : 0.f;
+      }
+    }
     if (k0 > 0) {
 #pragma unroll
       for (int i = 0; i < NT; ++i) { acc[i][0] *= corr0; acc[i][1] *= corr0; acc[i][2] *= corr1; acc[i][3] *= corr1; }
@@ -256,6 +267,15 @@ attn_bwd_dq_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const f
       float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       qk_product(Qs, Ks, lane, s);
       qk_product(Gs, Vs, lane, dp);
+      if (a.drop.thr16 != 0u) {   // dP = mask * d(P_dropped) / (1 - p)
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+          const uint32_t kp0 = keep8_attn(a.drop, r0, a.heads, h, (k0 >> 3) + n) >> (2 * t);
+          const uint32_t kp1 = keep8_attn(a.drop, r1, a.heads, h, (k0 >> 3) + n) >> (2 * t);
+          dp[n][0] = (kp0 & 1u) ? dp[n][0] * a.drop.scale : 0.f; dp[n][1] = (kp0 & 2u) ? dp[n][1] * a.drop.scale : 0.f;
+          dp[n][2] = (kp1 & 1u) ? dp[n][2] * a.drop.scale : 0.f; dp[n][3] = (kp1 & 2u) ? dp[n][3] * a.drop.scale : 0.f;
+        }
+      }
 #pragma unroll
       for (int n = 0; n < 2; ++n)
 #pragma unroll
@@ -333,8 +353,15 @@ attn_bwd_dkv_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const 
         const int qi = n * 8 + 2 * t + (c & 1);
         const int key = g + (c >> 1) * 8;
         const float p = (qi < nq && key < nkeys) ? __expf(s[n][c] * a.scale - lse_s[qi]) : 0.f;
-        pt[n][c] = p;
-        s[n][c] = p * (dp[n][c] - dl_s[qi]);
+        float pd = p, dpv = dp[n][c];
+        if (a.drop.thr16 != 0u) {
+          const int ka = k0 + key;
+          const bool kept = (keep8_attn(a.drop, seg0 + q0 + qi, a.heads, h, ka >> 3) >> (ka & 7)) & 1u;
+          pd = kept ? p * a.drop.scale : 0.f;
+          dpv = kept ? dpv * a.drop.scale : 0.f;
+        }
+        pt[n][c] = pd;                                   // dV += P_dropped^T dO
+        s[n][c] = p * (dpv - dl_s[qi]);                  // dS^T
       }
     const uint32_t pa[4] = {pack2(pt[0][0], pt[0][1]), pack2(pt[0][2], pt[0][3]), pack2(pt[1][0], pt[1][1]), pack2(pt[1][2], pt[1][3])};
     const uint32_t da[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
@@ -361,9 +388,15 @@ bool attn_mma_supported(int hd, int heads, int ld_or) {
   return hd >= 16 && hd <= 256 && (hd & 1) == 0 && (heads & 3) == 0 && (ld_or & 1) == 0;
 }
 
+static DropCfg attn_cfg(const nlv_dropout* d) {
+  DropCfg c = drop_off();
+  if (d != nullptr && d->thr16 != 0u) { c.thr16 = d->thr16; c.scale = d->scale; c.seed_lo = d->seed_lo; c.seed_hi = d->seed_hi; c.stream = d->stream; }
+  return c;
+}
+
 int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
-                        const void* work, int n_work, void* o, int ldo, float* lse, cudaStream_t s) {
-  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+                        const void* work, int n_work, void* o, int ldo, float* lse, const nlv_dropout* drop, cudaStream_t s) {
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop)};
   const size_t smem = 4 * 3 * TILE_B;
   int rc = opt_in_smem(attn_fwd_mma_kernel, smem);
   if (rc != NLV_OK) return rc;
@@ -373,8 +406,8 @@ int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const vo
 }
 
 int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
-                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, cudaStream_t s) {
-  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s) {
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop)};
   const size_t s1 = 2 * 4 * TILE_B, s2 = 4 * TILE_B;
   int rc = opt_in_smem(attn_bwd_dq_mma_kernel, s1);
   if (rc != NLV_OK) return rc;

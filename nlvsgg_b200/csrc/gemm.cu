@@ -1,5 +1,6 @@
 // nlv_gemm dispatcher + the exact-fp32 SIMT GEMM (parity mode, tiny / odd shapes).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nlv {
 
@@ -17,7 +18,8 @@ template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D, const float* __restrict__ bias,
                  const void* residual, int M, int N, int K, int lda, int ldb, int ldd, int ldr, int ab_dtype,
-                 int d_dtype, int r_dtype, int relu, int k_per_split, const void* gate, int ldg, int gate_dtype) {
+                 int d_dtype, int r_dtype, int relu, int k_per_split, const void* gate, int ldg, int gate_dtype, float gate_scale,
+                 const DropCfg drop) {
   __shared__ float As[TK][TM + 1];
   __shared__ float Bs[TK][TN + 1];
   const int tid = threadIdx.x;
@@ -73,7 +75,8 @@ gemm_simt_kernel(const void* __restrict__ A, const void* __restrict__ B, void* D
       if (split) { atomicAdd(reinterpret_cast<float*>(D) + (size_t)gm * ldd + gn, v); continue; }
       if (bias != nullptr) v += bias[gn];
       if (relu) v = fmaxf(v, 0.f);
-      if (gate != nullptr && !(ld_as_float(gate, gate_dtype, (size_t)gm * ldg + gn) > 0.f)) v = 0.f;
+      if (drop.thr16 != 0u) v = ((keep8_matrix(drop, gm, gn >> 3, (N + 7) >> 3) >> (gn & 7)) & 1u) ? v * drop.scale : 0.f;
+      if (gate != nullptr) v = (ld_as_float(gate, gate_dtype, (size_t)gm * ldg + gn) > 0.f) ? v * gate_scale : 0.f;
       if (residual != nullptr) v += ld_as_float(residual, r_dtype, (size_t)gm * ldr + gn);
       st_from_float(D, d_dtype, (size_t)gm * ldd + gn, v);
     }
@@ -85,7 +88,7 @@ int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
   NLV_CHECK_ARG(grid.y <= 65535, "gemm(simt): m=%d too large", g.m);
   int k_per_split = g.k;
   const int tiles = (int)(grid.x * grid.y);
-  if (tiles < 2 * sm_count() && g.k >= 2048 && g.d_dtype == NLV_F32 && !g.bias && !g.residual && !g.relu && !g.gate) {
+  if (tiles < 2 * sm_count() && g.k >= 2048 && g.d_dtype == NLV_F32 && !g.bias && !g.residual && !g.relu && !g.gate && g.drop.thr16 == 0u) {
     int want = cdiv(4 * sm_count(), tiles);
     if (want > g.k / 256) want = g.k / 256;
     if (want > 1) {
@@ -94,9 +97,12 @@ int gemm_simt(const nlv_gemm_args& g, cudaStream_t s) {
       { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, s); if (zrc != NLV_OK) return zrc; }
     }
   }
+  DropCfg dc;
+  dc.thr16 = g.drop.thr16; dc.scale = g.drop.scale; dc.seed_lo = g.drop.seed_lo; dc.seed_hi = g.drop.seed_hi; dc.stream = g.drop.stream;
 #define LAUNCH(AM, BM)                                                                                          \
   gemm_simt_kernel<AM, BM><<<grid, 256, 0, s>>>(g.a, g.b, g.d, g.bias, g.residual, g.m, g.n, g.k, g.lda, g.ldb, \
-                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu, k_per_split, g.gate, g.ldg, g.gate_dtype)
+                                                g.ldd, g.ldr, g.ab_dtype, g.d_dtype, g.r_dtype, g.relu, k_per_split, g.gate, g.ldg, g.gate_dtype, \
+                                                g.gate_scale == 0.f ? 1.f : g.gate_scale, dc)
   if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) LAUNCH(false, false);
   else if (g.a_major == NLV_MAJOR_K) LAUNCH(false, true);
   else if (g.b_major == NLV_MAJOR_K) LAUNCH(true, false);

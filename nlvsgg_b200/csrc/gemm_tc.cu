@@ -20,6 +20,7 @@
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nlv {
 namespace {
@@ -147,6 +148,8 @@ struct Params {
   int relu;
   const void* gate;
   int ldg, gate_dtype;
+  float gate_scale;
+  DropCfg drop;
   int num_m_blocks, num_n_blocks;
   int k_splits, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to a zeroed fp32 D
 };
@@ -366,7 +369,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
         }
+        if (p.drop.thr16 != 0u) {   // dropout of the activated value (before the residual); groups of 8 columns share one Philox call
+          const int gpr = (p.n + 7) >> 3;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            const uint32_t keep = keep8_matrix(p.drop, row, (n0 + c0 + j) >> 3, gpr);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[j + q] = ((keep >> q) & 1u) ? f[j + q] * p.drop.scale : 0.f;
+          }
+        }
         if (p.gate != nullptr) {
+          if (p.gate_scale != 1.f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.gate_scale;
+          }
           const size_t goff = (size_t)row * p.ldg + n0 + c0;
           if (p.gate_dtype == NLV_BF16) {
             const __nv_bfloat16* gt = reinterpret_cast<const __nv_bfloat16*>(p.gate) + goff;
@@ -522,6 +538,9 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.ldr = g.ldr;
   p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
   p.gate = g.gate; p.ldg = g.ldg; p.gate_dtype = g.gate_dtype;
+  p.gate_scale = g.gate_scale == 0.f ? 1.f : g.gate_scale;
+  p.drop.thr16 = g.drop.thr16; p.drop.scale = g.drop.scale; p.drop.seed_lo = g.drop.seed_lo; p.drop.seed_hi = g.drop.seed_hi;
+  p.drop.stream = g.drop.stream;
   p.num_m_blocks = cdiv(g.m, BLOCK_M);
   p.num_n_blocks = cdiv(g.n, BLOCK_N);
   // split-K when the output has too few tiles to fill the GPU and the reduction is long (weight gradients of the
@@ -530,7 +549,8 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   const int tiles0 = p.num_m_blocks * p.num_n_blocks;
   p.k_splits = 1;
   p.kb_per_split = nkb;
-  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu && g.gate == nullptr) {
+  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu && g.gate == nullptr &&
+      g.drop.thr16 == 0u) {
     int want = sm_count() / tiles0;
     if (want > nkb / 8) want = nkb / 8;
     if (want > 1) {

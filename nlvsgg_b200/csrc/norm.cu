@@ -294,7 +294,7 @@ int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, in
 int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
                             int y2dt, float* mean, float* rstd, cudaStream_t s);
 int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
-                               int cols, float* dx, void* dx2, int dx2dt, cudaStream_t s);
+                               int cols, float* dx, void* dx2, int dx2dt, const nlv_dropout* drop, cudaStream_t s);
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace nlv
 
@@ -317,15 +317,18 @@ int nlv_layernorm_fwd(const float* x, long long rows, int cols, const float* w, 
 }
 
 /* dw, db are ACCUMULATED into (callers zero them). */
-int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
-                      long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, void* stream) {
+int nlv_layernorm_bwd_drop(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                           long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db,
+                           const nlv_dropout* drop, void* stream) {
   NLV_CHECK_ARG(rows >= 0 && cols > 0 && cols <= 32 * LN_MAX_PER_LANE, "layernorm_bwd: cols=%d unsupported", cols);
   if (rows == 0) return NLV_OK;
   NLV_CHECK_ARG(dy && x && mean && rstd && w && dw && db && (dx || dx2), "layernorm_bwd: null pointer");
+  const bool dropping = drop != nullptr && drop->thr16 != 0u;
   if ((cols & 3) == 0 && al16(dy) && al16(x) && al16(w) && al16(dx) && (dx2 == nullptr || (reinterpret_cast<uintptr_t>(dx2) & 15) == 0)) {
-    const int rc = launch_layernorm_bwd_dx_v4(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, STREAM);
+    const int rc = launch_layernorm_bwd_dx_v4(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, drop, STREAM);
     if (rc != NLV_OK) return rc;
   } else {
+    if (dropping) { nlv::set_error("layernorm_bwd: the dropout variant needs 16-byte aligned rows (cols %% 4 == 0)"); return NLV_ERR_UNSUPPORTED; }
     layernorm_bwd_dx_kernel<<<cdiv(rows, 4), 128, 0, STREAM>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype);
     NLV_CHECK_LAUNCH();
   }
@@ -336,6 +339,11 @@ int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const 
   layernorm_bwd_param_kernel<<<grid, block, 0, STREAM>>>(dy, x, mean, rstd, rows, cols, dw, db);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
+}
+
+int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                      long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, void* stream) {
+  return nlv_layernorm_bwd_drop(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, dw, db, nullptr, stream);
 }
 
 /* Training-mode statistics.  seg: int[nseg+1] row offsets (device).  sums_ws: double[nseg*2*C] workspace (zeroed here).

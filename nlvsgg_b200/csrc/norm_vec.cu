@@ -1,5 +1,6 @@
 // 16-byte vectorised variants of the segmented BatchNorm kernels (channels-last rows x C, C % 8 == 0).
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nlv {
 
@@ -405,7 +406,7 @@ template <int NV>
 __global__ void __launch_bounds__(128)
 layernorm_bwd_dx_v4_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
                            const float* __restrict__ rstd, const float* __restrict__ w, long long rows, int cols,
-                           float* __restrict__ dx, void* __restrict__ dx2, int dx2dt) {
+                           float* __restrict__ dx, void* __restrict__ dx2, int dx2dt, const DropCfg drop) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (row >= rows) return;
@@ -442,7 +443,14 @@ layernorm_bwd_dx_v4_kernel(const float* __restrict__ dy, const float* __restrict
       o.x = rs * (g[j].x - s1 - xh[j].x * s2); o.y = rs * (g[j].y - s1 - xh[j].y * s2);
       o.z = rs * (g[j].z - s1 - xh[j].z * s2); o.w = rs * (g[j].w - s1 - xh[j].w * s2);
       if (dx) *reinterpret_cast<float4*>(dx + (size_t)row * cols + 4 * i) = o;
-      if (dx2) st_row4(dx2, dx2dt, (size_t)row * cols + 4 * i, o);
+      if (dx2) {
+        if (drop.thr16 != 0u) {   // second output = mask * dx / (1 - p): columns 4 i .. 4 i + 3 are one nibble of group i / 2
+          const uint32_t keep = keep8_matrix(drop, row, i >> 1, (cols + 7) >> 3) >> ((i & 1) * 4);
+          o.x = (keep & 1u) ? o.x * drop.scale : 0.f; o.y = (keep & 2u) ? o.y * drop.scale : 0.f;
+          o.z = (keep & 4u) ? o.z * drop.scale : 0.f; o.w = (keep & 8u) ? o.w * drop.scale : 0.f;
+        }
+        st_row4(dx2, dx2dt, (size_t)row * cols + 4 * i, o);
+      }
     }
   }
 }
@@ -459,11 +467,13 @@ int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const floa
   return NLV_OK;
 }
 int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
-                               int cols, float* dx, void* dx2, int dx2dt, cudaStream_t s) {
+                               int cols, float* dx, void* dx2, int dx2dt, const nlv_dropout* dr, cudaStream_t s) {
   const unsigned grid = (unsigned)cdiv(rows, 4);
-  if (cols <= 512) layernorm_bwd_dx_v4_kernel<4><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
-  else if (cols <= 1024) layernorm_bwd_dx_v4_kernel<8><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
-  else layernorm_bwd_dx_v4_kernel<16><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt);
+  DropCfg d = drop_off();
+  if (dr != nullptr && dr->thr16 != 0u) { d.thr16 = dr->thr16; d.scale = dr->scale; d.seed_lo = dr->seed_lo; d.seed_hi = dr->seed_hi; d.stream = dr->stream; }
+  if (cols <= 512) layernorm_bwd_dx_v4_kernel<4><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
+  else if (cols <= 1024) layernorm_bwd_dx_v4_kernel<8><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
+  else layernorm_bwd_dx_v4_kernel<16><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

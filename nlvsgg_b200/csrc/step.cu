@@ -151,7 +151,21 @@ struct nlv_session {
   int run_backward(const float* d26_in, const float* dobj_in);
   int prepare_weights();
   int mm(const T& a, int am, const T& b, int bm, const T& out, const float* bias = nullptr, const T* residual = nullptr,
-         bool relu = false, const T* gate = nullptr, bool exact = false);
+         bool relu = false, const T* gate = nullptr, bool exact = false, const nlv_dropout* drop = nullptr, float gate_scale = 1.f);
+  bool dropping = false;
+  // dropout site of a layer: 0 = attention-output residual, 1 = FFN inner (after ReLU), 2 = FFN-output residual, 3 = attention weights;
+  // 8000 = object-classifier pos_embed, 8001 = DSG-DETR positional encoder
+  nlv_dropout site(int layer, int which) const {
+    nlv_dropout d;
+    memset(&d, 0, sizeof(d));
+    if (dropping) {
+      d.thr16 = (unsigned)(M.dropout_p * 65536.f + 0.5f);
+      d.scale = 1.f / (1.f - M.dropout_p);
+      d.seed_lo = (unsigned)M.seed; d.seed_hi = (unsigned)(M.seed >> 32);
+      d.stream = (unsigned)(layer * 8 + which);
+    }
+    return d;
+  }
   int opnd(const T& x, T* out);
   int tma_ready(const T& x, T* out);
   int split3(const T& x, int major, int pattern, T* out);
@@ -243,7 +257,7 @@ int nlv_session::split3(const T& x, int major, int pattern, T* out) {
 }
 
 int nlv_session::mm(const T& a_in, int am, const T& b_in, int bm, const T& out, const float* bias, const T* residual, bool relu,
-                    const T* gate, bool exact) {
+                    const T* gate, bool exact, const nlv_dropout* drop, float gate_scale) {
   T a = a_in, b = b_in;
   const long long m = am == K_ ? a.rows : a.cols;
   const long long kdim = am == K_ ? a.cols : a.rows;
@@ -273,7 +287,8 @@ int nlv_session::mm(const T& a_in, int am, const T& b_in, int bm, const T& out, 
   g.ab_dtype = a.dt | force_simt; g.d_dtype = out.dt;
   g.relu = relu ? 1 : 0;
   if (residual != nullptr) { g.residual = residual->p; g.ldr = residual->ld; g.r_dtype = residual->dt; }
-  if (gate != nullptr) { g.gate = gate->p; g.ldg = gate->ld; g.gate_dtype = gate->dt; }
+  if (gate != nullptr) { g.gate = gate->p; g.ldg = gate->ld; g.gate_dtype = gate->dt; g.gate_scale = gate_scale; }
+  if (drop != nullptr) g.drop = *drop;
   if (g_prof_on) {   // algorithmic FLOPs of the product as the model states it (a bf16x3 product still counts 2mnk)
     g_next_flops = 2.0 * (double)m * (double)n * (double)kdim; g_next_m = (int)m; g_next_n = (int)n; g_next_k = (int)kdim; g_next_dt = a.dt;
   }
@@ -308,17 +323,18 @@ int nlv_session::encoder_fwd(int layer, const T& x, const T& xop, const int* wor
   if (!b16 && want_ctx) x1 = keep(Mr, D, NLV_F32);
   T h = ctx(Mr, DFF, AD), y2 = ctx(Mr, D, NLV_F32), m2 = ctx(Mr, 1, NLV_F32), r2 = ctx(Mr, 1, NLV_F32);
   OOM_CHECK();
+  const nlv_dropout d0 = site(layer, 0), d1 = site(layer, 1), d2 = site(layer, 2), d3 = site(layer, 3);
   CK(mm(xop, K_, W(LS(layer, NLV_L_INPROJ_W), 3 * D, D), K_, qkv, P(LS(layer, NLV_L_INPROJ_B))));
   g_next_units = 4.0 * (double)Mr * D * qkv.esz(); g_next_dt = qkv.dt;   // algorithmic bytes: Q, K, V in, O out
-  RUN(nlv_attn_fwd(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
-                   HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, st));
-  CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y1, P(LS(layer, NLV_L_OUTPROJ_B)), &x));
+  RUN(nlv_attn_fwd_drop(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
+                        HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, &d3, st));
+  CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y1, P(LS(layer, NLV_L_OUTPROJ_B)), &x, false, nullptr, false, &d0));
   g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y1.f(), Mr, D, P(LS(layer, NLV_L_NORMA_W)), P(LS(layer, NLV_L_NORMA_B)), 1e-5f, x1.f(),
                         b16 ? x1op.p : nullptr, NLV_BF16, m1.f(), r1.f(), st));
   const T& x1o = b16 ? x1op : x1;
-  CK(mm(x1o, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), K_, h, P(LS(layer, NLV_L_LIN1_B)), nullptr, true));
-  CK(mm(h, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), K_, y2, P(LS(layer, NLV_L_LIN2_B)), &x1));
+  CK(mm(x1o, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), K_, h, P(LS(layer, NLV_L_LIN1_B)), nullptr, true, nullptr, false, &d1));
+  CK(mm(h, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), K_, y2, P(LS(layer, NLV_L_LIN2_B)), &x1, false, nullptr, false, &d2));
   g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y2.f(), Mr, D, P(LS(layer, NLV_L_NORMB_W)), P(LS(layer, NLV_L_NORMB_B)), 1e-5f, x2.f(),
                         x2op.ok() ? x2op.p : nullptr, NLV_BF16, m2.f(), r2.f(), st));
@@ -334,25 +350,28 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   const bool b16 = AD == NLV_BF16;
   T dx = need_dx ? keep(Mr, D, NLV_F32) : T();
   Scope sc(this);
+  const nlv_dropout d0 = site(layer, 0), d1 = site(layer, 1), d2 = site(layer, 2), d3 = site(layer, 3);
   T dy2 = tmp(Mr, D, NLV_F32), dy2op = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
-  RUN(nlv_layernorm_bwd(dx2.f(), c.y2.f(), c.m2.f(), c.r2.f(), P(LS(layer, NLV_L_NORMB_W)), Mr, D, dy2.f(), b16 ? dy2op.p : nullptr, NLV_BF16,
-                        G(LS(layer, NLV_L_NORMB_W)), G(LS(layer, NLV_L_NORMB_B)), st));
+  // dy2 = gradient of the residual stream; dy2op = its copy behind the FFN-output dropout (mask * dy2 / (1 - p) when dropping)
+  RUN(nlv_layernorm_bwd_drop(dx2.f(), c.y2.f(), c.m2.f(), c.r2.f(), P(LS(layer, NLV_L_NORMB_W)), Mr, D, dy2.f(), b16 ? dy2op.p : nullptr,
+                             NLV_BF16, G(LS(layer, NLV_L_NORMB_W)), G(LS(layer, NLV_L_NORMB_B)), &d2, st));
   const T& dy2o = b16 ? dy2op : dy2;
-  CK(lin_grads(dy2o, c.h, dy2, LS(layer, NLV_L_LIN2_W), LS(layer, NLV_L_LIN2_B)));
+  CK(lin_grads(dy2o, c.h, dropping ? dy2o : dy2, LS(layer, NLV_L_LIN2_W), LS(layer, NLV_L_LIN2_B)));
   T dh = tmp(Mr, DFF, AD);
-  CK(mm(dy2o, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), MN_, dh, nullptr, nullptr, false, &c.h));   // ReLU backward fused
+  CK(mm(dy2o, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), MN_, dh, nullptr, nullptr, false, &c.h, false, nullptr,
+        dropping ? d1.scale : 1.f));   // ReLU (+ inner dropout) backward fused: h > 0 <=> kept and active
   CK(lin_grads(dh, c.x1op, dh, LS(layer, NLV_L_LIN1_W), LS(layer, NLV_L_LIN1_B)));
   T dx1 = tmp(Mr, D, NLV_F32);
   CK(mm(dh, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), MN_, dx1, nullptr, &dy2));
   T dy1 = tmp(Mr, D, NLV_F32), dy1op = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
-  RUN(nlv_layernorm_bwd(dx1.f(), c.y1.f(), c.m1.f(), c.r1.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy1.f(), b16 ? dy1op.p : nullptr, NLV_BF16,
-                        G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), st));
+  RUN(nlv_layernorm_bwd_drop(dx1.f(), c.y1.f(), c.m1.f(), c.r1.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy1.f(), b16 ? dy1op.p : nullptr,
+                             NLV_BF16, G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), &d0, st));
   const T& dy1o = b16 ? dy1op : dy1;
-  CK(lin_grads(dy1o, c.o, dy1, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
+  CK(lin_grads(dy1o, c.o, dropping ? dy1o : dy1, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
   T d_o = tmp(Mr, D, AD);
   CK(mm(dy1o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), MN_, d_o));
   T dqkv = tmp(Mr, 3 * D, AD), delta = tmp(Mr * HEADS, 1, NLV_F32);
@@ -360,9 +379,9 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   const T& q = c.qkv;
   const size_t e = q.esz();
   g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
-  RUN(nlv_attn_bwd(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work,
-                   c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e, dqkv.ld,
-                   (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, st));
+  RUN(nlv_attn_bwd_drop(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work,
+                        c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e, dqkv.ld,
+                        (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, &d3, st));
   CK(lin_grads(dqkv, c.xop, dqkv, LS(layer, NLV_L_INPROJ_W), LS(layer, NLV_L_INPROJ_B)));
   if (need_dx) {
     CK(mm(dqkv, K_, W(LS(layer, NLV_L_INPROJ_W), 3 * D, D), MN_, dx, nullptr, &dy1));
@@ -384,20 +403,21 @@ int nlv_session::decoder_fwd(int layer, const T& x, const T& xop, const T& xpop,
   if (!b16 && want_ctx) t = keep(Mr, D, NLV_F32);
   T h = ctx(Mr, DFF, AD);
   OOM_CHECK();
+  const nlv_dropout d0 = site(layer, 0), d1 = site(layer, 1), d2 = site(layer, 2), d3 = site(layer, 3);
   const T win = W(LS(layer, NLV_L_INPROJ_W), 3 * D, D);
   const float* bin = P(LS(layer, NLV_L_INPROJ_B));
   CK(mm(xpop, K_, win.rs(0, 2 * D), K_, qkv.cs(0, 2 * D), bin));
   CK(mm(xop, K_, win.rs(2 * D, D), K_, qkv.cs(2 * D, D), bin + 2 * D));
   g_next_units = 4.0 * (double)Mr * D * qkv.esz(); g_next_dt = qkv.dt;   // algorithmic bytes: Q, K, V in, O out
-  RUN(nlv_attn_fwd(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
-                   HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work, B.n_glob_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, st));
-  CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y, P(LS(layer, NLV_L_OUTPROJ_B)), &x));
+  RUN(nlv_attn_fwd_drop(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
+                        HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work, B.n_glob_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, &d3, st));
+  CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y, P(LS(layer, NLV_L_OUTPROJ_B)), &x, false, nullptr, false, &d0));
   g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y.f(), Mr, D, P(LS(layer, NLV_L_NORMA_W)), P(LS(layer, NLV_L_NORMA_B)), 1e-5f, t.f(), b16 ? top.p : nullptr,
                         NLV_BF16, m3.f(), r3.f(), st));
   const T& to = b16 ? top : t;
-  CK(mm(to, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), K_, h, P(LS(layer, NLV_L_LIN1_B)), nullptr, true));
-  CK(mm(h, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), K_, out, P(LS(layer, NLV_L_LIN2_B)), &t));
+  CK(mm(to, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), K_, h, P(LS(layer, NLV_L_LIN1_B)), nullptr, true, nullptr, false, &d1));
+  CK(mm(h, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), K_, out, P(LS(layer, NLV_L_LIN2_B)), &t, false, nullptr, false, &d2));
   if (c != nullptr) { c->xop = xop; c->xpop = xpop; c->qkv = qkv; c->o = o; c->lse = lse; c->y = y; c->m3 = m3; c->r3 = r3; c->top = to; c->h = h; }
   *out_ = out;
   return NLV_OK;
@@ -410,21 +430,28 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   const bool b16 = AD == NLV_BF16;
   T dx = keep(Mr, D, NLV_F32);
   Scope sc(this);
+  const nlv_dropout d0 = site(layer, 0), d1 = site(layer, 1), d2 = site(layer, 2), d3 = site(layer, 3);
   T doutop;
-  CK(opnd(dout, &doutop));
-  CK(lin_grads(doutop, c.h, dout, LS(layer, NLV_L_LIN2_W), LS(layer, NLV_L_LIN2_B)));
+  if (dropping) {     // operand behind the FFN-output dropout: mask * dout / (1 - p)
+    doutop = tmp(Mr, D, AD);
+    OOM_CHECK();
+    RUN(nlv_dropout_apply(dout.p, dout.dt, dout.ld, doutop.p, doutop.dt, doutop.ld, Mr, D, &d2, st));
+  } else {
+    CK(opnd(dout, &doutop));
+  }
+  CK(lin_grads(doutop, c.h, dropping ? doutop : dout, LS(layer, NLV_L_LIN2_W), LS(layer, NLV_L_LIN2_B)));
   T dh = tmp(Mr, DFF, AD);
-  CK(mm(doutop, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), MN_, dh, nullptr, nullptr, false, &c.h));
+  CK(mm(doutop, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), MN_, dh, nullptr, nullptr, false, &c.h, false, nullptr, dropping ? d1.scale : 1.f));
   CK(lin_grads(dh, c.top, dh, LS(layer, NLV_L_LIN1_W), LS(layer, NLV_L_LIN1_B)));
   T dt = tmp(Mr, D, NLV_F32);
   CK(mm(dh, K_, W(LS(layer, NLV_L_LIN1_W), DFF, D), MN_, dt, nullptr, &dout));
   T dy = tmp(Mr, D, NLV_F32), dyop = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
-  RUN(nlv_layernorm_bwd(dt.f(), c.y.f(), c.m3.f(), c.r3.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy.f(), b16 ? dyop.p : nullptr, NLV_BF16,
-                        G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), st));
+  RUN(nlv_layernorm_bwd_drop(dt.f(), c.y.f(), c.m3.f(), c.r3.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy.f(), b16 ? dyop.p : nullptr, NLV_BF16,
+                             G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), &d0, st));
   const T& dyo = b16 ? dyop : dy;
-  CK(lin_grads(dyo, c.o, dy, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
+  CK(lin_grads(dyo, c.o, dropping ? dyo : dy, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
   T d_o = tmp(Mr, D, AD);
   CK(mm(dyo, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), MN_, d_o));
   T dqkv = tmp(Mr, 3 * D, AD), delta = tmp(Mr * HEADS, 1, NLV_F32);
@@ -432,9 +459,9 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   const T& q = c.qkv;
   const size_t e = q.esz();
   g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
-  RUN(nlv_attn_bwd(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work,
-                   B.n_glob_work, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e,
-                   dqkv.ld, (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, st));
+  RUN(nlv_attn_bwd_drop(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work,
+                        B.n_glob_work, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e,
+                        dqkv.ld, (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, &d3, st));
   const T gw = mk(G(LS(layer, NLV_L_INPROJ_W)), NLV_F32, 3 * D, D);
   CK(mm(dqkv.cs(0, 2 * D), MN_, c.xpop, MN_, gw.rs(0, 2 * D)));
   CK(mm(dqkv.cs(2 * D, D), MN_, c.xop, MN_, gw.rs(2 * D, D)));
@@ -515,6 +542,11 @@ int nlv_session::object_classifier_fwd() {
   RUN(nlv_center_size(B.boxes, N, cs.f(), st));
   CK(bn_fwd(cs, B.box_seg, B.box_row, 1, NLV_P_OC_BN0_W, 0.01f / 10.0f, false, pos_bn, &oc.mean0, &oc.var0));
   CK(mm(pos_bn, K_, mk(P(NLV_P_OC_LIN1_W), NLV_F32, 128, 4), K_, objfeat.cs(2248, 128), P(NLV_P_OC_LIN1_B), nullptr, true, nullptr, true));
+  if (dropping) {     // nn.Dropout(0.1) that closes pos_embed (lib/sttran.py:46)
+    const nlv_dropout dp = site(1000, 0);
+    const T pe = objfeat.cs(2248, 128);
+    RUN(nlv_dropout_apply(pe.p, pe.dt, pe.ld, pe.p, pe.dt, pe.ld, N, 128, &dp, st));
+  }
   CK(mm(objfeat, K_, W(NLV_P_OC_DEC0_W, 1024, 2376), K_, h1, P(NLV_P_OC_DEC0_B)));
   CK(bn_fwd(h1, B.box_seg, B.box_row, 1, NLV_P_OC_BN1_W, 0.1f, true, h2, &oc.mean1, &oc.var1));
   CK(mm(h2, K_, mk(P(NLV_P_OC_DEC3_W), NLV_F32, 37, 1024), K_, obj_logits, P(NLV_P_OC_DEC3_B), nullptr, false, nullptr, true));
@@ -542,6 +574,10 @@ int nlv_session::object_classifier_bwd(const T& dlogits) {
   const T gatev = oc.objfeat.cs(2248, 128);
   const T dt128 = dtail.cs(200, 128);
   RUN(nlv_relu_mask(dt128.p, dt128.dt, dt128.ld, gatev.p, gatev.dt, gatev.ld, N, 128, dpos.p, dpos.dt, dpos.ld, st));
+  if (dropping) {     // kept entries (the only non-zero ones after the gate) pick up the 1 / (1 - p) of the forward dropout
+    const nlv_dropout dp = site(1000, 0);
+    RUN(nlv_dropout_apply(dpos.p, dpos.dt, dpos.ld, dpos.p, dpos.dt, dpos.ld, N, 128, &dp, st));
+  }
   CK(mm(dpos, MN_, oc.pos_bn, MN_, mk(G(NLV_P_OC_LIN1_W), NLV_F32, 128, 4), nullptr, nullptr, false, nullptr, true));
   RUN(nlv_colsum(dpos.p, dpos.dt, dpos.ld, N, 128, nullptr, 1, G(NLV_P_OC_LIN1_B), st));
   T dposbn = tmp(N, 4, NLV_F32), dcs = tmp(N, 4, NLV_F32);
@@ -760,7 +796,13 @@ int nlv_session::dsg_transformer_fwd(const T& rel_in, T* out_) {
   CK(encoder_fwd(0, rel_in, xop, B.local_work, B.n_local_work, false, &x, &xo, want_ctx ? &enc[0] : nullptr));
   T g = keep(R, D, NLV_F32), gop = b16 ? ctx(R, D, NLV_BF16) : T();
   OOM_CHECK();
-  RUN(nlv_gather_rows(x.p, NLV_F32, D, B.cls_perm, P(NLV_P_POS), B.cls_pos, D, R, D, g.p, NLV_F32, D, b16 ? gop.p : nullptr, NLV_BF16, D, st));
+  RUN(nlv_gather_rows(x.p, NLV_F32, D, B.cls_perm, P(NLV_P_POS), B.cls_pos, D, R, D, g.p, NLV_F32, D, (b16 && !dropping) ? gop.p : nullptr,
+                      NLV_BF16, D, st));
+  if (dropping) {     // PositionalEncoding.dropout (lib/dsg_detr.py:28,48) on x + pe
+    const nlv_dropout dp = site(1001, 0);
+    RUN(nlv_dropout_apply(g.p, g.dt, g.ld, g.p, g.dt, g.ld, R, D, &dp, st));
+    if (b16) RUN(nlv_convert(g.p, g.dt, g.ld, gop.p, gop.dt, gop.ld, R, D, st));
+  }
   if (!b16) gop = g;
   for (int i = 0; i < 3; ++i) {
     T g2, g2op;
@@ -785,6 +827,10 @@ int nlv_session::dsg_transformer_bwd(const T& dout, T* drel) {
   }
   T dx = keep(R, D, NLV_F32);   // the encoding is a constant buffer
   OOM_CHECK();
+  if (dropping) {
+    const nlv_dropout dp = site(1001, 0);
+    RUN(nlv_dropout_apply(dg.p, dg.dt, dg.ld, dg.p, dg.dt, dg.ld, R, D, &dp, st));
+  }
   RUN(nlv_gather_rows(dg.p, NLV_F32, D, B.cls_iperm, nullptr, nullptr, 0, R, D, dx.p, NLV_F32, D, nullptr, 0, D, st));
   CK(encoder_bwd(0, enc[0], dx, B.local_work, B.n_local_work, true, drel));
   return NLV_OK;
@@ -885,7 +931,6 @@ int nlv_session::setup(const nlv_model* model, const nlv_batch* batch, int flags
   NLV_CHECK_ARG(M.n_slots >= NLV_P_LAYER0 + n_layers * NLV_P_LAYER_STRIDE, "session: parameter table has %d slots, model needs %d", M.n_slots,
                 NLV_P_LAYER0 + n_layers * NLV_P_LAYER_STRIDE);
   NLV_CHECK_ARG(M.params != nullptr, "session: null parameter table");
-  NLV_CHECK_ARG(M.dropout_p == 0.f || !M.training || M.dropout_p < 1.f, "session: bad dropout_p");
   params.assign(M.params, M.params + M.n_slots);
   if (M.params_op != nullptr) pop.assign(M.params_op, M.params_op + M.n_slots); else pop.clear();
   if (M.grad_offset != nullptr) goff.assign(M.grad_offset, M.grad_offset + M.n_slots); else goff.clear();
@@ -893,6 +938,11 @@ int nlv_session::setup(const nlv_model* model, const nlv_batch* batch, int flags
   want_ctx = (flags & NLV_RUN_CTX) != 0;
   training = M.training != 0;
   AD = M.precision == NLV_PREC_BF16 ? NLV_BF16 : NLV_F32;
+  dropping = training && M.dropout_p > 0.f;
+  NLV_CHECK_ARG(!dropping || M.precision == NLV_PREC_BF16,
+                "session: dropout is implemented on the bf16 path (attention-weight masks live in the tensor-core attention kernels); "
+                "run the fp32 / bf16x3 parity modes with dropout 0");
+  NLV_CHECK_ARG(M.dropout_p >= 0.f && M.dropout_p < 1.f, "session: bad dropout_p");
   N = B.n_boxes; R = B.n_pairs; Mg = B.n_stream;
   NLV_CHECK_ARG(N >= 0 && R >= 0 && Mg >= 0 && B.nv >= 1, "session: bad batch sizes");
   return NLV_OK;

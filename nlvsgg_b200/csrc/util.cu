@@ -1,6 +1,7 @@
 // Small helper kernels of the model sequencer (step.cu): multi-segment convert / copy, weight layout permutation,
 // byte fill, the chain rule of the activated heads.
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace nlv {
 namespace {
@@ -96,6 +97,47 @@ __global__ void heads_activation_bwd_kernel(const float* __restrict__ datt, cons
 }
 
 __global__ void set_seg_kernel(int* p, int rows) { p[0] = 0; p[1] = rows; }
+
+// dst = keep ? src * scale : 0 ; one thread per group of 8 columns (one Philox call)
+__global__ void dropout_apply_kernel(const void* __restrict__ src, int sdt, int lds, void* dst, int ddt, int ldd, long long rows, int cols,
+                                     const DropCfg drop) {
+  const int gpr = (cols + 7) >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * gpr) return;
+  const long long r = i / gpr;
+  const int g = (int)(i - r * gpr);
+  const uint32_t keep = keep8_matrix(drop, r, g, gpr);
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int c = g * 8 + q;
+    if (c < cols) {
+      const float v = ld_as_float(src, sdt, (size_t)r * lds + c);
+      st_from_float(dst, ddt, (size_t)r * ldd + c, ((keep >> q) & 1u) ? v * drop.scale : 0.f);
+    }
+  }
+}
+__global__ void dropout_mask_kernel(long long rows, int cols, const DropCfg drop, unsigned char* __restrict__ out) {
+  const int gpr = (cols + 7) >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * gpr) return;
+  const long long r = i / gpr;
+  const int g = (int)(i - r * gpr);
+  const uint32_t keep = keep8_matrix(drop, r, g, gpr);
+  for (int q = 0; q < 8; ++q)
+    if (g * 8 + q < cols) out[(size_t)r * cols + g * 8 + q] = (keep >> q) & 1u;
+}
+__global__ void dropout_mask_attn_kernel(long long rows, int heads, int nkeys, const DropCfg drop, unsigned char* __restrict__ out) {
+  const int kgs = (nkeys + 7) >> 3;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * heads * kgs) return;
+  const int kg = (int)(i % kgs);
+  const long long rh = i / kgs;
+  const int h = (int)(rh % heads);
+  const long long r = rh / heads;
+  const uint32_t keep = keep8_attn(drop, r, heads, h, kg);
+  for (int q = 0; q < 8; ++q)
+    if (kg * 8 + q < nkeys) out[((size_t)r * heads + h) * nkeys + kg * 8 + q] = (keep >> q) & 1u;
+}
 
 // Zero-suppressed union features (packed feature files, nlvsgg_b200/featfile.py) -> dense bf16 rows [rows, 2048].
 // One warp per row.  The row's stored values (channel order, vals[off[row] .. off[row+1])) are staged in shared memory with
@@ -255,6 +297,43 @@ int nlv_create_dis(const float* conf, const float* other, const int* idx, long l
   if (n == 0) return NLV_OK;
   NLV_CHECK_ARG(conf && idx && out, "create_dis: null pointer");
   create_dis_kernel<<<cdiv(n * 36, 256), 256, 0, STREAM>>>(conf, other, idx, n, out);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+static DropCfg to_cfg(const nlv_dropout* d) {
+  DropCfg c = drop_off();
+  if (d != nullptr && d->thr16 != 0u) { c.thr16 = d->thr16; c.scale = d->scale; c.seed_lo = d->seed_lo; c.seed_hi = d->seed_hi; c.stream = d->stream; }
+  return c;
+}
+
+int nlv_dropout_apply(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows, int cols,
+                      const nlv_dropout* drop, void* stream) {
+  NLV_CHECK_ARG(rows >= 0 && cols >= 0, "dropout_apply: bad sizes");
+  if (rows * cols == 0) return NLV_OK;
+  NLV_CHECK_ARG(src && dst, "dropout_apply: null pointer");
+  const DropCfg c = to_cfg(drop);
+  if (c.thr16 == 0u) return nlv_convert(src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols, stream);
+  const long long n = rows * ((cols + 7) / 8);
+  dropout_apply_kernel<<<cdiv(n, 256), 256, 0, STREAM>>>(src, src_dtype, lds, dst, dst_dtype, ldd, rows, cols, c);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_dropout_mask(long long rows, int cols, const nlv_dropout* drop, unsigned char* out, void* stream) {
+  NLV_CHECK_ARG(rows >= 0 && cols >= 0 && out, "dropout_mask: bad arguments");
+  if (rows * cols == 0) return NLV_OK;
+  const long long n = rows * ((cols + 7) / 8);
+  dropout_mask_kernel<<<cdiv(n, 256), 256, 0, STREAM>>>(rows, cols, to_cfg(drop), out);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_dropout_mask_attn(long long rows, int heads, int nkeys, const nlv_dropout* drop, unsigned char* out, void* stream) {
+  NLV_CHECK_ARG(rows >= 0 && heads > 0 && nkeys > 0 && out, "dropout_mask_attn: bad arguments");
+  if (rows == 0) return NLV_OK;
+  const long long n = rows * heads * ((nkeys + 7) / 8);
+  dropout_mask_attn_kernel<<<cdiv(n, 256), 256, 0, STREAM>>>(rows, heads, nkeys, to_cfg(drop), out);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -32,56 +32,85 @@ def _limits():
 
 
 class PackedGT:
-    """Ground truth of a list of frames flattened into the kernel's arrays (host side, numpy)."""
+    """Ground truth of a list of frames flattened into the kernel's arrays (host side, numpy).
+
+    `pack_video` walks the python annotation structure of ONE video once (evaluation_recall.py:404-419: person = box 0,
+    class 1; attention / contacting triplets are (human, object, p), spatial ones (object, human, p)); ground truth is static
+    across epochs, so evaluators cache the result per annotation object and a batch is a concatenation of cached arrays."""
 
     def __init__(self):
-        self.rel, self.cls, self.box = [], [], []
+        self.rel, self.cls, self.box = [], [], []       # per frame (kept for callers that index frames)
         self.rel_off, self.box_off = [0], [0]
 
+    @staticmethod
+    def pack_video(gt, idx_att, idx_spa, idx_con):
+        """-> (rel i32[G,3], cls i32[Gb], box f32[Gb,4], rels per frame i64[F], boxes per frame i64[F])"""
+        rel, cls, box, nrel, nbox = [], [], [], [], []
+        for frame_gt in gt:
+            nb = len(frame_gt)
+            cls.append(1)
+            box.append(np.asarray(frame_gt[0]["person_bbox"], dtype=np.float64).reshape(-1)[:4])
+            g0 = len(rel)
+            for m, obj in enumerate(frame_gt[1:]):
+                box.append(np.asarray(obj["bbox"], dtype=np.float64))
+                cls.append(int(obj["class"]))
+                a = np.asarray(obj["attention_relationship"]).reshape(-1)
+                rel.append((0, m + 1, idx_att[int(a[0])]))
+                for sp in np.asarray(obj["spatial_relationship"]).reshape(-1).tolist():
+                    rel.append((m + 1, 0, idx_spa[int(sp)]))
+                for c in np.asarray(obj["contacting_relationship"]).reshape(-1).tolist():
+                    rel.append((0, m + 1, idx_con[int(c)]))
+            nrel.append(len(rel) - g0)
+            nbox.append(nb)
+        return (np.asarray(rel, dtype=np.int32).reshape(-1, 3), np.asarray(cls, dtype=np.int32),
+                np.asarray(box, dtype=np.float64).reshape(-1, 4).astype(np.float32),     # rounded to f32 exactly as :765 does
+                np.asarray(nrel, dtype=np.int64), np.asarray(nbox, dtype=np.int64))
+
     def add_frame(self, frame_gt, idx_att, idx_spa, idx_con):
-        """evaluation_recall.py:404-419: person = box 0 (class 1); attention/contacting triplets are
-        (human, object, p), spatial ones (object, human, p)."""
-        nb = len(frame_gt)
-        boxes = np.zeros((nb, 4), dtype=np.float64)
-        cls = np.zeros(nb, dtype=np.int32)
-        cls[0] = 1
-        boxes[0] = np.asarray(frame_gt[0]["person_bbox"], dtype=np.float64).reshape(-1)[:4]
-        rel = []
-        for m, obj in enumerate(frame_gt[1:]):
-            boxes[m + 1] = np.asarray(obj["bbox"], dtype=np.float64)
-            cls[m + 1] = int(obj["class"])
-            a = np.asarray(obj["attention_relationship"]).reshape(-1)
-            rel.append((0, m + 1, idx_att[int(a[0])]))
-            for s in np.asarray(obj["spatial_relationship"]).reshape(-1).tolist():
-                rel.append((m + 1, 0, idx_spa[int(s)]))
-            for c in np.asarray(obj["contacting_relationship"]).reshape(-1).tolist():
-                rel.append((0, m + 1, idx_con[int(c)]))
-        self.rel.append(np.asarray(rel, dtype=np.int32).reshape(-1, 3))
-        self.cls.append(cls)
-        self.box.append(boxes.astype(np.float32))        # rounded to f32 exactly as :765 does
-        self.rel_off.append(self.rel_off[-1] + len(rel))
-        self.box_off.append(self.box_off[-1] + nb)
+        rel, cls, box, nrel, nbox = self.pack_video([frame_gt], idx_att, idx_spa, idx_con)
+        self.rel.append(rel); self.cls.append(cls); self.box.append(box)
+        self.rel_off.append(self.rel_off[-1] + int(nrel[0]))
+        self.box_off.append(self.box_off[-1] + int(nbox[0]))
 
 
-def recall_match(pair_off, gt: PackedGT, pair_sub, pair_obj, att, spa, con, obj_scores, pred_cls, pred_boxes):
-    """Launch the kernel; returns u32[F,3,3,8] match sets (numpy)."""
+def recall_match(pair_off, gt, pair_sub, pair_obj, att, spa, con, obj_scores, pred_cls, pred_boxes, stats=None):
+    """Launch the kernel; returns u32[F,3,3,8] match sets (numpy).  gt: PackedGT (per-frame lists) or a dict of flat arrays
+    {rel, cls, box, rel_off, box_off}.  All host arrays travel in ONE pinned upload."""
+    from ..plan import pack_upload
     dev = att.device
     F = len(pair_off) - 1
     pmax, gmax, gbmax = _limits()
     po = np.asarray(pair_off, dtype=np.int32)
-    ro, bo = np.asarray(gt.rel_off, dtype=np.int32), np.asarray(gt.box_off, dtype=np.int32)
+    if isinstance(gt, PackedGT):
+        gt = {"rel_off": gt.rel_off, "box_off": gt.box_off,
+              "rel": np.concatenate(gt.rel) if gt.rel else np.zeros((0, 3), np.int32),
+              "cls": np.concatenate(gt.cls) if gt.cls else np.zeros(0, np.int32),
+              "box": np.concatenate(gt.box) if gt.box else np.zeros((0, 4), np.float32)}
+    ro, bo = np.asarray(gt["rel_off"], dtype=np.int32), np.asarray(gt["box_off"], dtype=np.int32)
     if F and (np.diff(po).max(initial=0) > pmax or np.diff(ro).max(initial=0) > gmax or np.diff(bo).max(initial=0) > gbmax):
         raise RuntimeError(f"recall_match: a frame exceeds the kernel limits (pairs<={pmax}, gt relations<={gmax}, gt boxes<={gbmax})")
-    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a, dtype=dt)).to(dev, non_blocking=True)
-    d_po, d_ro, d_bo = t(po, np.int32), t(ro, np.int32), t(bo, np.int32)
-    d_rel = t(np.concatenate(gt.rel) if gt.rel else np.zeros((0, 3)), np.int32)
-    d_cls = t(np.concatenate(gt.cls) if gt.cls else np.zeros(0), np.int32)
-    d_box = t(np.concatenate(gt.box) if gt.box else np.zeros((0, 4)), np.float32)
+    arrays = {"po": po, "ro": ro, "bo": bo, "rel": np.ascontiguousarray(gt["rel"], dtype=np.int32).reshape(-1, 3),
+              "cls": np.ascontiguousarray(gt["cls"], dtype=np.int32), "box": np.ascontiguousarray(gt["box"], dtype=np.float32).reshape(-1, 4)}
+    d = pack_upload(arrays, dev)
     out = torch.empty(F, 3, 3, 8, device=dev, dtype=torch.int32)
-    _C.check(_C.lib().nlv_recall_match(F, _ptr(d_po), _ptr(d_ro), _ptr(d_bo), _ptr(pair_sub), _ptr(pair_obj), _ptr(att),
-                                       _ptr(spa), _ptr(con), _ptr(obj_scores), _ptr(pred_cls), _ptr(pred_boxes), _ptr(d_rel),
-                                       _ptr(d_cls), _ptr(d_box), _ptr(out), _stream()), "recall_match")
-    return out.cpu().numpy().view(np.uint32)
+    ev0 = ev1 = None
+    if stats is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    _C.check(_C.lib().nlv_recall_match(F, _ptr(d["po"]), _ptr(d["ro"]), _ptr(d["bo"]), _ptr(pair_sub), _ptr(pair_obj), _ptr(att),
+                                       _ptr(spa), _ptr(con), _ptr(obj_scores), _ptr(pred_cls), _ptr(pred_boxes), _ptr(d["rel"]),
+                                       _ptr(d["cls"]), _ptr(d["box"]), _ptr(out), _stream()), "recall_match")
+    if stats is not None:
+        ev1.record()
+    res = out.cpu().numpy().view(np.uint32)
+    if stats is not None:
+        stats["kernel_ms"] = ev0.elapsed_time(ev1)
+        stats["h2d_bytes"] = int(sum(a.nbytes for a in arrays.values()))
+        stats["d2h_bytes"] = int(res.nbytes)
+        # algorithmic input of the kernel (SURVEY 8d): scores 3P*26*4... = per pair 26 floats + 2 indices, per box 4+1+1 words, GT arrays
+        P, N = int(pair_sub.shape[0]), int(pred_cls.shape[0])
+        stats["algorithmic_bytes"] = P * (26 * 4 + 8) + N * 24 + stats["h2d_bytes"] + stats["d2h_bytes"]
+    return res
 
 
 def _bits(words: np.ndarray) -> List[int]:
@@ -129,62 +158,95 @@ class SceneGraphEvaluator:
         """One video (the reference signature).  Mutates pred['attention_distribution'] (softmax), as :400 does."""
         self.evaluate_videos([(gt, pred)])
 
-    def evaluate_videos(self, items: Sequence[tuple]):
-        """Any number of (gt, pred) videos in ONE kernel launch; results are appended in input order."""
-        packed = PackedGT()
-        pair_off = [0]
-        subs, objs, atts, spas, cons, oscs, clss, boxs = [], [], [], [], [], [], [], []
-        box_base = 0
-        dev = None
-        for gt, pred in items:
-            pred["attention_distribution"] = nn.functional.softmax(pred["attention_distribution"], dim=1)
-            dev = pred["attention_distribution"].device
-            if dev.type != "cuda":
-                raise RuntimeError("SceneGraphEvaluator (nlvsgg_b200) needs CUDA tensors; there is no CPU fallback")
-            im_idx = pred["im_idx"].detach().cpu().numpy().astype(np.int64)
-            nf = len(gt)
-            cnt = np.bincount(im_idx, minlength=nf) if len(im_idx) else np.zeros(nf, dtype=np.int64)
-            assert len(cnt) == nf and (len(im_idx) == 0 or np.all(np.diff(im_idx) >= 0)), "im_idx must be sorted frame ids"
-            for f in range(nf):
-                packed.add_frame(gt[f], self._ia, self._is, self._ic)
-                pair_off.append(pair_off[-1] + int(cnt[f]))
-            pi = pred["pair_idx"].to(torch.int32) + box_base
-            subs.append(pi[:, 0]); objs.append(pi[:, 1])
-            atts.append(pred["attention_distribution"].float()); spas.append(pred["spatial_distribution"].float())
-            cons.append(pred["contacting_distribution"].float())
-            if self.mode == "predcls":
-                clss.append(pred["labels"].to(torch.int32)); oscs.append(pred["scores"].float())
-            else:
-                clss.append(pred["pred_labels"].to(torch.int32)); oscs.append(pred["pred_scores"].float())
-            boxs.append(pred["boxes"][:, 1:].float())
-            box_base += int(pred["boxes"].shape[0])
-        cat = lambda ts: (ts[0] if len(ts) == 1 else torch.cat(ts, 0)).contiguous()
-        masks = recall_match(pair_off, packed, cat(subs), cat(objs), cat(atts), cat(spas), cat(cons), cat(oscs), cat(clss),
-                             cat(boxs))
-        self._book(masks, packed)
+    def _packed(self, gt):
+        """Flattened ground truth of one video, cached per annotation object (static across epochs)."""
+        cache = self.__dict__.setdefault("_gt_cache", {})
+        hit = cache.get(id(gt))
+        if hit is not None and hit[0] is gt:
+            return hit[1]
+        packed = PackedGT.pack_video(gt, self._ia, self._is, self._ic)
+        if len(cache) > 65536:
+            cache.clear()
+        cache[id(gt)] = (gt, packed)
+        return packed
 
-    def _book(self, masks: np.ndarray, packed: PackedGT):
+    def evaluate_videos(self, items: Sequence[tuple]):
+        """Any number of (gt, pred) videos in ONE kernel launch; results are appended in input order.  One device -> host
+        read for the frame ids of all videos, one pinned upload of all ground truth, one read-back of the match sets."""
+        if len(items) == 0:
+            return
+        preds = [p for _, p in items]
+        dev = preds[0]["attention_distribution"].device
+        if dev.type != "cuda":
+            raise RuntimeError("SceneGraphEvaluator (nlvsgg_b200) needs CUDA tensors; there is no CPU fallback")
+        cat = lambda ts: (ts[0] if len(ts) == 1 else torch.cat(ts, 0)).contiguous()
+        n_pairs = [int(p["pair_idx"].shape[0]) for p in preds]
+        n_boxes = [int(p["boxes"].shape[0]) for p in preds]
+        att = nn.functional.softmax(cat([p["attention_distribution"].float() for p in preds]), dim=1)
+        o = 0
+        for p, n in zip(preds, n_pairs):          # :400 overwrites the caller's tensor with its softmax
+            p["attention_distribution"] = att[o:o + n]
+            o += n
+        im_all = cat([p["im_idx"].reshape(-1) for p in preds]).to(torch.int64).cpu().numpy()
+        packs = [self._packed(gt) for gt, _ in items]
+        nf = np.asarray([len(pk[3]) for pk in packs], dtype=np.int64)
+        # pairs per (video, frame): frame ids are sorted inside a video
+        voff = np.concatenate(([0], np.cumsum(n_pairs)))
+        foff = np.concatenate(([0], np.cumsum(nf)))
+        vid = np.repeat(np.arange(len(items)), n_pairs)
+        if len(im_all):
+            assert np.all(im_all < nf[vid]) and np.all((np.diff(im_all) >= 0) | (np.diff(vid) > 0)), "im_idx must be sorted frame ids"
+        cnt = np.bincount(foff[vid] + im_all, minlength=int(foff[-1])) if len(im_all) else np.zeros(int(foff[-1]), dtype=np.int64)
+        pair_off = np.concatenate(([0], np.cumsum(cnt)))
+        boff = np.concatenate(([0], np.cumsum(n_boxes)))[:-1]
+        pi = cat([p["pair_idx"] for p in preds]).to(torch.int32) + torch.from_numpy(np.repeat(boff, n_pairs).astype(np.int32)).to(dev)[:, None]
+        key_c, key_s = ("labels", "scores") if self.mode == "predcls" else ("pred_labels", "pred_scores")
+        gtd = {"rel": np.concatenate([pk[0] for pk in packs]), "cls": np.concatenate([pk[1] for pk in packs]),
+               "box": np.concatenate([pk[2] for pk in packs]),
+               "rel_off": np.concatenate(([0], np.cumsum(np.concatenate([pk[3] for pk in packs])))),
+               "box_off": np.concatenate(([0], np.cumsum(np.concatenate([pk[4] for pk in packs]))))}
+        stats = {}
+        masks = recall_match(pair_off, gtd, pi[:, 0].contiguous(), pi[:, 1].contiguous(), att, cat([p["spatial_distribution"].float() for p in preds]),
+                             cat([p["contacting_distribution"].float() for p in preds]), cat([p[key_s].float() for p in preds]),
+                             cat([p[key_c].to(torch.int32) for p in preds]), cat([p["boxes"][:, 1:].float() for p in preds]), stats)
+        self.last_kernel_ms, self.last_h2d_bytes = stats["kernel_ms"], stats["h2d_bytes"]
+        self.last_d2h_bytes, self.last_algorithmic_bytes = stats["d2h_bytes"], stats["algorithmic_bytes"]
+        self._book(masks, gtd)
+
+    def _book(self, masks: np.ndarray, gtd):
+        """Integer match sets -> the reference's per-frame floats, in the reference's order (numpy over all frames at once)."""
         m = self.mode
-        for f in range(masks.shape[0]):
-            rel = packed.rel[f]
-            G = rel.shape[0]
-            for pi, key in enumerate(("_recall", "_recall_nogc", "_semi_recall")):
-                for ki, k in enumerate(KS):
-                    n = int(sum(bin(int(w)).count("1") for w in masks[f, pi, ki]))
-                    self.result_dict[m + key][k].append(float(n) / float(G))
-            for pi, key in ((0, "_mean_recall"), (1, "_ng_mean_recall")):     # :69-87 / :146-165
-                for ki, k in enumerate(KS):
-                    hit = [0] * self.num_rel
-                    cnt = [0] * self.num_rel
-                    for g in range(G):
-                        cnt[int(rel[g, 2])] += 1
-                        cnt[0] += 1
-                    for g in _bits(masks[f, pi, ki]):
-                        hit[int(rel[g, 2])] += 1
-                        hit[0] += 1
-                    for n in range(self.num_rel):
-                        if cnt[n] > 0:
-                            self.result_dict[m + key + "_collect"][k][n].append(float(hit[n] / cnt[n]))
+        if isinstance(gtd, PackedGT):
+            gtd = {"rel": np.concatenate(gtd.rel) if gtd.rel else np.zeros((0, 3), np.int32), "rel_off": np.asarray(gtd.rel_off)}
+        F = masks.shape[0]
+        rel_off = np.asarray(gtd["rel_off"], dtype=np.int64)
+        G = np.diff(rel_off)                                              # GT relations per frame
+        pred_of = gtd["rel"][:, 2].astype(np.int64)                       # predicate of every GT relation
+        frame_of = np.repeat(np.arange(F), G)
+        local = np.arange(len(pred_of)) - rel_off[frame_of]               # index of the relation inside its frame
+        bits = np.unpackbits(masks.reshape(F, 3, 3, 8).view(np.uint8), axis=-1, bitorder="little").reshape(F, 3, 3, 256)
+        pop = bits.sum(-1).astype(np.float64)                             # |matched set| per (frame, protocol, K)
+        Gf = G.astype(np.float64)
+        for pi, key in enumerate(("_recall", "_recall_nogc", "_semi_recall")):
+            for ki, k in enumerate(KS):
+                self.result_dict[m + key][k].extend((pop[:, pi, ki] / Gf).tolist())
+        # mean-recall collectors (:69-87 / :146-165): per frame and predicate n, hits / count for predicates present in the
+        # frame; index 0 additionally counts every relation (the reference's `[0] += 1` alongside `[predicate] += 1`)
+        cnt = np.zeros((F, self.num_rel), dtype=np.int64)
+        np.add.at(cnt, (frame_of, pred_of), 1)
+        cnt[:, 0] += G
+        for pi, key in ((0, "_mean_recall"), (1, "_ng_mean_recall")):
+            for ki, k in enumerate(KS):
+                matched = bits[frame_of, pi, ki, local].astype(np.int64)
+                hit = np.zeros((F, self.num_rel), dtype=np.int64)
+                np.add.at(hit, (frame_of, pred_of), matched)
+                hit[:, 0] += hit.sum(1) - 0                                # every hit also counts for index 0
+                ratio = hit.astype(np.float64) / np.maximum(cnt, 1).astype(np.float64)
+                coll = self.result_dict[m + key + "_collect"][k]
+                for n in range(self.num_rel):
+                    sel = cnt[:, n] > 0
+                    if sel.any():
+                        coll[n].extend(ratio[sel, n].tolist())
 
     def calculate_mean_recall(self):
         for t in ("_mean_recall", "_ng_mean_recall"):      # :89-109 / :167-187

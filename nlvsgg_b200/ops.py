@@ -33,7 +33,7 @@ def _need_cuda(*ts):
 
 def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_major: int = MAJOR_K, b_major: int = MAJOR_K,
          bias: torch.Tensor | None = None, residual: torch.Tensor | None = None, relu: bool = False,
-         force_simt: bool = False, gate: torch.Tensor | None = None) -> torch.Tensor:
+         force_simt: bool = False, gate: torch.Tensor | None = None, drop=None, gate_scale: float = 1.0) -> torch.Tensor:
     """out[m,n] = act(sum_k A(m,k) B(n,k) + bias[n]) + residual[m,n].
 
     a: [m,k] (K-major) or [k,m] (MN-major); b: [n,k] or [k,n]; rows may be strided (stride(1) == 1)."""
@@ -66,6 +66,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, out: torch.Tensor, *, a_major: int = 
         g.gate, g.ldg, g.gate_dtype = gate.data_ptr(), gate.stride(0), _dt(gate)
     else:
         g.gate, g.ldg, g.gate_dtype = None, 0, 0
+    g.gate_scale = gate_scale
+    if drop is not None:
+        g.drop = drop
     if PROFILE is None:
         _C.check(_C.lib().nlv_gemm(ctypes.byref(g), _stream()), "gemm")
         return out
@@ -275,15 +278,35 @@ def layernorm_fwd(x, w, b, eps=1e-5, y2_dtype=None, want_y=True):
     return y, y2, mean, rstd
 
 
-def layernorm_bwd(dy, x, mean, rstd, w, dx2_dtype=None):
+def layernorm_bwd(dy, x, mean, rstd, w, dx2_dtype=None, drop=None):
     rows, cols = x.shape
     dx = torch.empty_like(x)
     dx2 = torch.empty(rows, cols, device=x.device, dtype=dx2_dtype) if dx2_dtype is not None else None
     dw = torch.zeros(cols, device=x.device, dtype=torch.float32)
     db = torch.zeros(cols, device=x.device, dtype=torch.float32)
-    _call("nlv_layernorm_bwd", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _LL(rows), cols, _ptr(dx), _ptr(dx2),
-          _dt(dx2) if dx2 is not None else 0, _ptr(dw), _ptr(db))
+    _call("nlv_layernorm_bwd_drop", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _LL(rows), cols, _ptr(dx), _ptr(dx2),
+          _dt(dx2) if dx2 is not None else 0, _ptr(dw), _ptr(db), ctypes.byref(drop) if drop is not None else None)
     return dx, dx2, dw, db
+
+
+def dropout_apply(src, drop, out_dtype=None, out=None):
+    rows, cols = src.shape
+    if out is None:
+        out = torch.empty(rows, cols, device=src.device, dtype=out_dtype or src.dtype)
+    _call("nlv_dropout_apply", _ptr(src), _dt(src), src.stride(0), _ptr(out), _dt(out), out.stride(0), _LL(rows), cols, ctypes.byref(drop))
+    return out
+
+
+def dropout_mask(rows, cols, drop, device="cuda"):
+    out = torch.empty(rows, cols, device=device, dtype=torch.uint8)
+    _call("nlv_dropout_mask", _LL(rows), cols, ctypes.byref(drop), _ptr(out))
+    return out
+
+
+def dropout_mask_attn(rows, heads, nkeys, drop, device="cuda"):
+    out = torch.empty(rows, heads, nkeys, device=device, dtype=torch.uint8)
+    _call("nlv_dropout_mask_attn", _LL(rows), heads, nkeys, ctypes.byref(drop), _ptr(out))
+    return out
 
 
 def bn_stats(x, seg, nseg, c, momentum, running_mean, running_var):
@@ -321,22 +344,23 @@ def bn_bwd(dy, x, yout, seg, row_seg, nseg, mean, var, w, use_batch_stats, dx_dt
     return dx, dw, db
 
 
-def attn_fwd(q, k, v, hd, heads, work, n_work, out_dtype, want_lse=True):
+def attn_fwd(q, k, v, hd, heads, work, n_work, out_dtype, want_lse=True, drop=None):
     rows = q.shape[0]
     o = torch.empty(rows, hd * heads, device=q.device, dtype=out_dtype)
     lse = torch.empty(rows * heads, device=q.device, dtype=torch.float32) if want_lse else None
-    _call("nlv_attn_fwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
-          _F(1.0 / (hd ** 0.5)), _ptr(work), n_work, _ptr(o), o.stride(0), _dt(o), _ptr(lse))
+    _call("nlv_attn_fwd_drop", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
+          _F(1.0 / (hd ** 0.5)), _ptr(work), n_work, _ptr(o), o.stride(0), _dt(o), _ptr(lse), ctypes.byref(drop) if drop is not None else None)
     return o, lse
 
 
-def attn_bwd(q, k, v, o, dout, lse, hd, heads, work, n_work, dq, dk, dv):
+def attn_bwd(q, k, v, o, dout, lse, hd, heads, work, n_work, dq, dk, dv, drop=None):
     rows = q.shape[0]
     delta = torch.empty(rows * heads, device=q.device, dtype=torch.float32)
     assert dq.dtype == dk.dtype == dv.dtype
-    _call("nlv_attn_bwd", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
+    _call("nlv_attn_bwd_drop", _ptr(q), q.stride(0), _ptr(k), k.stride(0), _ptr(v), v.stride(0), _dt(q), hd, heads,
           _F(1.0 / (hd ** 0.5)), _ptr(work), n_work, _ptr(o), o.stride(0), _dt(o), _ptr(dout), dout.stride(0), _dt(dout),
-          _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _dt(dq))
+          _ptr(lse), _ptr(delta), _ptr(dq), dq.stride(0), _ptr(dk), dk.stride(0), _ptr(dv), dv.stride(0), _dt(dq),
+          ctypes.byref(drop) if drop is not None else None)
 
 
 def heads_activation(logits):

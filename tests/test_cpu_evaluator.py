@@ -58,3 +58,61 @@ def test_perfect_predictions_give_full_recall():
     ev.evaluate_scene_graph(gt, pred)
     assert all(v == 1.0 for v in ev.result_dict["predcls_recall_nogc"][50])
     assert all(v == 1.0 for v in ev.result_dict["predcls_semi_recall"][50])
+
+
+def _book_loop(ev, masks, rels_per_frame):
+    """The per-frame / per-bit bookkeeping of lib/evaluation_recall.py:203-204,69-87,146-165 written as plain loops."""
+    from nlvsgg_b200.lib.evaluation_recall import KS, _bits
+    m = ev.mode
+    for f in range(masks.shape[0]):
+        rel = rels_per_frame[f]
+        G = rel.shape[0]
+        for pi, key in enumerate(("_recall", "_recall_nogc", "_semi_recall")):
+            for ki, k in enumerate(KS):
+                n = int(sum(bin(int(w)).count("1") for w in masks[f, pi, ki]))
+                ev.result_dict[m + key][k].append(float(n) / float(G))
+        for pi, key in ((0, "_mean_recall"), (1, "_ng_mean_recall")):
+            for ki, k in enumerate(KS):
+                hit, cnt = [0] * ev.num_rel, [0] * ev.num_rel
+                for g in range(G):
+                    cnt[int(rel[g, 2])] += 1
+                    cnt[0] += 1
+                for g in _bits(masks[f, pi, ki]):
+                    hit[int(rel[g, 2])] += 1
+                    hit[0] += 1
+                for n in range(ev.num_rel):
+                    if cnt[n] > 0:
+                        ev.result_dict[m + key + "_collect"][k][n].append(float(hit[n] / cnt[n]))
+
+
+def test_vectorised_booking_equals_the_reference_loops():
+    """The numpy bookkeeping of the CUDA evaluator's host side (no GPU needed: it consumes integer match sets)."""
+    import numpy as np
+    from nlvsgg_b200.lib.evaluation_recall import PackedGT, SceneGraphEvaluator
+    mk = lambda: SceneGraphEvaluator("sgdet", synth.AG_OBJECT_CLASSES, synth.AG_RELATIONS, synth.AG_ATTENTION, synth.AG_SPATIAL,
+                                     synth.AG_CONTACTING, iou_threshold=0.5, constraint="with")
+    a, b = mk(), mk()
+    a.register_container(); b.register_container()
+    _, gt = synth.synth_video(77, 9, 6, "sgdet", draw_fn=None, union_feat=False)
+    rel, cls, box, nrel, nbox = PackedGT.pack_video(gt, a._ia, a._is, a._ic)
+    # pack_video == the oracle's per-frame packing
+    names = synth.AG_RELATIONS
+    o = 0
+    for f, fg in enumerate(gt):
+        gb, gc, gr = oe.build_frame_gt(fg, synth.AG_ATTENTION, synth.AG_SPATIAL, synth.AG_CONTACTING, names)
+        assert np.array_equal(rel[o:o + len(gr)], gr.astype(np.int32)) and nrel[f] == len(gr) and nbox[f] == len(gc)
+        o += len(gr)
+    rng = np.random.default_rng(3)
+    F = len(gt)
+    rel_off = np.concatenate(([0], np.cumsum(nrel)))
+    masks = np.zeros((F, 3, 3, 8), dtype=np.uint32)
+    for f in range(F):
+        for pi in range(3):
+            for ki in range(3):
+                sel = rng.random(int(nrel[f])) < 0.4
+                for g in np.nonzero(sel)[0]:
+                    masks[f, pi, ki, g // 32] |= np.uint32(1) << np.uint32(g % 32)
+    a._book(masks, {"rel": rel, "rel_off": rel_off})
+    _book_loop(b, masks, [rel[rel_off[f]:rel_off[f + 1]] for f in range(F)])
+    a.calculate_mean_recall(); b.calculate_mean_recall()
+    assert a.result_dict == b.result_dict
