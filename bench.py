@@ -90,17 +90,40 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        # NVML in-process (initialised here, before the timed region): a query is microseconds and takes no driver-wide lock,
+        # whereas forking nvidia-smi every 100 ms showed up as multi-millisecond stalls of the launching thread
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _nvml_row(self):
+        n, h = self.nvml, self.handle
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") else \
+            n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)), str(n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)),
+                "%.1f" % (n.nvmlDeviceGetPowerUsage(h) / 1e3), act(0x8), act(0x40), act(0x20), act(0x4)]
 
     def run(self):
         while not self.stop_flag:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.rows.append([x.strip() for x in o.split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self._nvml_row())
+                else:
+                    o = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5).stdout.strip()
+                    if o:
+                        self.rows.append([x.strip() for x in o.split(",")])
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(0.05 if self.nvml is not None else 0.1)
 
     def summary(self):
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
@@ -538,14 +561,19 @@ def main():
 
     def e2e_loop(hb):
         """every step copies its own inputs from pinned host memory; the copy for step i+1 is issued on a side stream before step i
-        computes, so transfers and compute overlap in steady state; the loss is read back every step"""
+        computes, so transfers and compute overlap in steady state; every step's loss is copied back to the host behind the step
+        and read there one step later (while the next step runs), the last one before the closing event"""
         trainer.step_from_host(hb).item()
         barrier()
         ev0.record()
         nxt = trainer.prefetch(hb)
+        ticket = None
         for i in range(a.steps):
             loss_t, nxt = trainer.step_pipelined(nxt, hb if i + 1 < a.steps else None)
-            lv = loss_t.item()
+            if ticket is not None:
+                lv = trainer.loss_value(ticket)      # step i-1's loss (its own D2H copy), read while step i runs
+            ticket = trainer.last_ticket
+        lv = trainer.loss_value(ticket)
         ev1.record()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1) / a.steps], device=dev)

@@ -255,6 +255,23 @@ int nlv_nms(const float* dets, const long long* order, int n, float thr, int str
 int nlv_track_cost(const float* det_box_xywh, const float* trk_box_xywh, const float* det_feat, const float* trk_feat, int feat_dim,
                    const float* det_dist, const float* trk_dist, int dist_dim, int n_det, int n_trk, float w_class, float w_feat,
                    float w_bbox, float w_giou, float* cost, float* cost_dist, float* cost_feat, void* stream);
+/* scipy.optimize.linear_sum_assignment(cost) of lib/matcher.py:147-149 on the device (one warp, float64 duals, the same
+ * shortest-augmenting-path algorithm and tie rules -> identical assignments): match_of_row[i] = column assigned to row i
+ * or -1; at most 1024 rows / columns */
+int nlv_lsap(const float* cost, int n_rows, int n_cols, int ld, int* match_of_row, void* stream);
+/* lib/track.py:127-262 get_sequence(task="sgcls") for a batch of videos in ONE launch (one CTA per video): per key frame the
+ * matcher cost (lib/matcher.py:124-145), the assignment, the tau = 0.5 accept rule, cluster / track bookkeeping in the
+ * reference's order and the 50-frame track expiry.  boxes f32[N,5] (frame, x1, y1, x2, y2), cls = argmax of the
+ * distribution; det_off / frame_off int[V+1]; frame_start: per video T+1 offsets relative to its first detection
+ * (concatenated); frame_key: frame number per key frame; cost_off[v]: offset of video v in a cost plane of cost_elems
+ * (>= max detections per frame x detections of the video).  Outputs: cluster_of_det int[N] (cluster ids in creation
+ * order), n_clusters int[V], status int[V] (1: a frame exceeded the 1024-wide assignment state). */
+long long nlv_track_sequence_workspace(long long n_det_total, int feat_dim, int n_cls, long long cost_elems);
+int nlv_track_sequence(const float* boxes, const float* feats, int feat_dim, const int* cls, int n_cls, const int* det_off,
+                       const int* frame_off, const int* frame_start, const int* frame_key, int n_videos, long long n_det_total,
+                       int max_det_per_frame, float img_w, float img_h, float w_class, float w_feat, float w_bbox, float w_giou,
+                       int max_gap, const long long* cost_off, long long cost_elems, void* workspace, int* cluster_of_det,
+                       int* n_clusters, int* status, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Small multi-segment helpers used by the model sequencer

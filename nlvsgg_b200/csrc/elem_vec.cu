@@ -229,11 +229,13 @@ im2col_mask_pair_kernel(const float* __restrict__ m, __nv_bfloat16* __restrict__
 }
 
 // column sums with 8 channels per thread: block (C8x, 256/C8x) ; grid (ceil(C8/bx), row splits).
-// NC = 1 or 2 row classes accumulated in ONE pass (the decoder's per-slot sums); four rows in flight per thread so that
-// enough bytes are outstanding per SM to cover the DRAM latency (the loop is a pure stream: ~40 KB in flight per SM needed).
-template <int NC>
+// NC = 1 or 2 row classes accumulated in ONE pass (the decoder's per-slot sums).  BF = the input is bf16, known at compile
+// time: the U rows a thread has in flight are held as RAW 16 / 32-byte registers and unpacked only after all U loads were
+// issued (with a run-time dtype branch around load + unpack the compiler serialised the bf16 loads: one in flight per thread,
+// ~30% of the HBM rate).  U x 256 threads x 16-32 B x 4 blocks = 64-128 KB outstanding per SM.
+template <int NC, bool BF>
 __global__ void __launch_bounds__(256)
-colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, long long rows, int C8,
+colsum_v8_kernel(const void* __restrict__ x, int ld, long long rows, int C8,
                  const int* __restrict__ row_class, float* __restrict__ out, int cols) {
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (rows + gridDim.y - 1) / gridDim.y;
@@ -243,28 +245,44 @@ colsum_v8_kernel(const void* __restrict__ x, int xdt, int ld, long long rows, in
   for (int c = 0; c < NC; ++c)
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[c][q] = 0.f;
-  constexpr int U = 4;
+  constexpr int U = BF ? 8 : 4;
   if (c8 < C8) {
+    const char* base = reinterpret_cast<const char*>(x) + (size_t)c8 * (BF ? 16 : 32);
+    const size_t row_bytes = (size_t)ld * (BF ? 2 : 4);
     for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
-      V8 v[U];
+      uint4 ra[U], rb[U];
       int cl[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long rr = r + (long long)u * blockDim.y;
         cl[u] = -1;
+        ra[u] = make_uint4(0u, 0u, 0u, 0u);
+        rb[u] = ra[u];
         if (rr < r1) {
-          v[u] = ld8(x, xdt, (size_t)rr * ld + (size_t)c8 * 8);
-          cl[u] = (NC > 1 && row_class != nullptr) ? row_class[rr] : 0;
+          const uint4* q = reinterpret_cast<const uint4*>(base + (size_t)rr * row_bytes);
+          ra[u] = __ldg(q);
+          if (!BF) rb[u] = __ldg(q + 1);
+          cl[u] = (NC > 1 && row_class != nullptr) ? __ldg(row_class + rr) : 0;
         }
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u)
+      for (int u = 0; u < U; ++u) {
+        float f[8];
+        if (BF) {
+          const uint32_t w[4] = {ra[u].x, ra[u].y, ra[u].z, ra[u].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) { f[2 * q] = __uint_as_float(w[q] << 16); f[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u); }
+        } else {
+          f[0] = __uint_as_float(ra[u].x); f[1] = __uint_as_float(ra[u].y); f[2] = __uint_as_float(ra[u].z); f[3] = __uint_as_float(ra[u].w);
+          f[4] = __uint_as_float(rb[u].x); f[5] = __uint_as_float(rb[u].y); f[6] = __uint_as_float(rb[u].z); f[7] = __uint_as_float(rb[u].w);
+        }
 #pragma unroll
         for (int c = 0; c < NC; ++c)
           if (cl[u] == c) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) acc[c][q] += v[u].v[q];
+            for (int q = 0; q < 8; ++q) acc[c][q] += f[q];
           }
+      }
     }
   }
   // reduce over threadIdx.y in shared memory, then one atomic per column per block
@@ -415,8 +433,14 @@ int launch_colsum_v8(const void* x, int xdt, int ld, long long rows, int cols, c
   if (splits < 1) splits = 1;
   if (splits > 65535) splits = 65535;
   dim3 grid(gx, (unsigned)splits), block(bx, by);
-  if (n_class == 1 || row_class == nullptr) colsum_v8_kernel<1><<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, nullptr, out, cols);
-  else if (n_class == 2) colsum_v8_kernel<2><<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, row_class, out, cols);
+  const bool bf = xdt == NLV_BF16;
+  if (n_class == 1 || row_class == nullptr) {
+    if (bf) colsum_v8_kernel<1, true><<<grid, block, 0, s>>>(x, ld, rows, C8, nullptr, out, cols);
+    else colsum_v8_kernel<1, false><<<grid, block, 0, s>>>(x, ld, rows, C8, nullptr, out, cols);
+  } else if (n_class == 2) {
+    if (bf) colsum_v8_kernel<2, true><<<grid, block, 0, s>>>(x, ld, rows, C8, row_class, out, cols);
+    else colsum_v8_kernel<2, false><<<grid, block, 0, s>>>(x, ld, rows, C8, row_class, out, cols);
+  }
   else colsum_v8_multi_kernel<<<grid, block, 0, s>>>(x, xdt, ld, rows, C8, row_class, n_class, out, cols);
   NLV_CHECK_LAUNCH();
   return NLV_OK;

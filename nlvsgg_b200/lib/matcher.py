@@ -1,9 +1,9 @@
-"""Drop-in for lib/matcher.py:HungarianMatcher (:81-150): the four cost terms are fused in one kernel
-(``nlv_track_cost``); the linear-sum-assignment stays on the host (scipy), as in the reference (:147-149)."""
+"""Drop-in for lib/matcher.py:HungarianMatcher (:81-150), entirely on the device: the four cost terms are one kernel
+(``nlv_track_cost``) and the linear-sum assignment the reference hands to scipy on the host (:147-149) is ``nlv_lsap`` (one
+warp, the same shortest-augmenting-path algorithm with float64 duals and scipy's tie rules, so assignments are identical)."""
 import ctypes
 
 import torch
-from scipy.optimize import linear_sum_assignment
 from torch import nn
 
 from .. import _C
@@ -27,6 +27,20 @@ def track_cost(out_boxes, tgt_boxes, out_feat, tgt_feat, out_dist, tgt_dist, w_c
     return C, cd, cf
 
 
+def linear_sum_assignment(cost: torch.Tensor):
+    """scipy.optimize.linear_sum_assignment for a CUDA float matrix -> (row_ind, col_ind) int64 tensors on the device,
+    rows ascending (scipy's output order)."""
+    if cost.device.type != "cuda":
+        raise RuntimeError("linear_sum_assignment (nlvsgg_b200) runs on CUDA only; there is no CPU fallback")
+    c = cost.contiguous().float()
+    n, m = c.shape
+    match = torch.full((n,), -1, dtype=torch.int32, device=c.device)
+    if n and m:
+        _C.check(_C.lib().nlv_lsap(_ptr(c), n, m, m, _ptr(match), _stream()), "lsap")
+    rows = torch.nonzero(match >= 0)[:, 0]
+    return rows, match[rows].long()
+
+
 class HungarianMatcher(nn.Module):
     def __init__(self, cost_class: float = 1, cost_feature: float = 1, cost_bbox: float = 1, cost_giou: float = 1):
         super().__init__()
@@ -35,8 +49,9 @@ class HungarianMatcher(nn.Module):
 
     @torch.no_grad()
     def forward(self, outputs, targets):
-        """outputs/targets: {"boxes": xywh (normalised), "features": [n,2048], "dists": [n,C]} (matcher.py:124-149)."""
+        """outputs/targets: {"boxes": xywh (normalised), "features": [n,2048], "dists": [n,C]} (matcher.py:124-149).
+        Returns (row_ind, col_ind) as numpy arrays like the reference, and the two cost vectors of the matched pairs."""
         C, cd, cf = track_cost(outputs["boxes"], targets["boxes"], outputs["features"], targets["features"], outputs["dists"],
                                targets["dists"], self.cost_class, self.cost_feature, self.cost_bbox, self.cost_giou)
-        row_ind, col_ind = linear_sum_assignment(C.cpu())
-        return row_ind, col_ind, cd[row_ind, col_ind].cpu(), cf[row_ind, col_ind].cpu()
+        row_ind, col_ind = linear_sum_assignment(C)
+        return row_ind.cpu().numpy(), col_ind.cpu().numpy(), cd[row_ind, col_ind].cpu(), cf[row_ind, col_ind].cpu()

@@ -80,6 +80,11 @@ class Trainer:
         from .plan import Stager
         self.stager = Stager(dev)
         self._loss_ring, self._loss_i = torch.zeros(8, device=dev, dtype=F32), 0
+        # every step's loss is also copied to pinned host memory right behind the kernel that produced it (stream order), so
+        # a training loop can read step i's value while step i+1 is already enqueued: `loss_value(ticket)`
+        self._loss_host = torch.zeros(8, dtype=F32).pin_memory() if dev.type == "cuda" else torch.zeros(8, dtype=F32)
+        self._loss_ev = [None] * 8
+        self.last_ticket = None
 
     def _install_mirror(self):
         """bf16 operand mirror of the flat parameter buffer (rewritten by the AdamW kernel): the GEMM weights are used from
@@ -109,7 +114,20 @@ class Trainer:
         slot = self._loss_ring[self._loss_i % 8:self._loss_i % 8 + 1]
         self._loss_i += 1
         ops.convert(out["loss"].view(1, 1), F32, out=slot.view(1, 1))
+        j = (self._loss_i - 1) % 8
+        self._loss_host[j:j + 1].copy_(slot, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        self._loss_ev[j] = ev
+        self.last_ticket = (j, ev)
         return slot, out
+
+    def loss_value(self, ticket=None) -> float:
+        """Host value of a step's loss (ticket = `last_ticket` taken right after that step was enqueued).  Waits only for
+        that step's device-to-host copy, not for work enqueued after it."""
+        j, ev = ticket if ticket is not None else self.last_ticket
+        ev.synchronize()
+        return float(self._loss_host[j])
 
     def optimizer_step(self):
         lib = _C.lib()

@@ -41,3 +41,65 @@ def matcher_cost(out, tgt, w_class=0.5, w_feat=1.0, w_bbox=1.0, w_giou=0.5):
     cb = torch.cdist(ob, tb, p=1)
     cg = -giou(cxcywh_to_xyxy(ob), cxcywh_to_xyxy(tb))
     return w_class * cd + w_feat * cf + w_bbox * cb + w_giou * cg, cd, cf
+
+
+def lsap(cost):
+    """TEST INFRASTRUCTURE.  Restatement of scipy.optimize.linear_sum_assignment (SciPy 1.18, the rectangular shortest
+    augmenting path solver of Crouse 2016 that lib/matcher.py:147-149 calls): float64 duals, the problem transposed when
+    it has more rows than columns, and the column choice rule (lowest reduced cost; an equal cost replaces the choice only
+    when that column is unassigned) with the swap-remove `remaining` list.  csrc/track.cu:lsap_warp follows this line by
+    line; tests/test_cpu_tracking.py pins it against scipy itself, ties included.  -> (row_ind, col_ind)."""
+    import numpy as np
+    c = np.asarray(cost, dtype=np.float64)
+    tr = c.shape[1] < c.shape[0]
+    if tr:
+        c = c.T
+    nr, nc = c.shape
+    u, v = np.zeros(nr), np.zeros(nc)
+    col4row, row4col = -np.ones(nr, dtype=np.int64), -np.ones(nc, dtype=np.int64)
+    path = -np.ones(nc, dtype=np.int64)
+    for cur in range(nr):
+        remaining = [nc - it - 1 for it in range(nc)]
+        SR, SC = np.zeros(nr, bool), np.zeros(nc, bool)
+        spc = np.full(nc, np.inf)
+        min_val, i, sink = 0.0, cur, -1
+        while sink == -1:
+            index, lowest = -1, np.inf
+            SR[i] = True
+            for it, j in enumerate(remaining):
+                r = min_val + c[i, j] - u[i] - v[j]
+                if r < spc[j]:
+                    path[j] = i
+                    spc[j] = r
+                if spc[j] < lowest or (spc[j] == lowest and row4col[j] == -1):
+                    lowest = spc[j]
+                    index = it
+            min_val = lowest
+            if min_val == np.inf:
+                raise ValueError("cost matrix is infeasible")
+            j = remaining[index]
+            if row4col[j] == -1:
+                sink = j
+            else:
+                i = row4col[j]
+            SC[j] = True
+            remaining[index] = remaining[-1]
+            remaining.pop()
+        u[cur] += min_val
+        for r_ in range(nr):
+            if SR[r_] and r_ != cur:
+                u[r_] += min_val - spc[col4row[r_]]
+        for j in range(nc):
+            if SC[j]:
+                v[j] -= min_val - spc[j]
+        j = sink
+        while True:
+            i = path[j]
+            row4col[j] = i
+            col4row[i], j = j, col4row[i]
+            if i == cur:
+                break
+    if tr:
+        order = np.argsort(col4row, kind="stable")
+        return col4row[order], order
+    return np.arange(nr), col4row

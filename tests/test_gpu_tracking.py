@@ -44,6 +44,44 @@ def test_get_sequence_matches_reference(cuda_lib, name, task):
     assert got == case["indices"][task]                         # track assignment: bit-exact
 
 
+def test_device_lsap_is_scipy(cuda_lib):
+    """nlv_lsap vs scipy.optimize.linear_sum_assignment (the call of lib/matcher.py:147-149): identical assignments on
+    rectangular problems either way round, including integer-valued costs full of ties (the tie rules are scipy's)."""
+    from scipy.optimize import linear_sum_assignment as scipy_lsa
+    from nlvsgg_b200.lib.matcher import linear_sum_assignment
+    rng = np.random.default_rng(11)
+    shapes = [(1, 1), (1, 7), (7, 1), (5, 5), (20, 40), (40, 20), (33, 33), (64, 97), (130, 70), (3, 300), (257, 256)]
+    for n, m in shapes:
+        for kind in ("float", "ties", "coarse"):
+            if kind == "float":
+                c = rng.standard_normal((n, m)).astype(np.float32)
+            elif kind == "ties":
+                c = rng.integers(0, 4, (n, m)).astype(np.float32)
+            else:
+                c = (rng.integers(0, 50, (n, m)) / 8.0).astype(np.float32)
+            want_r, want_c = scipy_lsa(c)
+            got_r, got_c = linear_sum_assignment(torch.from_numpy(c).cuda())
+            assert got_r.cpu().tolist() == want_r.tolist() and got_c.cpu().tolist() == want_c.tolist(), (n, m, kind)
+    r, c = linear_sum_assignment(torch.zeros(4, 0).cuda())
+    assert r.numel() == 0 and c.numel() == 0
+
+
+def test_track_videos_batch_equals_single(cuda_lib):
+    """Several videos in one launch (one CTA each) give the clusters of the per-video calls."""
+    from nlvsgg_b200.lib.track import frame_number, track_videos
+    from oracle.make_golden_track import track_entry
+    vids = []
+    for name in ("track_a", "track_gap", "track_b"):
+        case = G.load_case(name)
+        entry, gt = track_entry(case["seed"], case["frames"], case["k"], case["stride"])
+        vids.append((entry["boxes"].cuda(), entry["features"].cuda(), entry["distribution"].cuda(), [frame_number(a[0]["frame"]) for a in gt]))
+    w = (0.5, 1.0, 1.0, 0.5)
+    single = [track_videos([b], [f], [d], [k], (480, 270), w)[0] for b, f, d, k in vids]
+    batch = track_videos([v[0] for v in vids], [v[1] for v in vids], [v[2] for v in vids], [v[3] for v in vids], (480, 270), w)
+    for a, b in zip(single, batch):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("n,thr", [(1, 0.5), (64, 0.4), (200, 0.6), (513, 0.3)])
 def test_nms_matches_oracle(cuda_lib, n, thr):
     from nlvsgg_b200.lib.roi_layers import nms

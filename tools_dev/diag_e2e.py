@@ -4,7 +4,7 @@ import torch, bench
 from nlvsgg_b200 import model as M, shapes, synth
 from nlvsgg_b200.trainer import Trainer
 class A: pass
-a = A(); a.videos = 64; a.frames = 30; a.boxes = 7; a.arch = "sttran"; a.precision = "bf16"
+a = A(); a.videos = 64; a.frames = 30; a.boxes = 7; a.arch = "sttran"; a.precision = "bf16"; a.config = "c2"
 dev = torch.device("cuda")
 tr = Trainer({k: v.to(dev) for k, v in synth.make_state_dict(shapes.sttran_template(), 0).items()}, "sgdet", "sttran", "bf16", device=dev)
 host = M.collate(bench.make_videos(a, 0, a.videos), "sgdet", pin=True)

@@ -1,0 +1,48 @@
+"""Dev: packed-input end-to-end step: copy alone, compute alone, both, pipelined."""
+import os, sys, time, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, bench
+from nlvsgg_b200 import featfile, model as M, shapes, synth
+from nlvsgg_b200.trainer import Trainer
+class A: pass
+a = A(); a.videos = 64; a.frames = 30; a.boxes = 7; a.arch = "sttran"; a.precision = "bf16"; a.config = "c2"
+dev = torch.device("cuda")
+tr = Trainer({k: v.to(dev) for k, v in synth.make_state_dict(shapes.sttran_template(), 0).items()}, "sgdet", "sttran", "bf16", device=dev, dropout=0.1)
+entries = bench.make_videos(a, 0, a.videos, with_gt=True)
+tmpdir = tempfile.mkdtemp(prefix="nlv_diag_", dir="/dev/shm")
+host = featfile.Loader(pin=True, depth=1).load(featfile.write_videos(tmpdir, entries))
+for k in M.TENSOR_KEYS:
+    t = getattr(host, k, None)
+    if t is not None: print(k, tuple(t.shape), t.dtype, "pinned" if t.is_pinned() else "PAGEABLE", t.numel() * t.element_size())
+print("bytes", M.input_bytes(host))
+def t(fn, n=5):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    torch.cuda.synchronize(); return (time.perf_counter() - t0) / n * 1e3
+res = M.upload(host, dev, rasterise=False)
+print("H2D only (main stream): %.1f ms" % t(lambda: M.upload(host, dev, rasterise=False)))
+s = torch.cuda.Stream()
+def side():
+    with torch.cuda.stream(s): M.upload(host, dev, rasterise=False)
+print("H2D only (side stream): %.1f ms" % t(side))
+def comp():
+    b = M.Batch(); b.__dict__.update(res.__dict__); tr.step(b)
+for _ in range(3): comp()
+print("compute only: %.1f ms" % t(comp))
+def both():
+    with torch.cuda.stream(s): M.upload(host, dev, rasterise=False)
+    comp()
+print("H2D(side) + compute concurrently: %.1f ms" % t(both))
+def pipe(n):
+    nxt = tr.prefetch(host)
+    for i in range(n):
+        t0 = time.perf_counter()
+        l, nxt = tr.step_pipelined(nxt, host if i + 1 < n else None)
+        t1 = time.perf_counter()
+        l.item()
+        t2 = time.perf_counter()
+        print("   step %d: host enqueue %.2f ms, wait for loss %.2f ms" % (i, 1e3 * (t1 - t0), 1e3 * (t2 - t1)))
+pipe(3)
+torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(8); torch.cuda.synchronize()
+print("pipelined per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
+print("mem allocated %.1f GB reserved %.1f GB" % (torch.cuda.memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9))

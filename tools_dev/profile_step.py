@@ -8,7 +8,7 @@ from nlvsgg_b200.trainer import Trainer
 
 class A: pass
 a = A(); a.videos = int(os.environ.get("VIDEOS", 64)); a.frames = 30; a.boxes = 7; a.arch = os.environ.get("ARCH", "sttran")
-a.precision = os.environ.get("PREC", "bf16")
+a.precision = os.environ.get("PREC", "bf16"); a.config = "c2"
 dev = torch.device("cuda")
 tmpl = shapes.sttran_template() if a.arch == "sttran" else shapes.dsg_template()
 tr = Trainer({k: v.to(dev) for k, v in synth.make_state_dict(tmpl, 0).items()}, "sgdet", a.arch, a.precision, device=dev)
