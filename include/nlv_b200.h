@@ -185,6 +185,13 @@ int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void
                       float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
                       int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                       int dqkv_dtype, const nlv_dropout* drop, void* stream);
+/* forward with the torch-1.10.1 reading of the INT key_padding_mask of lib/transformer_wk.py:154 (the mask value is ADDED to
+ * the logits instead of masking): every segment keeps work[i].w padded keys in its softmax, each with logit
+ * q . kpad * scale + 1 and value vpad, where kpad / vpad (f32[heads*hd]) are the K / V slices of in_proj_bias (a padded row
+ * is all-zero).  kpad = vpad = NULL: identical to nlv_attn_fwd_drop.  Inference only (no backward); SIMT kernels. */
+int nlv_attn_fwd_padkeys(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                         float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, const nlv_dropout* drop,
+                         const float* kpad, const float* vpad, void* stream);
 /* dst = keep(row, col) ? src * scale : 0 (dtype conversion allowed, dst may alias src); and the masks themselves as bytes
  * (tests): matrix sites [rows, cols], attention sites [rows, heads, nkeys] */
 int nlv_dropout_apply(const void* src, int src_dtype, int lds, void* dst, int dst_dtype, int ldd, long long rows, int cols,
@@ -400,6 +407,7 @@ typedef struct nlv_outputs {
 #define NLV_RUN_LOSS 2         /* fused CE / CE / BCE / BCE loss from the batch labels (+ its gradients when NLV_RUN_CTX) */
 #define NLV_RUN_BACKWARD 4     /* (plan only) size the workspace for a backward pass too */
 #define NLV_RUN_ACTIVATIONS 8  /* att / spa / con outputs (lib/sttran.py:404-409) */
+#define NLV_RUN_OBJECT_ONLY 16 /* stop after the object classifier head (obj_logits only): first stage of the sgcls test branch */
 
 /* out[0..3] = sizeof(nlv_model), sizeof(nlv_batch), sizeof(nlv_outputs), sizeof(nlv_gemm_args); returns 4 */
 int nlv_struct_sizes(int* out, int n);

@@ -110,7 +110,7 @@ class Outputs(ctypes.Structure):
     _fields_ = [(n, _vp) for n in ("obj_logits", "logits26", "att", "spa", "con", "loss", "masks", "rel_tokens", "rel_out", "d26", "dobj")]
 
 
-RUN_CTX, RUN_LOSS, RUN_BACKWARD, RUN_ACTIVATIONS = 1, 2, 4, 8
+RUN_CTX, RUN_LOSS, RUN_BACKWARD, RUN_ACTIVATIONS, RUN_OBJECT_ONLY = 1, 2, 4, 8, 16
 ARCH = {"sttran": 0, "dsg": 1}
 MODE = {"predcls": 0, "sgcls": 1, "sgdet": 2}
 PREC = {"bf16": 0, "bf16x3": 1, "fp32": 2}

@@ -89,3 +89,25 @@ def run_module(module: torch.nn.Module, kernels: E.Kernels, entries, mode: str, 
                 if not (mode == "predcls" and n.startswith("object_classifier.")):
                     buf += len(entries)
     return (obj if obj.numel() or mode != "predcls" else None), att, spa, con, batch
+
+
+def run_object_head(module: torch.nn.Module, kernels: E.Kernels, entry) -> torch.Tensor:
+    """Object-classifier logits [N,37] of lib/sttran.py:98-102 alone (inference): the sequencer stops after the head
+    (NLV_RUN_OBJECT_ONLY); the entry needs no pairs yet."""
+    dev = next(module.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("nlvsgg_b200 models run on CUDA only (sm_100a kernels); there is no CPU fallback")
+    e = {k: entry[k] for k in ("boxes", "features", "distribution", "labels", "scores") if k in entry}
+    n = e["boxes"].shape[0]
+    if "labels" not in e:
+        e["labels"] = torch.zeros(n, dtype=torch.int64, device=dev)
+    if "scores" not in e:
+        e["scores"] = torch.zeros(n, device=dev)
+    e["pair_idx"] = torch.zeros(0, 2, dtype=torch.int64, device=dev)
+    e["im_idx"] = torch.zeros(0, device=dev)
+    e["union_feat"] = torch.zeros(0, 2048, 7, 7, device=dev)
+    batch, plan = M.make_batch([e], dev, "sgcls")
+    P = {k: v.detach() for k, v in module_tensors(module).items()}
+    desc = M._desc(kernels, P, "sttran", "sgcls")
+    out, _ = E.run_forward(kernels, desc, P, batch, plan, False, False, fresh_ws=True, object_only=True)
+    return out["distribution"]

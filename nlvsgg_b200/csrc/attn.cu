@@ -28,7 +28,12 @@ struct AttnArgs {
   int ldq, ldk, ldv;
   int hd, heads;
   float scale;
-  const int4* work;        // {segment first row, segment length, first row of this item relative to segment, unused}
+  const int4* work;        // {segment first row, segment length, first row of this item relative to segment, padded keys}
+  // torch-1.10.1 semantics of the int key_padding_mask of lib/transformer_wk.py:154: a frame padded to the longest frame of its
+  // video keeps its work.w padded keys in the softmax with +1 added to their logits; a padded row is all-zero, so its key /
+  // value are the K / V slices of in_proj_bias (fp32 [heads*hd] each).  NULL: true masking (segments are simply unpadded).
+  const float* kpad;
+  const float* vpad;
 };
 
 template <typename T> __device__ __forceinline__ void st2(T* row, int w, float a, float b);
@@ -229,6 +234,32 @@ attn_fwd_kernel(AttnArgs a, TO* __restrict__ o, int ldo, float* __restrict__ lse
       for (int c = 0; c < C; ++c)
 #pragma unroll
         for (int j = 0; j < NW; ++j) { rk[c][j] = nk[c][j]; rv[c][j] = nv[c][j]; }
+    }
+  }
+  if (a.kpad != nullptr && w.w > 0) {
+    // the padded keys: one extra logit q . b_k + 1 per row, counted w.w times, carrying b_v
+    float kr[2 * NW], vr[2 * NW], z[4];
+#pragma unroll
+    for (int j = 0; j < NW; ++j) {
+      const int wd = lane + 32 * j;
+      const bool ok = wd < nwords;
+      const float2 kk = ok ? *reinterpret_cast<const float2*>(a.kpad + col0 + 2 * wd) : make_float2(0.f, 0.f);
+      const float2 vv = ok ? *reinterpret_cast<const float2*>(a.vpad + col0 + 2 * wd) : make_float2(0.f, 0.f);
+      kr[2 * j] = kk.x; kr[2 * j + 1] = kk.y; vr[2 * j] = vv.x; vr[2 * j + 1] = vv.y;
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) z[i] = dot8(q[i], kr);
+    allreduce<4>(z);
+    const float npad = (float)w.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float zi = z[i] + 1.f;
+      const float mx = fmaxf(m[i], zi);
+      const float corr = __expf(m[i] - mx), p = npad * __expf(zi - mx);
+      m[i] = mx;
+      l[i] = l[i] * corr + p;
+#pragma unroll
+      for (int e = 0; e < 2 * NW; ++e) acc[i][e] = fmaf(p, vr[e], acc[i][e] * corr);
     }
   }
 #pragma unroll
@@ -466,17 +497,26 @@ int nlv_attn_fwd(const void* q, int ldq, const void* k, int ldk, const void* v, 
 int nlv_attn_fwd_drop(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
                       float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, const nlv_dropout* drop,
                       void* stream) {
+  return nlv_attn_fwd_padkeys(q, ldq, k, ldk, v, ldv, in_dtype, hd, heads, scale, work, n_work, o, ldo, o_dtype, lse, drop, nullptr, nullptr,
+                              stream);
+}
+
+int nlv_attn_fwd_padkeys(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                         float scale, const void* work, int n_work, void* o, int ldo, int o_dtype, float* lse, const nlv_dropout* drop,
+                         const float* kpad, const float* vpad, void* stream) {
   int rc = check_common(hd, heads, n_work, ((ldq | ldk | ldv | ldo) & 1) == 0);
   if (rc != NLV_OK) return rc;
   if (n_work == 0) return NLV_OK;
   NLV_CHECK_ARG(q && k && v && work && o, "attn_fwd: null pointer");
-  if (in_dtype == NLV_BF16 && o_dtype == NLV_BF16 && use_mma() && attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo))
+  NLV_CHECK_ARG((kpad == nullptr) == (vpad == nullptr), "attn_fwd: kpad and vpad go together");
+  NLV_CHECK_ARG(kpad == nullptr || ((((uintptr_t)kpad | (uintptr_t)vpad) & 7) == 0), "attn_fwd: kpad / vpad must be 8-byte aligned");
+  if (kpad == nullptr && in_dtype == NLV_BF16 && o_dtype == NLV_BF16 && use_mma() && attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo))
     return launch_attn_fwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, o, ldo, lse, drop, STREAM);
   if (drop != nullptr && drop->thr16 != 0u) {
     nlv::set_error("attn_fwd: attention-weight dropout is implemented on the bf16 tensor-core path only");
     return NLV_ERR_UNSUPPORTED;
   }
-  AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+  AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, kpad, vpad};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define FWD(TI, TO) attn_fwd_kernel<TI, TO><<<grid, THREADS, 0, STREAM>>>(a, (TO*)o, ldo, lse)
   if (in_dtype == NLV_BF16 && o_dtype == NLV_BF16) FWD(bf16, bf16);
@@ -515,7 +555,7 @@ int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void
     nlv::set_error("attn_bwd: attention-weight dropout is implemented on the bf16 tensor-core path only");
     return NLV_ERR_UNSUPPORTED;
   }
-  AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work};
+  AttnArgs a{q, k, v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, nullptr, nullptr};
   const dim3 grid((unsigned)n_work * (unsigned)heads);
 #define BWD(TI, TG)                                                                                                         \
   do {                                                                                                                      \

@@ -326,8 +326,13 @@ int nlv_session::encoder_fwd(int layer, const T& x, const T& xop, const int* wor
   const nlv_dropout d0 = site(layer, 0), d1 = site(layer, 1), d2 = site(layer, 2), d3 = site(layer, 3);
   CK(mm(xop, K_, W(LS(layer, NLV_L_INPROJ_W), 3 * D, D), K_, qkv, P(LS(layer, NLV_L_INPROJ_B))));
   g_next_units = 4.0 * (double)Mr * D * qkv.esz(); g_next_dt = qkv.dt;   // algorithmic bytes: Q, K, V in, O out
-  RUN(nlv_attn_fwd_drop(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld, qkv.dt,
-                        HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, &d3, st));
+  // additive_mask (STTran spatial encoder, inference): the frame's padded keys stay in the softmax (lib/transformer_wk.py:154 under
+  // torch 1.10.1); their key / value are the K / V slices of the in-projection bias
+  const bool padkeys = M.additive_mask != 0 && M.arch == NLV_ARCH_STTRAN && work == B.local_work;
+  const float* inb = P(LS(layer, NLV_L_INPROJ_B));
+  RUN(nlv_attn_fwd_padkeys(qkv.p, qkv.ld, (char*)qkv.p + (size_t)D * qkv.esz(), qkv.ld, (char*)qkv.p + (size_t)2 * D * qkv.esz(), qkv.ld,
+                           qkv.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work, o.p, o.ld, o.dt, lse.ok() ? lse.f() : nullptr, &d3,
+                           padkeys ? inb + D : nullptr, padkeys ? inb + 2 * D : nullptr, st));
   CK(mm(o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), K_, y1, P(LS(layer, NLV_L_OUTPROJ_B)), &x, false, nullptr, false, &d0));
   g_next_units = (double)Mr * D * (4 + 4 + (b16 ? 2 : 0));
   RUN(nlv_layernorm_fwd(y1.f(), Mr, D, P(LS(layer, NLV_L_NORMA_W)), P(LS(layer, NLV_L_NORMA_B)), 1e-5f, x1.f(),
@@ -943,6 +948,8 @@ int nlv_session::setup(const nlv_model* model, const nlv_batch* batch, int flags
                 "session: dropout is implemented on the bf16 path (attention-weight masks live in the tensor-core attention kernels); "
                 "run the fp32 / bf16x3 parity modes with dropout 0");
   NLV_CHECK_ARG(M.dropout_p >= 0.f && M.dropout_p < 1.f, "session: bad dropout_p");
+  NLV_CHECK_ARG(!(M.additive_mask != 0 && (training || (flags & NLV_RUN_CTX))),
+                "session: additive_mask (the torch-1.10.1 int key_padding_mask reading) is an inference-only compatibility mode");
   N = B.n_boxes; R = B.n_pairs; Mg = B.n_stream;
   NLV_CHECK_ARG(N >= 0 && R >= 0 && Mg >= 0 && B.nv >= 1, "session: bad batch sizes");
   return NLV_OK;
@@ -977,6 +984,7 @@ int nlv_session::run_forward() {
     NLV_CHECK_ARG(dry || B.distribution != nullptr, "session: sgdet / sgcls need entry['distribution']");
     CK(object_classifier_fwd());
     feat_op = oc.objfeat.cs(0, 2048);
+    if (flags & NLV_RUN_OBJECT_ONLY) return NLV_OK;   // the sgcls test branch builds its pairs from these logits (lib/sttran.py:105-170)
   }
   CK(pair_tokens_fwd(feat_op));
   if (M.arch == NLV_ARCH_STTRAN) CK(sttran_transformer_fwd(rel, &xf_out));

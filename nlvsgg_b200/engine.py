@@ -257,12 +257,13 @@ def _view(ws: torch.Tensor, ptr: Optional[int], shape) -> Optional[torch.Tensor]
 
 def run_forward(k: Kernels, desc: ModelDesc, P, batch, plan: Plan, training: bool, want_ctx: bool, labels=None, with_loss: bool = False,
                 activations: bool = False, with_backward: bool = False, fresh_ws: bool = False,
-                grad_base: Optional[torch.Tensor] = None, grad_offsets=None):
+                grad_base: Optional[torch.Tensor] = None, grad_offsets=None, object_only: bool = False):
     """-> (outputs dict, Session).  The session holds everything backward needs (and keeps the workspace alive)."""
     lib = _C.lib()
     dev = batch.boxes.device
     sess = Session()
-    flags = (_C.RUN_CTX if want_ctx else 0) | (_C.RUN_LOSS if with_loss else 0) | (_C.RUN_ACTIVATIONS if activations else 0)
+    flags = (_C.RUN_CTX if want_ctx else 0) | (_C.RUN_LOSS if with_loss else 0) | (_C.RUN_ACTIVATIONS if activations else 0) | \
+        (_C.RUN_OBJECT_ONLY if object_only else 0)
     m = desc.fill(P, training, grad_base, grad_offsets)
     b = batch_desc(batch, plan, labels, dsg=(desc.arch == "dsg"))
     need = lib.nlv_session_plan(sess.h, ctypes.byref(m), ctypes.byref(b), flags | (_C.RUN_BACKWARD if (want_ctx and with_backward) else 0))
@@ -274,7 +275,7 @@ def run_forward(k: Kernels, desc: ModelDesc, P, batch, plan: Plan, training: boo
              "session_forward")
     sess.ws, sess.keep = ws, [m, b, batch, plan, labels, P]
     N, R = plan.N, plan.R
-    o = {"logits26": _view(ws, out.logits26, (R, 26))}
+    o = {"logits26": _view(ws, out.logits26, (R, 26))} if not object_only else {}
     if out.obj_logits:
         o["distribution"] = _view(ws, out.obj_logits, (N, 37))
     if activations:

@@ -103,6 +103,81 @@ class ObjectClassifier(nn.Module):
         return entry
 
 
+    # ---- sgcls, eval mode: lib/sttran.py:105-170 --------------------------------------------------------------------
+    def union_features(self, entry, frame_id, boxes_xyxy):
+        """Union-box features of one frame (lib/sttran.py:154-160).  The reference calls VinVL through
+        lib/extract_bbox_features.py (un-vendored scene_graph_benchmark); assign `union_feature_extractor` (callable
+        (entry, frame_id, boxes_xyxy[n,4]) -> [n,2048,7,7]) to plug any extractor in."""
+        fn = getattr(self, "union_feature_extractor", None)
+        if fn is not None:
+            return fn(entry, frame_id, boxes_xyxy)
+        try:
+            from lib.extract_bbox_features import extract_feature_given_bbox_base_feat_torch as vinvl
+        except Exception as e:
+            raise RuntimeError("sgcls evaluation re-extracts union features with the VinVL detector (lib/sttran.py:159, "
+                               "lib/extract_bbox_features.py); it is not importable here — set "
+                               "model.object_classifier.union_feature_extractor") from e
+        return vinvl(entry["faset_rcnn_model"], entry["transforms"], entry["cv2_imgs"][frame_id], boxes_xyxy, entry["fmaps"][frame_id], False)
+
+    @torch.no_grad()
+    def sgcls_test_branch(self, entry, logits):
+        """Classifier logits [N,37] -> labels, the human of every frame, the duplicate clean-up of the frame's most frequent
+        label, (human, object) pairs, union boxes / features and spatial masks; mutates and returns `entry` with the keys
+        the reference writes.  The per-frame / per-box python loops of :115-143 are index arithmetic on the device."""
+        boxes = entry["boxes"].float()
+        dev = boxes.device
+        box_idx = boxes[:, 0].long()
+        n = boxes.shape[0]
+        b = int(box_idx[-1].item()) + 1
+        dist = torch.softmax(logits[:, 1:].float(), dim=1)                                      # :107
+        scores, labels = torch.max(dist[:, 1:], dim=1)                                          # :108-109
+        labels = labels + 2
+        # human of a frame = its box with the highest person probability, first one on ties (:115-117)
+        hs = torch.sort(dist[:, 0], descending=True, stable=True)[1]
+        hs = hs[torch.sort(box_idx[hs], stable=True)[1]]
+        first = torch.ones(n, dtype=torch.bool, device=dev)
+        first[1:] = box_idx[hs][1:] != box_idx[hs][:-1]
+        human = torch.zeros(b, dtype=torch.int64, device=dev)
+        human[box_idx[hs][first]] = hs[first]
+        labels[human] = 1                                                                        # :119-120
+        scores[human] = dist[human, 0]
+        # most frequent label of every frame (smallest one on ties, as torch.mode); all its boxes but the most confident
+        # one lose that class and are re-labelled (:123-135)
+        ncls = dist.shape[1] + 1
+        hist = torch.zeros(b, ncls + 1, dtype=torch.int64, device=dev)
+        hist.index_put_((box_idx, labels), torch.ones_like(labels), accumulate=True)
+        dup = hist.argmax(1)[box_idx]                                                            # per box: its frame's duplicate class
+        cand = labels == dup
+        conf = dist.gather(1, (dup - 1).clamp(min=0)[:, None])[:, 0]
+        # the highest-confidence candidate of each frame survives (ascending argsort, last one kept)
+        key = torch.where(cand, conf, torch.full_like(conf, -1.0))
+        o1 = torch.sort(key, stable=True)[1]
+        o2 = o1[torch.sort(box_idx[o1], stable=True)[1]]
+        last = torch.ones(n, dtype=torch.bool, device=dev)
+        last[:-1] = box_idx[o2][:-1] != box_idx[o2][1:]
+        keep = torch.zeros(n, dtype=torch.bool, device=dev)
+        keep[o2[last]] = True
+        change = cand & ~keep
+        rows = torch.nonzero(change)[:, 0]
+        dist[rows, dup[rows] - 1] = 0
+        new_score, new_label = torch.max(dist[rows], dim=1)
+        labels[rows], scores[rows] = new_label + 1, new_score
+        # pairs (:138-146), union boxes (:150-151)
+        objs = torch.nonzero(labels != 1)[:, 0]
+        pair = torch.stack((human[box_idx[objs]], objs), 1)
+        im_idx = box_idx[objs].float()
+        union_boxes = torch.cat((im_idx[:, None], torch.min(boxes[pair[:, 0], 1:3], boxes[pair[:, 1], 1:3]),
+                                 torch.max(boxes[pair[:, 0], 3:5], boxes[pair[:, 1], 3:5])), 1)
+        frames_with_pairs = torch.unique(box_idx[objs]).tolist()
+        feats = [self.union_features(entry, f, union_boxes[union_boxes[:, 0] == f][:, 1:]) for f in frames_with_pairs]   # :154-160
+        entry["distribution"], entry["pred_scores"], entry["pred_labels"] = dist, scores, labels
+        entry["pair_idx"], entry["im_idx"], entry["human_idx"] = pair, im_idx, human[:, None]
+        entry["union_feat"] = torch.cat(feats).to(dev)
+        entry["union_box"] = union_boxes
+        entry["spatial_masks"] = ops.union_mask_pairs(boxes, pair, 27, -0.5)                     # :163-165
+        return entry
+
+
 class STTran(nn.Module):
     def __init__(self, mode="sgdet", attention_class_num=None, spatial_class_num=None, contact_class_num=None,
                  obj_classes=None, enc_layer_num=None, dec_layer_num=None, transformer_mode=None, is_wks=True,
@@ -133,13 +208,22 @@ class STTran(nn.Module):
         self.s_rel_compress = nn.Linear(1936, spatial_class_num)
         self.c_rel_compress = nn.Linear(1936, contact_class_num)
         self.kernels = E.Kernels(precision or os.environ.get("NLV_PRECISION", "bf16"), dropout=0.1)
+        # NLV_ADDITIVE_INT_MASK=1 (or model.kernels.additive_mask = True): evaluate with the torch-1.10.1 reading of the int
+        # key_padding_mask of lib/transformer_wk.py:154 (checkpoints trained by the original environment); inference only
+        self.kernels.additive_mask = os.environ.get("NLV_ADDITIVE_INT_MASK", "0") == "1"
 
     def forward(self, entry):
         """lib/sttran.py:375-411: mutates and returns ``entry``."""
         if self.mode == "sgcls" and not self.training:
-            # lib/sttran.py:105-170 re-extracts union features with VinVL (`extract_feature_given_bbox_base_feat_torch`, an
-            # un-vendored dependency, SURVEY.md §8c): there is no reference to run it against
-            raise NotImplementedError("sgcls evaluation needs the un-vendored VinVL feature extractor (lib/sttran.py:159)")
+            # lib/sttran.py:105-170: the classifier head runs first (one sequencer call that stops after it), the pairs are
+            # built from its labels, then the relation path runs like predcls on the inferred labels
+            logits = A.run_object_head(self, self.kernels, entry)
+            entry = self.object_classifier.sgcls_test_branch(entry, logits)
+            view = dict(entry)
+            view["labels"], view["scores"] = entry["pred_labels"], entry["pred_scores"]
+            _, att, spa, con, _ = A.run_module(self, self.kernels, [view], "predcls", "sttran")
+            entry["attention_distribution"], entry["spatial_distribution"], entry["contacting_distribution"] = att, spa, con
+            return entry
         if self.mode == "sgdet" and not self.is_wks and not self.training:
             # :185-283 — detections are filtered and paired here; the object classifier head is NOT applied (the detector's
             # distribution is kept), so the relation path runs exactly like predcls on the inferred labels

@@ -76,8 +76,9 @@ def pack_upload(arrays: Dict[str, np.ndarray], device, consumer_stream=None, sta
     return out
 
 
-def work_items(seg_start: np.ndarray, seg_len: np.ndarray) -> np.ndarray:
-    """int4 work list for the attention kernels: 16 rows of one segment per item."""
+def work_items(seg_start: np.ndarray, seg_len: np.ndarray, seg_pad: Optional[np.ndarray] = None) -> np.ndarray:
+    """int4 work list for the attention kernels: 16 rows of one segment per item.  seg_pad: padded keys of each segment
+    (4th field; only read by the additive-int-mask compatibility mode, lib/transformer_wk.py:154)."""
     seg_start = np.asarray(seg_start, dtype=np.int64)
     seg_len = np.asarray(seg_len, dtype=np.int64)
     nblk = (seg_len + 15) // 16
@@ -89,6 +90,8 @@ def work_items(seg_start: np.ndarray, seg_len: np.ndarray) -> np.ndarray:
     q0 = (np.arange(total) - first) * 16
     out = np.zeros((total, 4), dtype=np.int32)
     out[:, 0], out[:, 1], out[:, 2] = seg_start[seg], seg_len[seg], q0
+    if seg_pad is not None:
+        out[:, 3] = np.asarray(seg_pad, dtype=np.int64)[seg]
     return out
 
 
@@ -127,7 +130,10 @@ class Plan:
         start = np.concatenate(([0], np.cumsum(cnt)))                    # first token row of every (video, frame)
         # ---- frames = segments of the spatial encoder
         nz = cnt > 0
-        lw = work_items(start[:-1][nz], cnt[nz])
+        # padded keys of a frame = longest frame of its video (l, lib/transformer_wk.py:133) - its own pairs
+        has = nfr > 0
+        lmax = np.repeat(np.maximum.reduceat(cnt, fbase[:-1][has]), nfr[has]) if F else np.zeros(0, dtype=np.int64)
+        lw = work_items(start[:-1][nz], cnt[nz], (lmax - cnt)[nz])
         # ---- windows {j, j+1} inside each video (lib/transformer_wk.py:163-185): keep those with any token
         is_last = np.zeros(F, dtype=bool)
         is_last[fbase[1:][nfr > 0] - 1] = True

@@ -1,0 +1,96 @@
+"""TEST INFRASTRUCTURE — round-2 golden vectors written by running the reference itself (build container only):
+
+  sttran_sgcls_train        STTran(mode='sgcls').train(): lib/sttran.py:93-104 (+ loss, gradients, BN statistics)
+  additive_sttran_eval      sgdet eval with the int key_padding_mask of lib/transformer_wk.py:154 read as torch 1.10.1 did
+                            (mask value added to the logits; oracle/ref_harness.patch_mha_int_mask('additive'))
+  sgcls_test_branch_{a,b}   STTran(mode='sgcls').eval(): lib/sttran.py:105-170 with the un-vendored VinVL union-feature
+                            extractor (:159) replaced by a deterministic stand-in (RoIAlign on entry['fmaps'])
+
+    python -m oracle.make_golden_r2
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torchvision
+
+from nlvsgg_b200 import synth
+from oracle import cref, make_golden as MG, ref_harness as H
+
+GOLDEN = MG.GOLDEN
+
+
+def standin_union_features(fmaps, frame_id, boxes_xyxy):
+    """Deterministic replacement of extract_feature_given_bbox_base_feat_torch: 7x7 RoIAlign (1/16, sampling 0, the reference
+    CPU kernel's convention) of the frame's feature map."""
+    rois = torch.cat((torch.zeros(boxes_xyxy.shape[0], 1), boxes_xyxy.float()), 1)
+    return torchvision.ops.roi_align(fmaps[frame_id][None], rois, (7, 7), 1.0 / 16.0, 0, aligned=False)
+
+
+def sgcls_entry(seed, frames, k):
+    """A synthetic sgcls test entry: boxes / features / distribution as the detector leaves them + per-frame feature maps."""
+    entry, _ = synth.synth_video(seed, frames, k, "sgcls", draw_fn=None, union_feat=False)
+    g = torch.Generator().manual_seed(seed + 77)
+    e = {kk: entry[kk] for kk in ("boxes", "labels", "scores", "features", "distribution")}
+    # soften the pseudo distributions so that arg-max classes repeat inside a frame (the duplicate clean-up of :123-135 fires)
+    e["distribution"] = torch.softmax(torch.log(entry["distribution"]) + 1.5 * torch.randn(entry["distribution"].shape, generator=g), 1)
+    e["fmaps"] = torch.relu(torch.randn(frames, 2048, 17, 30, generator=g))
+    e["frame_names"] = ["synth.mp4/%06d.png" % f for f in range(frames)]
+    e["faset_rcnn_model"], e["transforms"], e["cv2_imgs"] = None, None, [None] * frames
+    return e
+
+
+def sgcls_branch_cases(ref):
+    for name, seed, frames, k in (("sgcls_test_branch_a", 41, 6, 6), ("sgcls_test_branch_b", 42, 9, 8)):
+        m = H.build_reference_sttran(ref, "sgcls")
+        sd = synth.make_state_dict(m.state_dict(), seed)
+        m.load_state_dict(sd)
+        m.eval()
+        entry = sgcls_entry(seed, frames, k)
+        fm = entry["fmaps"]
+        ref.sttran.extract_feature_given_bbox_base_feat_torch = \
+            lambda model, tr, img, boxes, fmap, flag: standin_union_features(fm, int((fm == fmap).flatten(1).all(1).nonzero()[0]), boxes)
+        e = {kk: (v.clone() if torch.is_tensor(v) else v) for kk, v in entry.items()}
+        with torch.no_grad():
+            m(e)
+        keys = ("distribution", "pred_scores", "pred_labels", "pair_idx", "im_idx", "union_box", "union_feat", "spatial_masks",
+                "attention_distribution", "spatial_distribution", "contacting_distribution")
+        out = {kk: e[kk].detach().clone() for kk in keys if kk != "union_feat"}       # the stand-in features are regenerated in the tests
+        out["union_feat_digest"] = torch.tensor([e["union_feat"].double().sum().item(), e["union_feat"].double().abs().sum().item()],
+                                                dtype=torch.float64)
+        out["union_feat_shape"] = tuple(e["union_feat"].shape)
+        torch.save({"name": name, "seed": seed, "frames": frames, "k": k, "outputs": out}, os.path.join(GOLDEN, name + ".pt"))
+        print("wrote", name, "pairs", int(e["pair_idx"].shape[0]))
+
+
+def additive_case(ref):
+    name, seed, frames, k, ep = "additive_sttran_eval", 9, 10, 5, 0.2
+    H.patch_mha_int_mask("additive")
+    try:
+        m = H.build_reference_sttran(ref, "sgdet")
+        sd = synth.make_state_dict(m.state_dict(), seed)
+        m.load_state_dict(sd)
+        m.eval()
+        entry, _ = synth.synth_video(seed, frames, k, "sgdet", draw_fn=cref.draw_union_boxes, empty_frame_prob=ep)
+        e = MG._clone_entry(entry)
+        with torch.no_grad():
+            m(e)
+    finally:
+        H.patch_mha_int_mask("bool")
+    torch.save({"name": name, "mode": "sgdet", "seed": seed, "frames": frames, "mean_boxes": k, "empty_frame_prob": ep, "training": False,
+                "n_boxes": int(entry["boxes"].shape[0]), "n_pairs": int(entry["pair_idx"].shape[0]),
+                "outputs": {kk: e[kk].detach().clone() for kk in MG.OUT_KEYS if kk in e and torch.is_tensor(e[kk])}},
+               os.path.join(GOLDEN, name + ".pt"))
+    print("wrote", name)
+
+
+def main():
+    ref = H.load_reference()
+    MG.run_model_case(ref, H.build_reference_sttran, "sttran", "sttran_sgcls_train", "sgcls", 8, 8, 5, 0.0, True)
+    additive_case(ref)
+    sgcls_branch_cases(ref)
+
+
+if __name__ == "__main__":
+    main()

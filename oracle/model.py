@@ -56,22 +56,31 @@ def batch_norm(x, sd, prefix, training, momentum, update_running=True):
     return F.batch_norm(x, rm, rv, sd[prefix + ".weight"], sd[prefix + ".bias"], False, momentum, 1e-5)
 
 
-def mha_segment(xq, xk, xv, w_in, b_in, w_out, b_out, nhead=N_HEAD):
-    """nn.MultiheadAttention on one unpadded segment: xq,xk,xv [L,d] -> [L,d]."""
+def mha_segment(xq, xk, xv, w_in, b_in, w_out, b_out, nhead=N_HEAD, n_pad=0):
+    """nn.MultiheadAttention on one unpadded segment: xq,xk,xv [L,d] -> [L,d].
+    n_pad > 0: the torch-1.10.1 reading of the int key_padding_mask of lib/transformer_wk.py:154 — the frame's n_pad all-zero
+    padded rows stay in the softmax as keys, with the mask value 1 ADDED to their logits."""
     L, d = xq.shape
     hd = d // nhead
+    if n_pad:
+        xk = torch.cat((xk, xk.new_zeros(n_pad, d)), 0)
+        xv = torch.cat((xv, xv.new_zeros(n_pad, d)), 0)
+    Lk = xk.shape[0]
     q = F.linear(xq, w_in[:d], b_in[:d]).view(L, nhead, hd).transpose(0, 1)
-    k = F.linear(xk, w_in[d:2 * d], b_in[d:2 * d]).view(L, nhead, hd).transpose(0, 1)
-    v = F.linear(xv, w_in[2 * d:], b_in[2 * d:]).view(L, nhead, hd).transpose(0, 1)
-    att = torch.softmax((q * (1.0 / math.sqrt(hd))) @ k.transpose(1, 2), dim=-1)
+    k = F.linear(xk, w_in[d:2 * d], b_in[d:2 * d]).view(Lk, nhead, hd).transpose(0, 1)
+    v = F.linear(xv, w_in[2 * d:], b_in[2 * d:]).view(Lk, nhead, hd).transpose(0, 1)
+    logits = (q * (1.0 / math.sqrt(hd))) @ k.transpose(1, 2)
+    if n_pad:
+        logits = logits + torch.cat((logits.new_zeros(L), logits.new_ones(n_pad)))
+    att = torch.softmax(logits, dim=-1)
     o = (att @ v).transpose(0, 1).reshape(L, d)
     return F.linear(o, w_out, b_out)
 
 
-def encoder_layer(x, sd, p, attn="self_attn"):
+def encoder_layer(x, sd, p, attn="self_attn", n_pad=0):
     """Post-norm encoder layer on one segment (lib/transformer.py:20-30 / nn.TransformerEncoderLayer)."""
     a = mha_segment(x, x, x, sd[f"{p}.{attn}.in_proj_weight"], sd[f"{p}.{attn}.in_proj_bias"],
-                    sd[f"{p}.{attn}.out_proj.weight"], sd[f"{p}.{attn}.out_proj.bias"])
+                    sd[f"{p}.{attn}.out_proj.weight"], sd[f"{p}.{attn}.out_proj.bias"], n_pad=n_pad)
     x = F.layer_norm(x + a, (x.shape[1],), sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"])
     h = F.linear(F.relu(F.linear(x, sd[f"{p}.linear1.weight"], sd[f"{p}.linear1.bias"])),
                  sd[f"{p}.linear2.weight"], sd[f"{p}.linear2.bias"])
@@ -95,20 +104,23 @@ def _num_layers(sd, prefix):
     return n
 
 
-def glocal_transformer(features, im_idx, sd, prefix="glocal_transformer"):
-    """transformer_wk.forward, mode='latter' (lib/transformer_wk.py:130-217)."""
+def glocal_transformer(features, im_idx, sd, prefix="glocal_transformer", additive_mask=False):
+    """transformer_wk.forward, mode='latter' (lib/transformer_wk.py:130-217).  additive_mask: the spatial encoder's int
+    key_padding_mask as torch 1.10.1 read it (see mha_segment; one encoder layer, as the reference configures it)."""
     fid = im_idx.to(torch.int64)
     b = int(fid[-1]) + 1
     rows = [torch.nonzero(fid == f).flatten() for f in range(b)]
     n_enc = _num_layers(sd, f"{prefix}.local_attention.layers")
     n_dec = _num_layers(sd, f"{prefix}.global_attention.layers")
+    assert not additive_mask or n_enc == 1
+    lmax = max(r.numel() for r in rows)
     local = torch.zeros_like(features)
     for f in range(b):
         if rows[f].numel() == 0:
             continue
         x = features[rows[f]]
         for i in range(n_enc):
-            x = encoder_layer(x, sd, f"{prefix}.local_attention.layers.{i}")
+            x = encoder_layer(x, sd, f"{prefix}.local_attention.layers.{i}", n_pad=(lmax - rows[f].numel()) if additive_mask else 0)
         local[rows[f]] = x
     windows = [j for j in range(b - 1) if rows[j].numel() + rows[j + 1].numel() > 0]
     if len(windows) == 0:
@@ -175,12 +187,55 @@ def relation_heads(x, sd):
 # --------------------------------------------------------------------------------------
 # models
 # --------------------------------------------------------------------------------------
+def sgcls_test_branch(entry, logits, union_feature_fn, draw_fn):
+    """lib/sttran.py:105-170 (mode 'sgcls', eval): object labels from the classifier head, the human of every frame, the
+    duplicate-class clean-up of the frame's most frequent label, (human, object) pairs, union boxes, union features through
+    `union_feature_fn(frame_id, boxes_xyxy[n,4]) -> [n,2048,7,7]` (the un-vendored VinVL extractor of :159) and the masks.
+    Returns a dict with the keys the reference writes."""
+    boxes = entry["boxes"]
+    box_idx = boxes[:, 0].long()
+    b = int(box_idx[-1] + 1)
+    dist = torch.softmax(logits[:, 1:], dim=1)                                     # :107
+    scores, labels = torch.max(dist[:, 1:], dim=1)                                 # :108
+    labels = labels + 2
+    gidx = torch.arange(boxes.shape[0])
+    human = torch.zeros(b, dtype=torch.int64)
+    for i in range(b):                                                             # :115-117
+        human[i] = gidx[box_idx == i][torch.argmax(dist[box_idx == i, 0])]
+    labels[human] = 1
+    scores[human] = dist[human, 0]
+    for i in range(b):                                                             # :123-135
+        present = boxes[:, 0] == i
+        dup = torch.mode(labels[present])[0]
+        if torch.sum(labels[present] == dup) > 0:
+            pos = labels[present] == dup
+            for j in torch.argsort(dist[present][pos][:, dup - 1])[:-1]:
+                ci = gidx[present][pos][j]
+                dist[ci, dup - 1] = 0
+                labels[ci] = torch.argmax(dist[ci]) + 1
+                scores[ci] = torch.max(dist[ci])
+    im_idx, pair = [], []
+    for j in range(b):                                                             # :138-143
+        for m in gidx[box_idx == j][labels[box_idx == j] != 1]:
+            im_idx.append(j)
+            pair.append([int(human[j]), int(m)])
+    pair = torch.tensor(pair, dtype=torch.int64).reshape(-1, 2)
+    im_idx = torch.tensor(im_idx, dtype=torch.float)
+    union = torch.cat((im_idx[:, None], torch.min(boxes[:, 1:3][pair[:, 0]], boxes[:, 1:3][pair[:, 1]]),
+                       torch.max(boxes[:, 3:5][pair[:, 0]], boxes[:, 3:5][pair[:, 1]])), 1)   # :150-151
+    feats = [union_feature_fn(f, union[union[:, 0] == f][:, 1:]) for f in range(b) if (union[:, 0] == f).any()]   # :154-160
+    rois = torch.cat((boxes[pair[:, 0], 1:], boxes[pair[:, 1], 1:]), 1).numpy()
+    return {"distribution": dist, "pred_scores": scores, "pred_labels": labels, "pair_idx": pair, "im_idx": im_idx,
+            "union_box": union, "union_feat": torch.cat(feats), "human_idx": human,
+            "spatial_masks": torch.from_numpy(draw_fn(rois.astype("float32"), 27) - 0.5)}
+
+
 def sttran_forward(sd: Dict[str, torch.Tensor], entry: dict, mode: str = "sgdet", training: bool = False,
-                   update_running: bool = True, return_tokens: bool = False) -> dict:
+                   update_running: bool = True, return_tokens: bool = False, additive_mask: bool = False) -> dict:
     """lib/sttran.py:375-411.  Returns a new dict with the keys the reference adds/overwrites."""
     out = object_classifier(entry, sd, mode, training, update_running=update_running)
     tok = pair_tokens(entry, out["pred_labels"], sd, training, update_running)
-    g = glocal_transformer(tok, entry["im_idx"], sd)
+    g = glocal_transformer(tok, entry["im_idx"], sd, additive_mask=additive_mask)
     out.update(relation_heads(g, sd))
     if return_tokens:
         out["rel_features"], out["global_output"] = tok, g

@@ -83,3 +83,38 @@ def test_oracle_dsg_matches_reference_golden():
         pred = omodel.dsg_forward(sd, entry, case["mode"], training=False)
     for k, want in case["outputs"].items():
         assert G.rel_err(pred[k], want) < 2e-5, k
+
+
+def test_oracle_additive_int_mask_matches_reference_golden():
+    """lib/transformer_wk.py:154 under torch 1.10.1 (the int key_padding_mask is ADDED to the logits): golden written by the
+    reference with that reading of the mask; the plain restatement must NOT match it (the mode changes the numbers)."""
+    case = G.load_case("additive_sttran_eval")
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    sd = synth.make_state_dict(G.sttran_template(), case["seed"])
+    with torch.no_grad():
+        pred = omodel.sttran_forward(sd, entry, "sgdet", training=False, additive_mask=True)
+        plain = omodel.sttran_forward(sd, entry, "sgdet", training=False)
+    for k, want in case["outputs"].items():
+        assert G.rel_err(pred[k], want) < 2e-5, k
+    assert G.rel_err(plain["attention_distribution"], case["outputs"]["attention_distribution"]) > 1e-3
+
+
+@pytest.mark.parametrize("name", ["sgcls_test_branch_a", "sgcls_test_branch_b"])
+def test_oracle_sgcls_test_branch_matches_reference_golden(name):
+    """lib/sttran.py:105-170 (sgcls, eval) with the un-vendored union-feature extractor replaced by the same stand-in the
+    golden was written with: labels, humans, duplicate clean-up, pairs, union boxes and masks are exact."""
+    from oracle.make_golden_r2 import sgcls_entry, standin_union_features
+    case = G.load_case(name)
+    entry = sgcls_entry(case["seed"], case["frames"], case["k"])
+    sd = synth.make_state_dict(G.sttran_template(), case["seed"])
+    with torch.no_grad():
+        logits = omodel.object_classifier(entry, sd, "sgcls", False)["distribution"]
+        got = omodel.sgcls_test_branch(entry, logits, lambda f, b: standin_union_features(entry["fmaps"], f, b), cref.draw_union_boxes)
+    want = case["outputs"]
+    for k in ("pred_labels", "pair_idx"):
+        assert torch.equal(got[k], want[k]), k
+    assert torch.equal(got["im_idx"], want["im_idx"]) and torch.equal(got["union_box"], want["union_box"])
+    assert torch.equal(got["spatial_masks"].float(), want["spatial_masks"].float())
+    assert G.rel_err(got["distribution"], want["distribution"]) < 1e-5 and G.rel_err(got["pred_scores"], want["pred_scores"]) < 1e-5
+    assert tuple(got["union_feat"].shape) == tuple(want["union_feat_shape"])
+    assert abs(got["union_feat"].double().sum().item() - want["union_feat_digest"][0].item()) <= 1e-6 * want["union_feat_digest"][1].item()

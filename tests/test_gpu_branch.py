@@ -72,3 +72,29 @@ def test_full_forward_of_the_branch_matches_oracle_model(cuda_lib):
         assert G.rel_err(pred[k].float().cpu(), want[k]) < 1e-4, k
     # the detector's distribution is kept (the classifier head is not applied on this branch)
     assert np.array_equal(pred["distribution"].cpu().numpy(), prod["distribution"])
+
+
+@pytest.mark.parametrize("name", ["sgcls_test_branch_a", "sgcls_test_branch_b"])
+def test_sgcls_test_branch_matches_reference_golden(cuda_lib, name):
+    """STTran(mode='sgcls').eval() (lib/sttran.py:105-170) against goldens written by the reference itself with the
+    un-vendored union-feature extractor replaced by a stand-in (oracle/make_golden_r2.py): the classifier head stops the
+    sequencer after the logits, the branch builds labels / humans / duplicate clean-up / pairs / union boxes / masks on the
+    device (all exact), the relation path then runs on the inferred labels."""
+    from nlvsgg_b200.lib.sttran import STTran
+    from oracle.make_golden_r2 import sgcls_entry, standin_union_features
+    case = G.load_case(name)
+    entry = sgcls_entry(case["seed"], case["frames"], case["k"])
+    m = STTran("sgcls", 3, 6, 17, synth.AG_OBJECT_CLASSES, 1, 3, "wk", True, 2048, precision="fp32")
+    m.load_state_dict(synth.make_state_dict(G.sttran_template(), case["seed"]))
+    m = m.cuda().eval()
+    fm = entry["fmaps"]
+    m.object_classifier.union_feature_extractor = lambda e, f, boxes: standin_union_features(fm, f, boxes.cpu()).cuda()
+    with torch.no_grad():
+        out = m(_cuda({k: v for k, v in entry.items() if k != "fmaps"}))
+    want = case["outputs"]
+    for k in ("pred_labels", "pair_idx", "im_idx", "union_box"):
+        assert torch.equal(out[k].cpu(), want[k]), k
+    assert torch.equal(out["spatial_masks"].cpu().float(), want["spatial_masks"].float())
+    assert tuple(out["union_feat"].shape) == tuple(want["union_feat_shape"])
+    for k in ("distribution", "pred_scores", "attention_distribution", "spatial_distribution", "contacting_distribution"):
+        assert G.rel_err(out[k].cpu(), want[k]) < 1e-3, k

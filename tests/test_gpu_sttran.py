@@ -69,6 +69,29 @@ def test_sttran_eval_matches_reference(cuda_lib, name, precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
+def test_additive_int_mask_mode_matches_reference(cuda_lib, precision):
+    """kernels.additive_mask: the int key_padding_mask of lib/transformer_wk.py:154 as torch 1.10.1 read it (+1 on the logits
+    of the padded keys instead of masking them) — golden written by the reference under that reading; inference only."""
+    from oracle import cref
+    case = G.load_case("additive_sttran_eval")
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    m = _build(case, precision, False)
+    m.kernels.additive_mask = True
+    with torch.no_grad():
+        pred = m(_entry_cuda(entry))
+    for k, want in case["outputs"].items():
+        assert G.rel_err(pred[k].cpu(), want) < TOL[precision], f"{k}: rel err {G.rel_err(pred[k].cpu(), want):.3e}"
+    m.kernels.additive_mask = False
+    with torch.no_grad():
+        plain = m(_entry_cuda(entry))
+    assert G.rel_err(plain["attention_distribution"].cpu(), case["outputs"]["attention_distribution"]) > 1e-3
+    m.kernels.additive_mask = True
+    m.train()
+    with pytest.raises(RuntimeError, match="inference-only"):
+        m(_entry_cuda(entry))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3", "bf16"])
 @pytest.mark.parametrize("name", [n for n in G.model_cases("sttran_") if "train" in n])
 def test_sttran_train_step_matches_reference(cuda_lib, name, precision):
     from oracle import cref
@@ -149,3 +172,67 @@ def test_batched_videos_equal_single_videos(cuda_lib):
     wantobj = torch.cat([s["distribution"] for s in singles])
     assert G.rel_err(out["logits26"].cpu(), want26.cpu()) < 1e-5
     assert G.rel_err(out["distribution"].cpu(), wantobj.cpu()) < 1e-5
+
+
+class _RefStyleAdamW:
+    """The update rule of the reference optimizer (lib/AdamW.py:64-112), restated: decoupled decay and the Adam step are
+    applied through `p.data` — invisible to autograd version counters, which is what a weight cache must survive."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+        self.params, self.lr, self.betas, self.eps, self.wd = list(params), lr, betas, eps, weight_decay
+        self.state = {}
+
+    def step(self):
+        b1, b2 = self.betas
+        for i, p in enumerate(self.params):
+            if p.grad is None:
+                continue
+            p.data.mul_(1 - self.lr * self.wd)
+            st = self.state.setdefault(i, {"step": 0, "m": torch.zeros_like(p.data), "v": torch.zeros_like(p.data)})
+            st["step"] += 1
+            st["m"].mul_(b1).add_(p.grad.data, alpha=1 - b1)
+            st["v"].mul_(b2).addcmul_(p.grad.data, p.grad.data, value=1 - b2)
+            denom = st["v"].sqrt().add_(self.eps)
+            step_size = self.lr * (1 - b2 ** st["step"]) ** 0.5 / (1 - b1 ** st["step"])
+            p.data.add_(st["m"].div(denom).mul_(-step_size))
+
+    def zero_grad(self):
+        for p in self.params:
+            p.grad = None
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_dropin_training_loop_with_reference_style_optimizer(cuda_lib, precision):
+    """model(entry); loss.backward(); optimizer.step() twice, the optimizer writing through p.data like lib/AdamW.py:
+    the second forward must see the updated weights (fp32: step-2 outputs equal the CPU oracle put through the same loop)."""
+    from oracle import cref, model as omodel
+    case = G.load_case("sttran_sgdet_train")
+    entry, _ = G.case_inputs(case, cref.draw_union_boxes)
+    m = _build(case, precision, True)
+    opt = _RefStyleAdamW(m.parameters(), lr=2e-3)
+    outs = []
+    for _ in range(2):
+        opt.zero_grad()
+        pred = m(_entry_cuda(entry))
+        outs.append({k: pred[k].detach().cpu().clone() for k in OUT_KEYS})
+        _reference_style_loss(pred).backward()
+        opt.step()
+    # the same two iterations on the CPU oracle
+    sd = synth.make_state_dict(G.sttran_template(), case["seed"])
+    names = [n for n, _ in m.named_parameters()]
+    for n in names:
+        sd[n].requires_grad_(True)
+    oopt = _RefStyleAdamW([sd[n] for n in names], lr=2e-3)
+    wants = []
+    for _ in range(2):
+        oopt.zero_grad()
+        pred = omodel.sttran_forward(sd, entry, "sgdet", training=True)
+        wants.append({k: pred[k].detach().clone() for k in OUT_KEYS})
+        omodel.training_loss(pred, entry, "sgdet").backward()
+        oopt.step()
+    moved = G.rel_err(wants[1]["attention_distribution"], wants[0]["attention_distribution"])
+    assert moved > 5e-2, moved                                         # the step is large enough to matter
+    assert G.rel_err(outs[1]["attention_distribution"], outs[0]["attention_distribution"]) > 0.5 * moved   # weights really moved
+    if precision == "fp32":
+        for k in OUT_KEYS:
+            assert G.rel_err(outs[1][k], wants[1][k]) < 2e-3, k
