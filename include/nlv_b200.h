@@ -198,6 +198,12 @@ int nlv_dropout_apply(const void* src, int src_dtype, int lds, void* dst, int ds
                       const nlv_dropout* drop, void* stream);
 int nlv_dropout_mask(long long rows, int cols, const nlv_dropout* drop, unsigned char* out, void* stream);
 int nlv_dropout_mask_attn(long long rows, int heads, int nkeys, const nlv_dropout* drop, unsigned char* out, void* stream);
+/* LayerNorm backward in one pass over dy and x: dx, dx2 (optionally dropout-masked like nlv_layernorm_bwd_drop), dw += , db +=
+ * and dprev += colsum(dx2 values) — the bias gradient of the Linear in front of the residual sum (nullable).
+ * cols % 8 == 0, cols <= 2048 */
+int nlv_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                            long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, float* dprev,
+                            const nlv_dropout* drop, void* stream);
 /* nlv_layernorm_bwd whose second output dx2 is the dropout-masked, scaled copy of dx (operand of the GEMMs behind a
  * residual dropout: d(dropout(a)) = mask * dx / (1 - p)); dx itself stays unmasked (the residual branch) */
 int nlv_layernorm_bwd_drop(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,

@@ -4,8 +4,12 @@
 //
 // One persistent CTA per SM, 320 threads:
 //   warp 0 (lane 0) : TMA producer   — cp.async.bulk.tensor 2-D boxes into a 128B-swizzled smem ring
-//   warp 1 (lane 0) : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, 128 x BLOCK_N x 16 per instruction,
-//                                      accumulators double-buffered in TMEM (2 x BLOCK_N columns)
+//   warp 1 (lane 0) : MMA issuer     — tcgen05.mma.kind::f16, accumulators double-buffered in TMEM (2 x BLOCK_N columns).
+//                                      MODE 2 (default when m > 128): the two CTAs of a cluster form a CTA PAIR and the
+//                                      leader issues tcgen05.mma.cta_group::2 — one 256 x BLOCK_N x 16 instruction over
+//                                      both SMs, each CTA staging its own 128 A rows and HALF of the B tile (6-8 stages
+//                                      instead of 4-6, half the B shared-memory reads per SM).  MODE 1: cta_group::1 with
+//                                      the B tile multicast to both CTAs.  MODE 0: single CTA, 128 x BLOCK_N x 16.
 //   warps 2..9      : epilogue       — tcgen05.ld 32x32b (one TMEM lane = one output row per thread); warps w and w+4
 //                                      share a TMEM lane quarter and take alternate 32-column chunks (the epilogue of
 //                                      small-K products is bound by memory instructions in flight per warp);
@@ -33,12 +37,15 @@ constexpr int NUM_THREADS = 64 + 32 * NUM_EPI_WARPS;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KiB
 constexpr int ATOM_BYTES = 64 * BLOCK_K * 2;          // one [64 mn x 64 k] MN-major box, 8 KiB
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MODE>
 struct Cfg {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGES = (BLOCK_N == 256) ? 4 : 6;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // 256 or 512, power of two
-  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + 1024 /*align*/;
+  static constexpr int B_ROWS = MODE == 2 ? BLOCK_N / 2 : BLOCK_N;     // B rows staged per CTA
+  static constexpr int B_STAGE_BYTES = B_ROWS * BLOCK_K * 2;
+  static constexpr int STAGES = MODE == 2 ? ((BLOCK_N == 256) ? 6 : 8) : ((BLOCK_N == 256) ? 4 : 6);
+  static constexpr int ACC_STAGES = 512 / BLOCK_N;   // accumulator stages in TMEM: 2 x 256 or 4 x 128 columns (all 512)
+  static constexpr int TMEM_COLS = ACC_STAGES * BLOCK_N;
+  static constexpr int SMEM_BYTES = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 256 /*barriers*/ + NUM_EPI_WARPS * 4096 /*epilogue staging*/ +
+                                    1024 /*align*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -100,6 +107,52 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
   return r;
 }
+// ---- CTA pair (cta_group::2) ----
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {   // same offset in CTA `rank` of the cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+  return r;
+}
+// the box lands in THIS CTA's shared memory, its bytes complete on the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_cluster(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_cluster(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar, uint16_t mask) {   // arrives on `bar`'s offset in every CTA of mask
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -160,24 +213,27 @@ struct Params {
 // CM = CTAs per cluster along M (1 or 2).  With CM == 2 the two CTAs compute vertically adjacent 128 x BLOCK_N tiles and
 // share the B tile: each loads half of it and multicasts it into both shared memories, cutting the L2->SM operand
 // traffic per tile from (128 + BLOCK_N) to (128 + BLOCK_N/2) rows per k-block.
-template <int BLOCK_N, bool A_MN, bool B_MN, int CM>
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const Params p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, MODE>;
+  constexpr int CM = MODE == 0 ? 1 : 2;          // CTAs per cluster
+  constexpr bool PAIR = MODE == 2;               // one cta_group::2 MMA over both CTAs
   constexpr int STAGES = C::STAGES;
-  constexpr uint32_t STAGE_TX = A_STAGE_BYTES + C::B_STAGE_BYTES;
+  constexpr uint32_t STAGE_TX = (A_STAGE_BYTES + C::B_STAGE_BYTES) * (PAIR ? 2 : 1);   // pair: both CTAs' boxes complete on the leader's barrier
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t bar_base = smem_b + STAGES * C::B_STAGE_BYTES;
-  // barrier layout: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], then the TMEM base address word
+  // barrier layout: full[STAGES], empty[STAGES], tmem_full[4], tmem_empty[4], then the TMEM base address word
+  constexpr int ACC = C::ACC_STAGES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tmem_full_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
-  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+  auto tmem_empty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -185,19 +241,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), CM);   // one tcgen05.commit arrival per CTA that received the stage's data
+      mbar_init(empty_bar(s), MODE == 1 ? 2 : 1);   // MODE 1: one tcgen05.commit arrival per CTA that wrote into this stage
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ACC; ++s) {
       mbar_init(tmem_full_bar(s), 1);
-      mbar_init(tmem_empty_bar(s), NUM_EPI_WARPS);  // one arrive per epilogue warp
+      mbar_init(tmem_empty_bar(s), NUM_EPI_WARPS * (PAIR ? 2 : 1));  // one arrive per epilogue warp (pair: of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
   }
-  if (warp == 1) {  // whole warp: allocate TMEM columns
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 1) {  // whole warp: allocate TMEM columns (pair: the same columns in both CTAs)
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -208,6 +269,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int num_k_blocks = (p.k + BLOCK_K - 1) / BLOCK_K;
   const int cta_rank = CM > 1 ? (int)cluster_ctarank() : 0;
+  // the last n-block issues a narrower instruction (N rounded up to 16; 32 for a pair so that each CTA's half stays a multiple
+  // of 16) instead of multiplying zero-filled columns: n = 1936 = 7 x 256 + 144 would otherwise spend 5.5% of its tensor
+  // time on padding.  In pair mode CTA r stages the B rows [n0 + r * n_inst / 2, ...) — the halves of the instruction's N.
+  auto n_inst_of = [&](int n0) -> int {
+    const int n_left = p.n - n0;
+    if (n_left >= BLOCK_N) return BLOCK_N;
+    return PAIR ? ((n_left + 31) & ~31) : ((n_left + 15) & ~15);
+  };
   const int num_mp = (p.num_m_blocks + CM - 1) / CM;          // groups of CM vertically adjacent tiles
   const int num_work = num_mp * p.num_n_blocks * p.k_splits;
   const int work0 = blockIdx.x / CM, work_stride = gridDim.x / CM;
@@ -226,12 +295,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // of A once per n-block: 3x the algorithmic DRAM traffic on the [22931 x 1936 x 1936] products)
         const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
         const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
+        const int nb0 = PAIR ? n0 + cta_rank * (n_inst_of(n0) / 2) : n0;     // first B row this CTA stages (pair mode)
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
           const int k0 = kb * BLOCK_K;
           const uint32_t sa = smem_a + stage * A_STAGE_BYTES;
           const uint32_t sb = smem_b + stage * C::B_STAGE_BYTES;
+          if constexpr (PAIR) {
+            // both CTAs' boxes complete on the leader's full barrier; only the leader posts the expected byte count
+            const uint32_t lbar = map_to_cta(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
+            if constexpr (A_MN) {
+#pragma unroll
+              for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_pair(sa + i * ATOM_BYTES, &tmap_a, lbar, m0 + 64 * i, k0);
+            } else {
+              tma_load_2d_pair(sa, &tmap_a, lbar, k0, m0);
+            }
+            if constexpr (B_MN) {
+#pragma unroll
+              for (int i = 0; i < C::B_ROWS / 64; ++i) tma_load_2d_pair(sb + i * ATOM_BYTES, &tmap_b, lbar, nb0 + 64 * i, k0);
+            } else {
+              tma_load_2d_pair(sb, &tmap_b, lbar, k0, nb0);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
+          mbar_arrive_expect_tx(full_bar(stage), STAGE_TX);
           if constexpr (A_MN) {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * ATOM_BYTES, &tmap_a, full_bar(stage), m0 + 64 * i, k0);
@@ -265,11 +354,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ===================== MMA issuer =====================
+    if (lane == 0 && (!PAIR || cta_rank == 0)) {
+      // ===================== MMA issuer (pair: the leader CTA only) =====================
       // instruction descriptor: D=f32, A=B=bf16, majors, N>>3 at [17,23), M>>4 at [24,29)
       const uint32_t idesc0 = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                              ((uint32_t)(BLOCK_M >> 4) << 24);
+                              ((uint32_t)((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);
       // K-major  : 8-row groups 1024 B apart (SBO); 16 k-elements = +32 B on the start address
       // MN-major : 64-mn atoms 8 KiB apart (LBO), 8-k groups 1024 B apart (SBO); 16 k-elements = +2048 B
       constexpr uint32_t A_LBO = A_MN ? ATOM_BYTES : 16, A_KSTEP = A_MN ? 2048 : 32;
@@ -280,14 +369,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       for (int work = work0; work < num_work; work += work_stride, ++iter) {
         const int kb0 = (work % p.k_splits) * p.kb_per_split;
         const int kb1 = min(num_k_blocks, kb0 + p.kb_per_split);
-        // the last n-block issues a narrower instruction (N rounded up to 16) instead of multiplying zero-filled columns:
-        // n = 1936 = 7 x 256 + 144 would otherwise spend 5.5% of its tensor time on padding
-        const int n_left = p.n - ((work / p.k_splits) % p.num_n_blocks) * BLOCK_N;
-        const uint32_t n_inst = n_left >= BLOCK_N ? (uint32_t)BLOCK_N : (uint32_t)((n_left + 15) & ~15);
+        const uint32_t n_inst = (uint32_t)n_inst_of(((work / p.k_splits) % p.num_n_blocks) * BLOCK_N);
         const uint32_t idesc = idesc0 | ((n_inst >> 3) << 17);
-        const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1;
-        mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
+        const int acc = iter % ACC;
+        const uint32_t acc_phase = (iter / ACC) & 1;
+        if constexpr (PAIR) mbar_wait_cluster(tmem_empty_bar(acc), acc_phase ^ 1u);   // arrivals come from both CTAs' epilogues
+        else mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -299,12 +386,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc(sa + k * A_KSTEP, A_LBO, 1024);
             const uint64_t bdesc = make_smem_desc(sb + k * B_KSTEP, B_LBO, 1024);
-            tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            if constexpr (PAIR) tc_mma_bf16_pair(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
           }
-          // frees the smem slot when these MMAs retire — in BOTH CTAs of a pair, since each also wrote the peer's copy
+          // frees the smem slot when these MMAs retire — in BOTH CTAs of a cluster (MODE 1: each also wrote the peer's copy;
+          // pair: the instruction read both CTAs' stages); the accumulator-ready signal of a pair goes to both epilogues
           if constexpr (CM == 1) tc_commit(empty_bar(stage));
+          else if constexpr (PAIR) tc_commit_pair(empty_bar(stage), (uint16_t)3);
           else tc_commit_mc(empty_bar(stage), (uint16_t)((1u << CM) - 1));
-          if (kb == kb1 - 1) tc_commit(tmem_full_bar(acc));
+          if (kb == kb1 - 1) {
+            if constexpr (PAIR) tc_commit_pair(tmem_full_bar(acc), (uint16_t)3);
+            else tc_commit(tmem_full_bar(acc));
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -319,42 +412,72 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                                : ((p.ldd & 3) == 0 && ((uintptr_t)p.d & 15) == 0);
     const bool split = p.k_splits > 1;
     const bool bias_vec = ((uintptr_t)p.bias & 15) == 0;
+    const bool res_fast = p.residual != nullptr && p.r_dtype != NLV_BF16 && !split && !d_bf16 && vec_ok && (p.ldr & 3) == 0 &&
+                          ((uintptr_t)p.residual & 15) == 0;
+    uint8_t* const stg = smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 2) * 4096;   // this warp's staging tile
     for (int work = work0; work < num_work; work += work_stride, ++iter) {
       const int tile = work / p.k_splits;
       const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
       const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
-      const int acc = iter & 1;
-      const uint32_t acc_phase = (iter >> 1) & 1;
-      mbar_wait(tmem_full_bar(acc), acc_phase);
-      tc_fence_after();
+      const int acc = iter % ACC;
+      const uint32_t acc_phase = (iter / ACC) & 1;
       const int row = m0 + quarter * 32 + lane;
       const bool row_ok = row < p.m;
+      constexpr int CSTEP = 32 * (NUM_EPI_WARPS / 4);
+      // fp32 residual rows are requested one chunk AHEAD of their use — the first chunk's before the accumulator is even
+      // ready — so that the DRAM latency of the residual stream overlaps the MMAs / the previous chunk's stores instead of
+      // being paid once per chunk by every epilogue warp
+      float4 rcur[8];
+      // (mapping of the transposed store below: register `it` = row it * 4 + lane / 8 of the warp's 32, columns 4 (lane % 8) ..)
+      auto prefetch_res = [&](int c0, float4 (&dst)[8]) -> bool {
+        if (!res_fast || c0 >= BLOCK_N || n0 + c0 + 32 > p.n) return false;      // warp-uniform
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int grow = m0 + quarter * 32 + it * 4 + (lane >> 3);
+          dst[it] = grow < p.m ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)grow * p.ldr + n0 + c0 + (lane & 7) * 4)
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        return true;
+      };
+      bool have_res = prefetch_res(chunk0, rcur);
+      mbar_wait(tmem_full_bar(acc), acc_phase);
+      tc_fence_after();
       const uint32_t taddr_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BLOCK_N;
       bool released = false;
-      constexpr int CSTEP = 32 * (NUM_EPI_WARPS / 4);
 #pragma unroll 1
       for (int c0 = chunk0; c0 < BLOCK_N; c0 += CSTEP) {
         if (n0 + c0 >= p.n) break;  // warp-uniform
         uint32_t v[32];
         tmem_ld32(taddr_row + c0, v);
+        float4 rnext[8];
+        const bool have_next = prefetch_res(c0 + CSTEP, rnext);
+        const bool have_now = have_res;
+        float4 rnow[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { rnow[j] = rcur[j]; rcur[j] = rnext[j]; }
+        have_res = have_next;
         tmem_ld_wait();
         if (c0 + CSTEP >= BLOCK_N || n0 + c0 + CSTEP >= p.n) {
           // this warp's last chunk of the tile: its share of the accumulator stage goes back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+          if (lane == 0) {
+            if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));   // the leader's MMA warp owns both halves
+            else mbar_arrive(tmem_empty_bar(acc));
+          }
           released = true;
         }
-        if (!row_ok) continue;
         const int ncol = min(32, p.n - (n0 + c0));
         float f[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+        for (int j = 0; j < 32; ++j) f[j] = row_ok ? __uint_as_float(v[j]) : 0.f;
         if (split) {  // partial sum of one k range: accumulate into the zero-initialised fp32 output
-          float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + n0 + c0;
+          if (row_ok) {
+            float* o = reinterpret_cast<float*>(p.d) + (size_t)row * p.ldd + n0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ncol) atomicAdd(o + j, f[j]);
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) atomicAdd(o + j, f[j]);
+          }
           continue;
         }
         if (p.bias != nullptr) {
@@ -383,7 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             for (int q = 0; q < 8; ++q) f[j + q] = ((keep >> q) & 1u) ? f[j + q] * p.drop.scale : 0.f;
           }
         }
-        if (p.gate != nullptr) {
+        if (p.gate != nullptr && row_ok) {
           if (p.gate_scale != 1.f) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= p.gate_scale;
@@ -415,7 +538,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (j < ncol && !(gt[j] > 0.f)) f[j] = 0.f;
           }
         }
-        if (p.residual != nullptr) {
+        // full, aligned chunks leave through the warp's 4 KB staging tile: the accumulator arrives one ROW per thread, a
+        // row-per-thread store touches 32 rows x 16 bytes per instruction (half-filled sectors); transposed through shared
+        // memory (16-byte slots XOR-swizzled by the row: conflict-free both ways) every store / residual load instruction
+        // covers whole 128-byte (fp32) or 64-byte (bf16) row segments
+        const bool fast = ncol == 32 && vec_ok;   // warp-uniform
+        const bool res_late = fast && !d_bf16 && res_fast;          // fp32 residual added after the transposition (coalesced)
+        if (p.residual != nullptr && !res_late && row_ok) {
           const size_t roff = (size_t)row * p.ldr + n0 + c0;
           if (p.r_dtype == NLV_BF16) {
             const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
@@ -424,45 +553,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
               if (j < ncol) f[j] += __bfloat162float(r[j]);
           } else {
             const float* r = reinterpret_cast<const float*>(p.residual) + roff;
-            if (ncol == 32 && (p.ldr & 3) == 0 && ((uintptr_t)p.residual & 15) == 0) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(r + j);
-                f[j] += t.x; f[j + 1] += t.y; f[j + 2] += t.z; f[j + 3] += t.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (j < ncol) f[j] += r[j];
-            }
+            for (int j = 0; j < 32; ++j)
+              if (j < ncol) f[j] += r[j];
           }
         }
-        const size_t doff = (size_t)row * p.ldd + n0 + c0;
-        if (d_bf16) {
-          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
-          if (ncol == 32 && vec_ok) {
+        if (fast && !d_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 t;
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
-              t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(o + j) = t;
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          __syncwarp();
+          const int sub = lane >> 3, piece = lane & 7;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + sub;
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
+            const int grow = m0 + quarter * 32 + rr;
+            if (grow < p.m) {
+              if (res_late) {
+                float4 t;
+                if (have_now) t = rnow[it];
+                else t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)grow * p.ldr + n0 + c0 + piece * 4);
+                o.x += t.x; o.y += t.y; o.z += t.z; o.w += t.w;
+              }
+              *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.d) + (size_t)grow * p.ldd + n0 + c0 + piece * 4) = o;
             }
-          } else {
+          }
+          __syncwarp();
+        } else if (fast) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 t;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[8 * j], f[8 * j + 1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[8 * j + 2], f[8 * j + 3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[8 * j + 4], f[8 * j + 5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[8 * j + 6], f[8 * j + 7]);
+            t.x = *reinterpret_cast<uint32_t*>(&h0); t.y = *reinterpret_cast<uint32_t*>(&h1);
+            t.z = *reinterpret_cast<uint32_t*>(&h2); t.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) = t;
+          }
+          __syncwarp();
+          const int sub = lane >> 2, piece = lane & 3;
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + sub;
+            const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
+            const int grow = m0 + quarter * 32 + rr;
+            if (grow < p.m) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)grow * p.ldd + n0 + c0 + piece * 8) = o;
+          }
+          __syncwarp();
+        } else if (row_ok) {
+          const size_t doff = (size_t)row * p.ldd + n0 + c0;
+          if (d_bf16) {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.d) + doff;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < ncol) o[j] = __float2bfloat16_rn(f[j]);
-          }
-        } else {
-          float* o = reinterpret_cast<float*>(p.d) + doff;
-          if (ncol == 32 && vec_ok) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
           } else {
+            float* o = reinterpret_cast<float*>(p.d) + doff;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
               if (j < ncol) o[j] = f[j];
@@ -472,7 +620,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       if (!released) {   // no column chunk fell to this warp (narrow last n-block)
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+        if (lane == 0) {
+          if constexpr (PAIR) mbar_arrive_cluster(map_to_cta(tmem_empty_bar(acc), 0));
+          else mbar_arrive(tmem_empty_bar(acc));
+        }
       }
     }
   }
@@ -481,7 +632,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   if constexpr (CM > 1) cluster_sync_all();   // no CTA exits while its peer may still multicast into it
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
   }
 }
 
@@ -527,16 +679,17 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, 
   return NLV_OK;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int CM>
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE>
 int launch(const nlv_gemm_args& g, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, MODE>;
+  constexpr int CM = MODE == 0 ? 1 : 2;
   CUtensorMap ta, tb;
   int rc;
   if (A_MN) rc = make_tmap(&ta, g.a, g.k, g.m, g.lda, 64, BLOCK_K);
   else      rc = make_tmap(&ta, g.a, g.m, g.k, g.lda, BLOCK_K, BLOCK_M);
   if (rc != NLV_OK) return rc;
   if (B_MN) rc = make_tmap(&tb, g.b, g.k, g.n, g.ldb, 64, BLOCK_K);
-  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N / CM);
+  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N / CM);   // MODE 1: the half this CTA multicasts; MODE 2: the half it stages
   if (rc != NLV_OK) return rc;
   Params p;
   p.d = g.d; p.bias = g.bias; p.residual = g.residual;
@@ -564,7 +717,7 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
       { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, stream); if (zrc != NLV_OK) return zrc; }
     }
   }
-  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, CM>;
+  auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
     NLV_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -592,12 +745,12 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   return NLV_OK;
 }
 
-template <int BLOCK_N, int CM>
+template <int BLOCK_N, int MODE>
 int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
-  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false, CM>(g, s);
-  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_MN) return launch<BLOCK_N, false, true, CM>(g, s);
-  if (g.a_major == NLV_MAJOR_MN && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, true, false, CM>(g, s);
-  return launch<BLOCK_N, true, true, CM>(g, s);
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false, MODE>(g, s);
+  if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_MN) return launch<BLOCK_N, false, true, MODE>(g, s);
+  if (g.a_major == NLV_MAJOR_MN && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, true, false, MODE>(g, s);
+  return launch<BLOCK_N, true, true, MODE>(g, s);
 }
 
 }  // namespace
@@ -605,11 +758,15 @@ int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
 int gemm_tc(const nlv_gemm_args& g, cudaStream_t stream) {
   NLV_CHECK_ARG(((uintptr_t)g.a & 15) == 0 && ((uintptr_t)g.b & 15) == 0, "gemm(bf16): a and b must be 16-byte aligned");
   NLV_CHECK_ARG((g.lda & 7) == 0 && (g.ldb & 7) == 0, "gemm(bf16): lda=%d and ldb=%d must be multiples of 8", g.lda, g.ldb);
-  // pairs of CTAs sharing a multicast B tile whenever there are at least two row tiles (NLV_GEMM_CLUSTER=1 disables)
-  static const int cluster_ok = [] { const char* e = getenv("NLV_GEMM_CLUSTER"); return e == nullptr || atoi(e) != 1; }();
-  const bool pair = cluster_ok && g.m > BLOCK_M;
-  if (g.n > 128) return pair ? dispatch_major<256, 2>(g, stream) : dispatch_major<256, 1>(g, stream);
-  return pair ? dispatch_major<128, 2>(g, stream) : dispatch_major<128, 1>(g, stream);
+  // at least two row tiles: CTA pairs running cta_group::2 MMAs (NLV_GEMM_CLUSTER=2: the cta_group::1 kernel with a multicast
+  // B tile instead; =1: single CTAs)
+  static const int mode_env = [] { const char* e = getenv("NLV_GEMM_CLUSTER"); const int v = e == nullptr ? 0 : atoi(e); return v == 1 ? 0 : (v == 2 ? 1 : 2); }();
+  // short reductions (k < 512: the 7x7 / 3x3-data-gradient convolutions) turn tiles over every few k-blocks; there the pair's
+  // cross-CTA hand-shakes cost more than its shared-memory savings (measured: 157 vs 107 and 472 vs 422 TFLOP/s)
+  int mode = g.m > BLOCK_M ? mode_env : 0;
+  if (mode == 2 && g.k < 512) mode = 1;
+  if (g.n > 128) return mode == 2 ? dispatch_major<256, 2>(g, stream) : mode == 1 ? dispatch_major<256, 1>(g, stream) : dispatch_major<256, 0>(g, stream);
+  return mode == 2 ? dispatch_major<128, 2>(g, stream) : mode == 1 ? dispatch_major<128, 1>(g, stream) : dispatch_major<128, 0>(g, stream);
 }
 
 }  // namespace nlv

@@ -5,6 +5,8 @@
 // BatchNorm  : lib/sttran.py:43,49,340,344 (BatchNorm1d(4, m=0.001), BatchNorm1d(1024), BatchNorm2d(128/256, m=0.01)).
 //              The reference runs one video per step, so batch statistics are per video; `seg` holds the row
 //              offsets of each video inside a multi-video batch (nseg+1 entries).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace nlv {
@@ -295,6 +297,9 @@ int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const floa
                             int y2dt, float* mean, float* rstd, cudaStream_t s);
 int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
                                int cols, float* dx, void* dx2, int dx2dt, const nlv_dropout* drop, cudaStream_t s);
+int launch_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
+                               int cols, float* dx, void* dx2, int dx2dt, float* dw, float* db, float* dprev, const nlv_dropout* dr,
+                               cudaStream_t s);
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace nlv
 
@@ -339,6 +344,25 @@ int nlv_layernorm_bwd_drop(const float* dy, const float* x, const float* mean, c
   layernorm_bwd_param_kernel<<<grid, block, 0, STREAM>>>(dy, x, mean, rstd, rows, cols, dw, db);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
+}
+
+/* one pass: additionally accumulates colsum(dx2 as stored, before rounding) into dprev (nullable) — the bias gradient of the
+ * Linear layer in front of the residual sum.  cols % 8 == 0, cols <= 2048, 16-byte aligned rows. */
+int nlv_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,
+                            long long rows, int cols, float* dx, void* dx2, int dx2_dtype, float* dw, float* db, float* dprev,
+                            const nlv_dropout* drop, void* stream) {
+  NLV_CHECK_ARG(rows >= 0 && cols > 0 && cols <= 2048 && (cols & 7) == 0, "layernorm_bwd_fused: cols=%d unsupported", cols);
+  if (rows == 0) return NLV_OK;
+  NLV_CHECK_ARG(dy && x && mean && rstd && w && dw && db && (dx || dx2), "layernorm_bwd_fused: null pointer");
+  NLV_CHECK_ARG(al16(dy) && al16(x) && (dx == nullptr || al16(dx)) && (dx2 == nullptr || al16(dx2)), "layernorm_bwd_fused: 16-byte alignment");
+  static const bool two_pass = [] { const char* e = getenv("NLV_LN_BWD_FUSED"); return e != nullptr && e[0] == '0'; }();
+  if (two_pass) {   // debugging switch: the two-kernel form + a separate column sum
+    int rc = nlv_layernorm_bwd_drop(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, dw, db, drop, stream);
+    if (rc != NLV_OK || dprev == nullptr) return rc;
+    const bool masked = drop != nullptr && drop->thr16 != 0u && dx2 != nullptr;
+    return nlv_colsum(masked ? dx2 : (const void*)dx, masked ? dx2_dtype : NLV_F32, cols, rows, cols, nullptr, 1, dprev, stream);
+  }
+  return launch_layernorm_bwd_fused(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2_dtype, dw, db, dprev, drop, STREAM);
 }
 
 int nlv_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* w,

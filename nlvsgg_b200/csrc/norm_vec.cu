@@ -1,4 +1,6 @@
 // 16-byte vectorised variants of the segmented BatchNorm kernels (channels-last rows x C, C % 8 == 0).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -63,11 +65,16 @@ namespace {
 
 // per (segment, channel) sums: block (bx = min(C8,32) channel groups, by rows); grid (ceil(C8/bx), nseg, splits).
 // MODE 0: sum x, sum x^2 (forward statistics).  MODE 1: sum dy, sum dy*xhat (backward), optional ReLU mask by yout.
-template <int MODE>
-__global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const void* __restrict__ dy, int dydt, int lddy,
-                                  const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ seg,
-                                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
-                                  double* __restrict__ sums) {
+// BF: every input is bf16 (compile time) -> a row in flight is one uint4 per tensor; U rows are requested before the first
+// is unpacked.  A block walks a LONG row range (geometry below: ~4 blocks per SM in total), so the shared-memory reduction
+// and the double atomics at its end are amortised over thousands of rows; per-thread partials are fp32 over 16 x U rows,
+// folded into double.
+template <int MODE, bool BF, int U>
+__global__ void __launch_bounds__(256, 2)
+bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, const void* __restrict__ dy, int dydt, int lddy,
+                  const void* __restrict__ yout, int ydt, int ldy, const int* __restrict__ seg,
+                  const float* __restrict__ mean, const float* __restrict__ var, float eps, int C,
+                  double* __restrict__ sums) {
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
   const int C8 = C >> 3;
   const int s = blockIdx.y;
@@ -75,56 +82,52 @@ __global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, 
   const long long per = (e - a + gridDim.z - 1) / gridDim.z;
   const long long r0 = a + (long long)blockIdx.z * per, r1 = min(e, r0 + per);
   const bool active = c8 < C8 && r0 < r1;
-  float m[8], rs[8];
-  if (MODE == 1 && active) {
-#pragma unroll
-    for (int q = 0; q < 8; ++q) { m[q] = mean[(size_t)s * C + c8 * 8 + q]; rs[q] = rsqrtf(var[(size_t)s * C + c8 * 8 + q] + eps); }
-  }
-  // fp32 partials over short runs of rows, folded into double every 64 rows
   double d1[8], d2[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { d1[q] = 0.0; d2[q] = 0.0; }
   float f1[8], f2[8];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) { f1[q] = 0.f; f2[q] = 0.f; }
+  for (int q = 0; q < 8; ++q) { d1[q] = 0.0; d2[q] = 0.0; f1[q] = 0.f; f2[q] = 0.f; }
   int run = 0;
-  // U rows in flight per thread, loaded RAW (16 / 32 bytes) and unpacked after all loads were issued: a converting load
-  // inside the loop left one row outstanding per thread and the statistics pass at ~20% of the HBM rate
-  constexpr int U = 4;
   const bool relu_mask = MODE == 1 && yout != nullptr;
+  const int xd = BF ? NLV_BF16 : xdt, gd = BF ? NLV_BF16 : dydt, yd = BF ? NLV_BF16 : ydt;
   for (long long r = r0 + threadIdx.y; active && r < r1; r += (long long)blockDim.y * U) {
     R8 xr[U], gr[U], yr[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
-        xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + (size_t)c8 * 8);
-        if (MODE == 1) gr[u] = nv_ld8_raw(dy, dydt, (size_t)rr * lddy + (size_t)c8 * 8);
-        if (relu_mask) yr[u] = nv_ld8_raw(yout, ydt, (size_t)rr * ldy + (size_t)c8 * 8);
+        if (BF) {
+          xr[u].a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + (size_t)rr * ldx + (size_t)c8 * 8));
+          if (MODE == 1) gr[u].a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (size_t)rr * lddy + (size_t)c8 * 8));
+          if (relu_mask) yr[u].a = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(yout) + (size_t)rr * ldy + (size_t)c8 * 8));
+        } else {
+          xr[u] = nv_ld8_raw(x, xdt, (size_t)rr * ldx + (size_t)c8 * 8);
+          if (MODE == 1) gr[u] = nv_ld8_raw(dy, dydt, (size_t)rr * lddy + (size_t)c8 * 8);
+          if (relu_mask) yr[u] = nv_ld8_raw(yout, ydt, (size_t)rr * ldy + (size_t)c8 * 8);
+        }
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long rr = r + (long long)u * blockDim.y;
       if (rr < r1) {
-        const V8 xv = nv_unpack(xr[u], xdt);
+        const V8 xv = nv_unpack(xr[u], xd);
         if (MODE == 0) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) { f1[q] += xv.v[q]; f2[q] = fmaf(xv.v[q], xv.v[q], f2[q]); }
         } else {
-          V8 g = nv_unpack(gr[u], dydt);
+          V8 g = nv_unpack(gr[u], gd);
           if (relu_mask) {
-            const V8 yo = nv_unpack(yr[u], ydt);
+            const V8 yo = nv_unpack(yr[u], yd);
 #pragma unroll
             for (int q = 0; q < 8; ++q)
               if (!(yo.v[q] > 0.f)) g.v[q] = 0.f;
           }
 #pragma unroll
-          for (int q = 0; q < 8; ++q) { f1[q] += g.v[q]; f2[q] = fmaf(g.v[q], (xv.v[q] - m[q]) * rs[q], f2[q]); }
+          for (int q = 0; q < 8; ++q) { f1[q] += g.v[q]; f2[q] = fmaf(g.v[q], xv.v[q], f2[q]); }   // sum dy * x: centred below
         }
       }
     }
-    if (++run == 4) {
+    if (++run == 16) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) { d1[q] += (double)f1[q]; d2[q] += (double)f2[q]; f1[q] = 0.f; f2[q] = 0.f; }
       run = 0;
@@ -132,6 +135,14 @@ __global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, 
   }
 #pragma unroll
   for (int q = 0; q < 8; ++q) { d1[q] += (double)f1[q]; d2[q] += (double)f2[q]; }
+  if (MODE == 1 && active) {   // sum dy * xhat = rstd * (sum dy * x - mean * sum dy), in double
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const double mq = (double)mean[(size_t)s * C + c8 * 8 + q];
+      const double rq = (double)rsqrtf(var[(size_t)s * C + c8 * 8 + q] + eps);
+      d2[q] = rq * (d2[q] - mq * d1[q]);
+    }
+  }
   // reduce over threadIdx.y in shared memory, then one double atomic per (segment, channel) per block
   __shared__ double red[256 * 8];
   for (int pass = 0; pass < 2; ++pass) {
@@ -139,9 +150,9 @@ __global__ void bn_sums_v8_kernel(const void* __restrict__ x, int xdt, int ldx, 
 #pragma unroll
     for (int q = 0; q < 8; ++q) mine[q] = pass == 0 ? d1[q] : d2[q];
     __syncthreads();
-    if (threadIdx.y == 0 && active) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) {
+    // thread (x, y) adds up channel q = y % 8 (+ 8 per further y group) of column group x over all rows of the tile
+    for (int q = threadIdx.y; q < 8; q += blockDim.y) {
+      if (c8 < C8) {
         double t = 0.0;
         for (int yy = 0; yy < blockDim.y; ++yy) t += red[(yy * blockDim.x + threadIdx.x) * 8 + q];
         atomicAdd(sums + ((size_t)s * 2 + pass) * C + c8 * 8 + q, t);
@@ -286,16 +297,20 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const
   }
 }
 
-void sums_geometry(int C, long long rows, int nseg, dim3& grid, dim3& block) {
+void sums_geometry(int C, long long rows, int nseg, int unroll, dim3& grid, dim3& block) {
   const int C8 = C >> 3;
   int bx = 1;
   while (bx < C8 && bx < 32) bx <<= 1;
   const int by = 256 / bx;
-  long long per_seg = nseg > 0 ? rows / nseg : rows;
-  int splits = (int)((per_seg + 32LL * by - 1) / (32LL * by));
+  const int gx = cdiv(C8, bx);
+  const long long per_seg = nseg > 0 ? rows / nseg : rows;
+  // ~4 blocks per SM over the whole grid; a block covers at least one unrolled sweep of its tile
+  long long splits = cdiv(4LL * sm_count(), (long long)gx * (nseg > 0 ? nseg : 1));
+  const long long max_splits = cdiv(per_seg, (long long)by * unroll);
+  if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   if (splits > 256) splits = 256;
-  grid = dim3(cdiv(C8, bx), nseg, splits);
+  grid = dim3(gx, nseg, (unsigned)splits);
   block = dim3(bx, by);
 }
 
@@ -303,16 +318,20 @@ void sums_geometry(int C, long long rows, int nseg, dim3& grid, dim3& block) {
 
 int launch_bn_sums_fwd_v8(const void* x, int xdt, int ld, const int* seg, int nseg, long long rows, int C, double* sums, cudaStream_t s) {
   dim3 grid, block;
-  sums_geometry(C, rows, nseg, grid, block);
-  bn_sums_v8_kernel<0><<<grid, block, 0, s>>>(x, xdt, ld, nullptr, 0, 0, nullptr, 0, 0, seg, nullptr, nullptr, 0.f, C, sums);
+  sums_geometry(C, rows, nseg, 8, grid, block);
+  if (xdt == NLV_BF16) bn_sums_v8_kernel<0, true, 8><<<grid, block, 0, s>>>(x, xdt, ld, nullptr, 0, 0, nullptr, 0, 0, seg, nullptr, nullptr, 0.f, C, sums);
+  else bn_sums_v8_kernel<0, false, 4><<<grid, block, 0, s>>>(x, xdt, ld, nullptr, 0, 0, nullptr, 0, 0, seg, nullptr, nullptr, 0.f, C, sums);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
 int launch_bn_sums_bwd_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy, const int* seg,
                           int nseg, const float* mean, const float* var, float eps, long long rows, int C, double* sums, cudaStream_t s) {
   dim3 grid, block;
-  sums_geometry(C, rows, nseg, grid, block);
-  bn_sums_v8_kernel<1><<<grid, block, 0, s>>>(x, xdt, ldx, dy, dydt, lddy, yout, ydt, ldy, seg, mean, var, eps, C, sums);
+  sums_geometry(C, rows, nseg, 4, grid, block);
+  if (xdt == NLV_BF16 && dydt == NLV_BF16 && (yout == nullptr || ydt == NLV_BF16))
+    bn_sums_v8_kernel<1, true, 4><<<grid, block, 0, s>>>(x, xdt, ldx, dy, dydt, lddy, yout, ydt, ldy, seg, mean, var, eps, C, sums);
+  else
+    bn_sums_v8_kernel<1, false, 2><<<grid, block, 0, s>>>(x, xdt, ldx, dy, dydt, lddy, yout, ydt, ldy, seg, mean, var, eps, C, sums);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }
@@ -475,6 +494,132 @@ layernorm_bwd_dx_v4_kernel(const float* __restrict__ dy, const float* __restrict
   }
 }
 
+
+// LayerNorm backward in ONE pass over dy and x (the two-kernel form read both twice: 22 bytes per element instead of 14):
+// dx (fp32), its operand copy dx2 (bf16 / fp32, optionally dropout-masked), dw, db AND the column sums of dx2 — the bias
+// gradient of the Linear layer that produced the normalised sum, which used to be a separate pass over dx.
+// Column-owner layout: thread t owns columns [8 t, 8 t + 8) for every row of the block's row range, so the three per-column
+// accumulators live in registers; the two per-row statistics (sum g, sum g * xhat) are block reductions, done for U rows at
+// a time behind one barrier (double-buffered scratch).  U rows x 64 bytes are in flight per thread.
+template <int U, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+layernorm_bwd_fused_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ mean,
+                           const float* __restrict__ rstd, const float* __restrict__ w, long long rows, int cols,
+                           long long rows_per_block, float* __restrict__ dx, void* __restrict__ dx2, int dx2dt,
+                           float* __restrict__ dw, float* __restrict__ db, float* __restrict__ dprev, const DropCfg drop) {
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int c0 = t * 8;
+  const bool active = c0 < cols;
+  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  __shared__ float red[2][8][2 * U];
+  float wv[8], aw[8], ab[8], ap[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { wv[q] = active ? w[c0 + q] : 0.f; aw[q] = 0.f; ab[q] = 0.f; ap[q] = 0.f; }
+  const float inv_cols = 1.f / (float)cols;
+  const int gpr = (cols + 7) >> 3;
+  int buf = 0;
+  for (long long r = r0; r < r1; r += U, buf ^= 1) {
+    float4 g0[U], g1[U], x0[U], x1[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u;
+      if (active && rr < r1) {
+        const float4* gp = reinterpret_cast<const float4*>(dy + (size_t)rr * cols + c0);
+        const float4* xp = reinterpret_cast<const float4*>(x + (size_t)rr * cols + c0);
+        g0[u] = __ldg(gp); g1[u] = __ldg(gp + 1); x0[u] = __ldg(xp); x1[u] = __ldg(xp + 1);
+      } else {
+        g0[u] = g1[u] = x0[u] = x1[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float mu[U], rs[U], s[2 * U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u < r1 ? r + u : r1 - 1;
+      mu[u] = __ldg(mean + rr); rs[u] = __ldg(rstd + rr);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float* xe = reinterpret_cast<float*>(&x0[u]);      // x0 / x1 become xhat in place
+      float* xf = reinterpret_cast<float*>(&x1[u]);
+      const float* ge = reinterpret_cast<const float*>(&g0[u]);
+      const float* gf = reinterpret_cast<const float*>(&g1[u]);
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        xe[q] = (xe[q] - mu[u]) * rs[u]; xf[q] = (xf[q] - mu[u]) * rs[u];
+        const float ga = ge[q] * wv[q], gb = gf[q] * wv[4 + q];
+        s1 += ga + gb;
+        s2 += ga * xe[q] + gb * xf[q];
+      }
+      if (!active) { s1 = 0.f; s2 = 0.f; }       // xhat of the zero-filled idle columns is not zero
+      s[2 * u] = s1; s[2 * u + 1] = s2;
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * U; ++k) s[k] = warp_sum(s[k]);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 2 * U; ++k) red[buf][warp][k] = s[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2 * U; ++k) {
+      float tot = 0.f;
+#pragma unroll
+      for (int wq = 0; wq < 8; ++wq) tot += red[buf][wq][k];
+      s[k] = tot * inv_cols;
+    }
+    if (!active) continue;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long rr = r + u;
+      if (rr >= r1) break;
+      const float* xe = reinterpret_cast<const float*>(&x0[u]);
+      const float* xf = reinterpret_cast<const float*>(&x1[u]);
+      const float* ge = reinterpret_cast<const float*>(&g0[u]);
+      const float* gf = reinterpret_cast<const float*>(&g1[u]);
+      float o[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        o[q] = rs[u] * (ge[q] * wv[q] - s[2 * u] - xe[q] * s[2 * u + 1]);
+        o[4 + q] = rs[u] * (gf[q] * wv[4 + q] - s[2 * u] - xf[q] * s[2 * u + 1]);
+        aw[q] = fmaf(ge[q], xe[q], aw[q]); aw[4 + q] = fmaf(gf[q], xf[q], aw[4 + q]);
+        ab[q] += ge[q]; ab[4 + q] += gf[q];
+      }
+      if (dx != nullptr) {
+        float4* op = reinterpret_cast<float4*>(dx + (size_t)rr * cols + c0);
+        op[0] = make_float4(o[0], o[1], o[2], o[3]); op[1] = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (drop.thr16 != 0u) {
+        const uint32_t keep = keep8_matrix(drop, rr, t, gpr);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) o[q] = ((keep >> q) & 1u) ? o[q] * drop.scale : 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) ap[q] += o[q];
+      if (dx2 != nullptr) {
+        if (dx2dt == NLV_BF16) {
+          uint4 pk;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) h[q] = __floats2bfloat162_rn(o[2 * q], o[2 * q + 1]);
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(dx2) + (size_t)rr * cols + c0) = pk;
+        } else {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(dx2) + (size_t)rr * cols + c0);
+          op[0] = make_float4(o[0], o[1], o[2], o[3]); op[1] = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      atomicAdd(dw + c0 + q, aw[q]);
+      atomicAdd(db + c0 + q, ab[q]);
+      if (dprev != nullptr) atomicAdd(dprev + c0 + q, ap[q]);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
@@ -494,6 +639,24 @@ int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mea
   if (cols <= 512) layernorm_bwd_dx_v4_kernel<4><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
   else if (cols <= 1024) layernorm_bwd_dx_v4_kernel<8><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
   else layernorm_bwd_dx_v4_kernel<16><<<grid, 128, 0, s>>>(dy, x, mean, rstd, w, rows, cols, dx, dx2, dx2dt, d);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int launch_layernorm_bwd_fused(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
+                               int cols, float* dx, void* dx2, int dx2dt, float* dw, float* db, float* dprev, const nlv_dropout* dr,
+                               cudaStream_t s) {
+  DropCfg d = drop_off();
+  if (dr != nullptr && dr->thr16 != 0u) { d.thr16 = dr->thr16; d.scale = dr->scale; d.seed_lo = dr->seed_lo; d.seed_hi = dr->seed_hi; d.stream = dr->stream; }
+  // two blocks of U = 2 rows per SM (NLV_LN_BWD_U=4: one block of 4 rows; measured alternative)
+  static const int u4 = [] { const char* e = getenv("NLV_LN_BWD_U"); return e != nullptr && atoi(e) == 4; }();
+  const int U = u4 ? 4 : 2;
+  long long blocks = (u4 ? 1LL : 2LL) * sm_count();
+  long long per = (rows + blocks - 1) / blocks;
+  per = (per + U - 1) / U * U;
+  blocks = (rows + per - 1) / per;
+  if (u4) layernorm_bwd_fused_kernel<4, 1><<<(unsigned)blocks, 256, 0, s>>>(dy, x, mean, rstd, w, rows, cols, per, dx, dx2, dx2dt, dw, db, dprev, d);
+  else layernorm_bwd_fused_kernel<2, 2><<<(unsigned)blocks, 256, 0, s>>>(dy, x, mean, rstd, w, rows, cols, per, dx, dx2, dx2dt, dw, db, dprev, d);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -300,6 +300,7 @@ int nlv_session::mm(const T& a_in, int am, const T& b_in, int bm, const T& out, 
 int nlv_session::lin_grads(const T& dy_op, const T& x_op, const T& dy_bias, int wslot, int bslot) {
   const T gw = mk(G(wslot), NLV_F32, dy_op.cols, x_op.cols);
   CK(mm(dy_op, MN_, x_op, MN_, gw));
+  if (bslot < 0) return NLV_OK;       // the bias gradient was accumulated by the kernel that produced dy (fused LayerNorm backward)
   g_next_units = (double)dy_bias.rows * dy_bias.cols * dy_bias.esz();
   RUN(nlv_colsum(dy_bias.p, dy_bias.dt, dy_bias.ld, dy_bias.rows, dy_bias.cols, nullptr, 1, G(bslot), st));
   return NLV_OK;
@@ -360,10 +361,10 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
   // dy2 = gradient of the residual stream; dy2op = its copy behind the FFN-output dropout (mask * dy2 / (1 - p) when dropping)
-  RUN(nlv_layernorm_bwd_drop(dx2.f(), c.y2.f(), c.m2.f(), c.r2.f(), P(LS(layer, NLV_L_NORMB_W)), Mr, D, dy2.f(), b16 ? dy2op.p : nullptr,
-                             NLV_BF16, G(LS(layer, NLV_L_NORMB_W)), G(LS(layer, NLV_L_NORMB_B)), &d2, st));
+  RUN(nlv_layernorm_bwd_fused(dx2.f(), c.y2.f(), c.m2.f(), c.r2.f(), P(LS(layer, NLV_L_NORMB_W)), Mr, D, dy2.f(), b16 ? dy2op.p : nullptr,
+                              NLV_BF16, G(LS(layer, NLV_L_NORMB_W)), G(LS(layer, NLV_L_NORMB_B)), G(LS(layer, NLV_L_LIN2_B)), &d2, st));
   const T& dy2o = b16 ? dy2op : dy2;
-  CK(lin_grads(dy2o, c.h, dropping ? dy2o : dy2, LS(layer, NLV_L_LIN2_W), LS(layer, NLV_L_LIN2_B)));
+  CK(lin_grads(dy2o, c.h, dy2, LS(layer, NLV_L_LIN2_W), -1));
   T dh = tmp(Mr, DFF, AD);
   CK(mm(dy2o, K_, W(LS(layer, NLV_L_LIN2_W), D, DFF), MN_, dh, nullptr, nullptr, false, &c.h, false, nullptr,
         dropping ? d1.scale : 1.f));   // ReLU (+ inner dropout) backward fused: h > 0 <=> kept and active
@@ -373,10 +374,10 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   T dy1 = tmp(Mr, D, NLV_F32), dy1op = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
-  RUN(nlv_layernorm_bwd_drop(dx1.f(), c.y1.f(), c.m1.f(), c.r1.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy1.f(), b16 ? dy1op.p : nullptr,
-                             NLV_BF16, G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), &d0, st));
+  RUN(nlv_layernorm_bwd_fused(dx1.f(), c.y1.f(), c.m1.f(), c.r1.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy1.f(), b16 ? dy1op.p : nullptr,
+                              NLV_BF16, G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), G(LS(layer, NLV_L_OUTPROJ_B)), &d0, st));
   const T& dy1o = b16 ? dy1op : dy1;
-  CK(lin_grads(dy1o, c.o, dropping ? dy1o : dy1, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
+  CK(lin_grads(dy1o, c.o, dy1, LS(layer, NLV_L_OUTPROJ_W), -1));
   T d_o = tmp(Mr, D, AD);
   CK(mm(dy1o, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), MN_, d_o));
   T dqkv = tmp(Mr, 3 * D, AD), delta = tmp(Mr * HEADS, 1, NLV_F32);
@@ -453,10 +454,10 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   T dy = tmp(Mr, D, NLV_F32), dyop = b16 ? tmp(Mr, D, NLV_BF16) : T();
   OOM_CHECK();
   g_next_units = (double)Mr * D * (4 + 4 + 4 + (b16 ? 2 : 0));
-  RUN(nlv_layernorm_bwd_drop(dt.f(), c.y.f(), c.m3.f(), c.r3.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy.f(), b16 ? dyop.p : nullptr, NLV_BF16,
-                             G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), &d0, st));
+  RUN(nlv_layernorm_bwd_fused(dt.f(), c.y.f(), c.m3.f(), c.r3.f(), P(LS(layer, NLV_L_NORMA_W)), Mr, D, dy.f(), b16 ? dyop.p : nullptr, NLV_BF16,
+                              G(LS(layer, NLV_L_NORMA_W)), G(LS(layer, NLV_L_NORMA_B)), G(LS(layer, NLV_L_OUTPROJ_B)), &d0, st));
   const T& dyo = b16 ? dyop : dy;
-  CK(lin_grads(dyo, c.o, dropping ? dyo : dy, LS(layer, NLV_L_OUTPROJ_W), LS(layer, NLV_L_OUTPROJ_B)));
+  CK(lin_grads(dyo, c.o, dy, LS(layer, NLV_L_OUTPROJ_W), -1));
   T d_o = tmp(Mr, D, AD);
   CK(mm(dyo, K_, W(LS(layer, NLV_L_OUTPROJ_W), D, D), MN_, d_o));
   T dqkv = tmp(Mr, 3 * D, AD), delta = tmp(Mr * HEADS, 1, NLV_F32);

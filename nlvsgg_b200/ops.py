@@ -289,6 +289,20 @@ def layernorm_bwd(dy, x, mean, rstd, w, dx2_dtype=None, drop=None):
     return dx, dx2, dw, db
 
 
+def layernorm_bwd_fused(dy, x, mean, rstd, w, dx2_dtype=None, drop=None, want_dprev=True):
+    """One-pass backward: -> (dx, dx2, dw, db, dprev) with dprev = column sums of the dx2 values (bias gradient of the Linear in
+    front of the residual sum)."""
+    rows, cols = x.shape
+    dx = torch.empty_like(x)
+    dx2 = torch.empty(rows, cols, device=x.device, dtype=dx2_dtype) if dx2_dtype is not None else None
+    dw = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    db = torch.zeros(cols, device=x.device, dtype=torch.float32)
+    dprev = torch.zeros(cols, device=x.device, dtype=torch.float32) if want_dprev else None
+    _call("nlv_layernorm_bwd_fused", _ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(w), _LL(rows), cols, _ptr(dx), _ptr(dx2),
+          _dt(dx2) if dx2 is not None else 0, _ptr(dw), _ptr(db), _ptr(dprev), ctypes.byref(drop) if drop is not None else None)
+    return dx, dx2, dw, db, dprev
+
+
 def dropout_apply(src, drop, out_dtype=None, out=None):
     rows, cols = src.shape
     if out is None:

@@ -45,4 +45,41 @@ def pipe(n):
 pipe(3)
 torch.cuda.synchronize(); t0 = time.perf_counter(); pipe(8); torch.cuda.synchronize()
 print("pipelined per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
+def pipe2(n):
+    """compute of step i enqueued BEFORE the host prepares / enqueues the copies of step i+1"""
+    nxt = tr.prefetch(host)
+    for i in range(n):
+        b, plan, ev = nxt
+        torch.cuda.current_stream().wait_event(ev)
+        tr.forward_backward(b, plan)
+        tr.optimizer_step()
+        tk = tr.last_ticket
+        nxt = tr.prefetch(host) if i + 1 < n else None
+        tr.loss_value(tk)
+pipe2(3)
+torch.cuda.synchronize(); t0 = time.perf_counter(); pipe2(8); torch.cuda.synchronize()
+print("compute-first pipelined per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
+def pipe3(n):
+    """lagged loss read, current ordering"""
+    nxt = tr.prefetch(host); tk = None
+    for i in range(n):
+        l, nxt = tr.step_pipelined(nxt, host if i + 1 < n else None)
+        if tk is not None: tr.loss_value(tk)
+        tk = tr.last_ticket
+    tr.loss_value(tk)
+pipe3(3)
+torch.cuda.synchronize(); t0 = time.perf_counter(); pipe3(8); torch.cuda.synchronize()
+print("lagged-loss pipelined per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
+def pipe4(n):
+    """no copies at all: the loop overhead alone"""
+    tk = None
+    for i in range(n):
+        bb = M.Batch(); bb.__dict__.update(res.__dict__)
+        tr.step(bb)
+        if tk is not None: tr.loss_value(tk)
+        tk = tr.last_ticket
+    tr.loss_value(tk)
+pipe4(3)
+torch.cuda.synchronize(); t0 = time.perf_counter(); pipe4(8); torch.cuda.synchronize()
+print("resident loop with lagged loss per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
 print("mem allocated %.1f GB reserved %.1f GB" % (torch.cuda.memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9))
