@@ -260,9 +260,10 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
                 "ms_per_step": ms, "algorithmic_bytes_per_step": by}
     extra = {
         "gather_union_rows": hbm(("nlv_union_unpack", "nlv_nchw_to_rows"), 2.0 * n_stored_values),
-        "attention_fwd": hbm(("nlv_attn_fwd",)),
-        "attention_bwd": hbm(("nlv_attn_bwd",)),
-        "layernorm": hbm(("nlv_layernorm_fwd", "nlv_layernorm_bwd")),
+        "attention_fwd": hbm(("nlv_attn_fwd", "nlv_attn_fwd_drop", "nlv_attn_fwd_padkeys")),
+        "attention_bwd": hbm(("nlv_attn_bwd", "nlv_attn_bwd_drop")),
+        "layernorm": hbm(("nlv_layernorm_fwd", "nlv_layernorm_bwd", "nlv_layernorm_bwd_drop", "nlv_layernorm_bwd_fused")),
+        "batchnorm": hbm(("nlv_bn_stats", "nlv_bn_apply", "nlv_bn_bwd")),
         "bias_grad_colsum": hbm(("nlv_colsum",)),
     }
     if adamw_ms:
@@ -566,10 +567,13 @@ def main():
         trainer.step_from_host(hb).item()
         barrier()
         ev0.record()
-        nxt = trainer.prefetch(hb)
+        depth = int(os.environ.get("NLV_BENCH_PREFETCH", "2"))
+        queue = [trainer.prefetch(hb) for _ in range(min(depth, a.steps))]    # copies run up to two steps ahead of the compute
         ticket = None
         for i in range(a.steps):
-            loss_t, nxt = trainer.step_pipelined(nxt, hb if i + 1 < a.steps else None)
+            loss_t, _ = trainer.step_pipelined(queue.pop(0), None)            # step i is enqueued first ...
+            if i + depth < a.steps:
+                queue.append(trainer.prefetch(hb))                            # ... then the copies of step i+2 (behind those of i+1)
             if ticket is not None:
                 lv = trainer.loss_value(ticket)      # step i-1's loss (its own D2H copy), read while step i runs
             ticket = trainer.last_ticket
@@ -585,7 +589,7 @@ def main():
     if not a.no_e2e:
         ems, lv = e2e_loop(host)
         e2e = {"value": total_frames / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-               "ms_per_step": ems, "last_loss": lv, "input_pipelining": "H2D of step i+1 overlaps compute of step i (side stream)",
+               "ms_per_step": ems, "last_loss": lv, "input_pipelining": "H2D copies run up to two steps ahead of the compute on a side stream; each loss is read one step late from its own pinned copy",
                "host_format": in_fmt, "cpu_binding": numa,
                "h2d_gb_per_s_if_copy_bound": h2d_bytes / ems / 1e6}
     sampler.stop_flag = True

@@ -435,6 +435,11 @@ int nlv_session_forward(nlv_session* s, const nlv_model* model, const nlv_batch*
 int nlv_session_set_gradients(nlv_session* s, float* grad_base, long long grad_elems, const long long* grad_offset, int n_slots);
 /* gradients of every parameter into model->grad_base; d26 / dobj NULL -> the loss's own gradients (NLV_RUN_LOSS) */
 int nlv_session_backward(nlv_session* s, const float* d26, const float* dobj, void* stream);
+/* fn(user) is called from inside nlv_session_backward, on the calling thread, right after the last kernel that writes a gradient
+ * of the temporal-decoder (STTran) / global (DSG-DETR) layers has been enqueued — those layers are the tail of the gradient
+ * buffer, so a data-parallel caller can start their all-reduce on another stream while the rest of the backward pass runs
+ * (bucketed and overlapped).  NULL removes the hook. */
+int nlv_session_set_tail_hook(nlv_session* s, void (*fn)(void*), void* user);
 /* standalone spatio-temporal transformer (lib/transformer_wk.py:130-217 forward(features, im_idx)) over the same
  * session machinery: only the layer slots and NLV_P_POS of `model` are read; x f32[R,1936] -> *out f32[R,1936] (in the
  * workspace).  workspace == NULL: dry run, returns the workspace bytes needed (with NLV_RUN_BACKWARD: backward included) */

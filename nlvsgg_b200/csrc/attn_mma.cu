@@ -14,6 +14,9 @@
 // by moving Q/K/V/dO once (HBM), and mma.sync on 16-row tiles already makes the arithmetic a small fraction of the copy time.
 // Replaces torch.nn.MultiheadAttention's core (lib/transformer.py:9-13,38-42, lib/dsg_detr.py:21-22) with
 // key_padding_mask semantics folded into the segment bounds.
+#include <initializer_list>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "philox.cuh"
 
@@ -26,6 +29,8 @@ constexpr int ROWB = KP * 2;       // 528 bytes
 constexpr int TILE_B = 16 * ROWB;  // 8448 bytes: one 16-row tile
 constexpr int NT = 32;             // 8-column output tiles covering 256 columns
 
+struct Lead { int lw; bool wide; };
+
 struct MArgs {
   const bf16 *q, *k, *v;
   int ldq, ldk, ldv;
@@ -33,7 +38,15 @@ struct MArgs {
   float scale;
   const int4* work;
   DropCfg drop;     // dropout on the attention weights (nn.MultiheadAttention(dropout=0.1), lib/transformer.py:9,38)
+  int skip_short;   // backward: segments of <= 16 rows are taken by the fused single-tile kernel; the two-kernel path skips them
+  int wide;         // every pointer / row stride / slice width is 16-byte aligned: tiles hold aligned supersets, 16-byte copies
 };
+__device__ __forceinline__ Lead lead_of(const MArgs& a, int col0) {
+  Lead le;
+  le.wide = a.wide != 0;
+  le.lw = le.wide ? (int)(((unsigned)col0 * 2u) & 15u) >> 2 : 0;
+  return le;
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
@@ -67,17 +80,41 @@ __device__ __forceinline__ float quad_sum(float x) {
   return x + __shfl_xor_sync(0xffffffffu, x, 2);
 }
 
-// zero the padding words 121..127 (columns hd..255) of a 16-row tile; done once per tile buffer (copies never touch them)
-__device__ __forceinline__ void zero_pad(uint32_t tile, int nwords, int lane) {
-  const int npad = 128 - nwords;
+// Tile layout with 16-byte copies: a head slice starts 4 * (h % 4) bytes past a 16-byte boundary of its row (484-byte
+// slices), so the tile holds the 16-byte ALIGNED superset of the slice: logical word w of the head sits at tile word w + lw
+// (lw = lead words, 0..3) and one cp.async.16 per lane moves a whole row (31 chunks) instead of four 4-byte copies.  The
+// words in front of / behind the slice inside the first / last chunk belong to the neighbouring heads: they are zeroed
+// after the copy in the K and V tiles (`fix_junk`) — every product contracting over the columns has K or V as one operand
+// — and are never stored.  lw = 0 with 4-byte copies when the pointers / strides are not 16-byte aligned.
+
+// zero the words outside [lw, lw + nwords) of a 16-row tile that copies never touch (lw + nwords rounded up to a chunk .. 127)
+__device__ __forceinline__ void zero_pad(uint32_t tile, int nwords, int lane, Lead ld = Lead{0, false}) {
+  const int first = ld.wide ? ((ld.lw + nwords + 3) & ~3) : nwords;
+  const int npad = 128 - first;
   for (int i = lane; i < 16 * npad; i += 32) {
-    const int r = i / npad, w = nwords + i % npad;
+    const int r = i / npad, w = first + i % npad;
     asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + r * ROWB + w * 4), "r"(0u) : "memory");
   }
 }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 // rows [first, first + cnt) of `src` (already offset to the head's first column) -> tile rows [r0, r0 + nr); rows >= cnt are zeroed
 __device__ __forceinline__ void load_rows(uint32_t tile, const bf16* src, int ld, long long first, int cnt, int r0, int nr, int nwords,
-                                          int lane) {
+                                          int lane, Lead le = Lead{0, false}) {
+  if (le.wide) {
+    const int nchunks = (le.lw + nwords + 3) >> 2;      // 16-byte chunks of the aligned superset (31 for 242-wide heads)
+    for (int r = r0; r < r0 + nr; ++r) {
+      const uint32_t dst = tile + r * ROWB;
+      if (r < cnt) {
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(src + (size_t)(first + r) * ld) - 4 * le.lw;
+        if (lane < nchunks) cp_async16(dst + lane * 16, s + lane * 16);
+      } else if (lane < nchunks) {
+        asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst + lane * 16), "r"(0u) : "memory");
+      }
+    }
+    return;
+  }
   for (int r = r0; r < r0 + nr; ++r) {
     const uint32_t dst = tile + r * ROWB;
     if (r < cnt) {
@@ -96,9 +133,43 @@ __device__ __forceinline__ void load_rows(uint32_t tile, const bf16* src, int ld
     }
   }
 }
-// coalesced copy of tile rows [0, cnt) (first nwords words) to global rows
+// after the copies of a K / V tile have landed: zero the neighbouring heads' words inside the first and last chunk
+__device__ __forceinline__ void fix_junk(uint32_t tile, int nwords, int lane, Lead le, int r0 = 0, int nr = 16) {
+  if (!le.wide) return;
+  const int tail0 = le.lw + nwords, tail1 = (tail0 + 3) & ~3;
+  const int per = le.lw + (tail1 - tail0);               // junk words per row (0..6)
+  for (int i = lane; i < nr * per; i += 32) {
+    const int r = r0 + i / per, j = i % per;
+    const int w = j < le.lw ? j : tail0 + (j - le.lw);
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + r * ROWB + w * 4), "r"(0u) : "memory");
+  }
+}
+// coalesced copy of tile rows [0, cnt) (the head's nwords words) to global rows
 __device__ __forceinline__ void store_rows(uint32_t tile, bf16* dst, int ld, long long first, int cnt, int nwords, int lane, int r0 = 0,
-                                           int rstep = 1) {
+                                           int rstep = 1, Lead le = Lead{0, false}) {
+  if (le.wide) {
+    const int w0 = lane * 4;                              // this lane's chunk: tile words w0 .. w0 + 3
+    const int lo = le.lw, hi = le.lw + nwords;            // the head's words
+    for (int r = r0; r < cnt; r += rstep) {
+      uint8_t* d = reinterpret_cast<uint8_t*>(dst + (size_t)(first + r) * ld) - 4 * le.lw;
+      if (w0 >= lo && w0 + 4 <= hi) {
+        uint32_t v0, v1, v2, v3;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v0), "=r"(v1), "=r"(v2), "=r"(v3) : "r"(tile + r * ROWB + w0 * 4));
+        *reinterpret_cast<uint4*>(d + w0 * 4) = make_uint4(v0, v1, v2, v3);
+      } else if (w0 < hi && w0 + 4 > lo) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int w = w0 + j;
+          if (w >= lo && w < hi) {
+            uint32_t v;
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(tile + r * ROWB + w * 4));
+            *reinterpret_cast<uint32_t*>(d + w * 4) = v;
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int r = r0; r < cnt; r += rstep) {
     bf16* d = dst + (size_t)(first + r) * ld;
 #pragma unroll
@@ -163,8 +234,9 @@ attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ 
   const long long seg0 = w.x;
   const int L = w.y, q0 = w.z, nq = min(16, L - q0);
   const uint32_t Qs = smem_addr(smem) + warp * 3 * TILE_B, Ks = Qs + TILE_B, Vs = Ks + TILE_B;
-  zero_pad(Qs, nwords, lane); zero_pad(Ks, nwords, lane); zero_pad(Vs, nwords, lane);
-  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane);
+  const Lead le = lead_of(a, col0);
+  zero_pad(Qs, nwords, lane, le); zero_pad(Ks, nwords, lane, le); zero_pad(Vs, nwords, lane, le);
+  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane, le);
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float acc[NT][4];
@@ -173,10 +245,11 @@ attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ 
   for (int k0 = 0; k0 < L; k0 += 16) {
     const int nk = min(16, L - k0);
     if (k0 > 0) __syncwarp();
-    load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane);
-    load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane);
+    load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane, le);
+    load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane, le);
     cp_async_wait_all();
     __syncwarp();
+    if (le.wide) { fix_junk(Ks, nwords, lane, le); __syncwarp(); }      // V only feeds output columns here: its junk is never stored
     float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     qk_product(Qs, Ks, lane, s);
     float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -219,7 +292,7 @@ attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ 
   __syncwarp();
   acc_to_tile<NT>(Qs, lane, 0, acc, 1.f / l0, 1.f / l1);   // the Q tile is dead: reuse it to transpose the output for row-contiguous stores
   __syncwarp();
-  store_rows(Qs, o + col0, ldo, seg0 + q0, nq, nwords, lane);
+  store_rows(Qs, o + col0, ldo, seg0 + q0, nq, nwords, lane, 0, 1, le);
   if (lse != nullptr && t == 0) {
     if (g < nq) lse[(seg0 + q0 + g) * a.heads + h] = m0 + __logf(l0);
     if (g + 8 < nq) lse[(seg0 + q0 + g + 8) * a.heads + h] = m1 + __logf(l1);
@@ -239,10 +312,12 @@ attn_bwd_dq_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const f
   const int h = (blockIdx.x % hgroups) * 2 + warp, col0 = h * a.hd, nwords = a.hd >> 1;
   const long long seg0 = w.x;
   const int L = w.y, q0 = w.z, nq = min(16, L - q0);
+  if (a.skip_short && L <= 16) return;
   const uint32_t Qs = smem_addr(smem) + warp * 4 * TILE_B, Gs = Qs + TILE_B, Ks = Gs + TILE_B, Vs = Ks + TILE_B;
-  zero_pad(Qs, nwords, lane); zero_pad(Gs, nwords, lane); zero_pad(Ks, nwords, lane); zero_pad(Vs, nwords, lane);
-  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane);
-  load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, 0, 16, nwords, lane);
+  const Lead le = lead_of(a, col0);
+  zero_pad(Qs, nwords, lane, le); zero_pad(Gs, nwords, lane, le); zero_pad(Ks, nwords, lane, le); zero_pad(Vs, nwords, lane, le);
+  load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, 0, 16, nwords, lane, le);
+  load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, 0, 16, nwords, lane, le);
   const long long r0 = seg0 + q0 + g, r1 = r0 + 8;
   const float ls0 = g < nq ? lse[r0 * a.heads + h] : 0.f, ls1 = g + 8 < nq ? lse[r1 * a.heads + h] : 0.f;
 
@@ -260,10 +335,11 @@ attn_bwd_dq_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const f
       const int nk = min(16, L - k0);
       if (!first_load) __syncwarp();
       first_load = false;
-      load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane);
-      load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane);
+      load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nk, 0, 16, nwords, lane, le);
+      load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nk, 0, 16, nwords, lane, le);
       cp_async_wait_all();
       __syncwarp();
+      if (le.wide) { fix_junk(Ks, nwords, lane, le); fix_junk(Vs, nwords, lane, le); __syncwarp(); }
       float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
       qk_product(Qs, Ks, lane, s);
       qk_product(Gs, Vs, lane, dp);
@@ -302,7 +378,7 @@ attn_bwd_dq_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const f
   __syncwarp();
   acc_to_tile<NT>(Qs, lane, 0, acc, a.scale, a.scale);
   __syncwarp();
-  store_rows(Qs, dq + col0, lddq, seg0 + q0, nq, nwords, lane);
+  store_rows(Qs, dq + col0, lddq, seg0 + q0, nq, nwords, lane, 0, 1, le);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -319,11 +395,13 @@ attn_bwd_dkv_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const 
   const int h = blockIdx.x % a.heads, col0 = h * a.hd, nwords = a.hd >> 1;
   const long long seg0 = w.x;
   const int L = w.y, k0 = w.z, nkeys = min(16, L - k0);
+  if (a.skip_short && L <= 16) return;
   const uint32_t Ks = smem_addr(smem), Vs = Ks + TILE_B, Qs = Vs + TILE_B, Gs = Qs + TILE_B;
   // each warp prepares / loads 8 rows of every tile
-  if (warp == 0) { zero_pad(Ks, nwords, lane); zero_pad(Qs, nwords, lane); } else { zero_pad(Vs, nwords, lane); zero_pad(Gs, nwords, lane); }
-  load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nkeys, warp * 8, 8, nwords, lane);
-  load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nkeys, warp * 8, 8, nwords, lane);
+  const Lead le = lead_of(a, col0);
+  if (warp == 0) { zero_pad(Ks, nwords, lane, le); zero_pad(Qs, nwords, lane, le); } else { zero_pad(Vs, nwords, lane, le); zero_pad(Gs, nwords, lane, le); }
+  load_rows(Ks, a.k + col0, a.ldk, seg0 + k0, nkeys, warp * 8, 8, nwords, lane, le);
+  load_rows(Vs, a.v + col0, a.ldv, seg0 + k0, nkeys, warp * 8, 8, nwords, lane, le);
 
   constexpr int NH = NT / 2;
   const int nt0 = warp * NH;
@@ -333,14 +411,15 @@ attn_bwd_dkv_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const 
   for (int q0 = 0; q0 < L; q0 += 16) {
     const int nq = min(16, L - q0);
     if (q0 > 0) __syncthreads();                      // both warps are done with the previous Q / dO tiles
-    load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, warp * 8, 8, nwords, lane);
-    load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, warp * 8, 8, nwords, lane);
+    load_rows(Qs, a.q + col0, a.ldq, seg0 + q0, nq, warp * 8, 8, nwords, lane, le);
+    load_rows(Gs, dout + col0, lddo, seg0 + q0, nq, warp * 8, 8, nwords, lane, le);
     if (threadIdx.x < 16) {
       const bool ok = (int)threadIdx.x < nq;
       lse_s[threadIdx.x] = ok ? lse[(seg0 + q0 + threadIdx.x) * a.heads + h] : 0.f;
       dl_s[threadIdx.x] = ok ? delta[(seg0 + q0 + threadIdx.x) * a.heads + h] : 0.f;
     }
     cp_async_wait_all();
+    if (le.wide && q0 == 0) { __syncwarp(); fix_junk(Ks, nwords, lane, le, warp * 8, 8); fix_junk(Vs, nwords, lane, le, warp * 8, 8); }   // own rows
     __syncthreads();
     float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
     qk_product(Ks, Qs, lane, s);      // S^T : rows = keys (g, g+8), columns = queries
@@ -372,8 +451,141 @@ attn_bwd_dkv_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const 
   acc_to_tile<NH>(Qs, lane, nt0, accK, a.scale, a.scale);   // Q / dO tiles are dead: transpose dK / dV through them
   acc_to_tile<NH>(Gs, lane, nt0, accV, 1.f, 1.f);
   __syncthreads();
-  store_rows(Qs, dk + col0, lddk, seg0 + k0, nkeys, nwords, lane, warp, 2);
-  store_rows(Gs, dv + col0, lddv, seg0 + k0, nkeys, nwords, lane, warp, 2);
+  store_rows(Qs, dk + col0, lddk, seg0 + k0, nkeys, nwords, lane, warp, 2, le);
+  store_rows(Gs, dv + col0, lddv, seg0 + k0, nkeys, nwords, lane, warp, 2, le);
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, segments of at most 16 rows (one tile: every frame and nearly every 2-frame window): ONE kernel reads Q, K, V
+// and dO once and writes dQ, dK, dV — the two-kernel form above reads all four tiles twice and passes delta through
+// memory.  CTA = 3 warps on one (segment, head) sharing the four tiles; each warp owns one output and recomputes the
+// 16 x 16 score products it needs in the orientation that makes its left operand an A fragment:
+//   warp 0: S, dP (rows = queries)   -> delta, dS   -> dQ = dS K
+//   warp 1: S^T, dP^T (rows = keys)  -> delta, dS^T -> dK = dS^T Q
+//   warp 2: S^T                      -> P^T         -> dV = P^T dO
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96, 3)
+attn_bwd_fused_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, const float* __restrict__ lse, bf16* __restrict__ dq, int lddq,
+                          bf16* __restrict__ dk, int lddk, bf16* __restrict__ dv, int lddv) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float lse_s[16];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int4 w = a.work[blockIdx.x / a.heads];
+  const int L = w.y;
+  if (L > 16) return;                                   // longer segments: the two-kernel path
+  const int h = blockIdx.x % a.heads, col0 = h * a.hd, nwords = a.hd >> 1;
+  const long long seg0 = w.x;
+  const uint32_t Qs = smem_addr(smem), Ks = Qs + TILE_B, Vs = Ks + TILE_B, Gs = Vs + TILE_B;
+  // warp w prepares / loads rows [r0, r0 + nr) of every tile
+  const int r0 = warp == 0 ? 0 : (warp == 1 ? 6 : 11), nr = warp == 0 ? 6 : 5;
+  const Lead le = lead_of(a, col0);
+  if (warp == 0) { zero_pad(Qs, nwords, lane, le); zero_pad(Ks, nwords, lane, le); } else if (warp == 1) zero_pad(Vs, nwords, lane, le); else zero_pad(Gs, nwords, lane, le);
+  load_rows(Qs, a.q + col0, a.ldq, seg0, L, r0, nr, nwords, lane, le);
+  load_rows(Ks, a.k + col0, a.ldk, seg0, L, r0, nr, nwords, lane, le);
+  load_rows(Vs, a.v + col0, a.ldv, seg0, L, r0, nr, nwords, lane, le);
+  load_rows(Gs, dout + col0, lddo, seg0, L, r0, nr, nwords, lane, le);
+  if (threadIdx.x < 16) lse_s[threadIdx.x] = (int)threadIdx.x < L ? lse[(seg0 + threadIdx.x) * a.heads + h] : 0.f;
+  cp_async_wait_all();
+  if (le.wide) { __syncwarp(); fix_junk(Ks, nwords, lane, le, r0, nr); fix_junk(Vs, nwords, lane, le, r0, nr); }   // own rows
+  __syncthreads();
+
+  float acc[NT][4];
+#pragma unroll
+  for (int i = 0; i < NT; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+  if (warp == 0) {
+    // rows = queries g, g + 8; columns = keys n * 8 + 2 t + (c & 1)
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    qk_product(Qs, Ks, lane, s);
+    qk_product(Gs, Vs, lane, dp);
+    const float ls0 = lse_s[g], ls1 = lse_s[g + 8];
+    if (a.drop.thr16 != 0u) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        const uint32_t kp0 = keep8_attn(a.drop, seg0 + g, a.heads, h, n) >> (2 * t);
+        const uint32_t kp1 = keep8_attn(a.drop, seg0 + g + 8, a.heads, h, n) >> (2 * t);
+        dp[n][0] = (kp0 & 1u) ? dp[n][0] * a.drop.scale : 0.f; dp[n][1] = (kp0 & 2u) ? dp[n][1] * a.drop.scale : 0.f;
+        dp[n][2] = (kp1 & 1u) ? dp[n][2] * a.drop.scale : 0.f; dp[n][3] = (kp1 & 2u) ? dp[n][3] * a.drop.scale : 0.f;
+      }
+    }
+    float e0 = 0.f, e1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int key = n * 8 + 2 * t + (c & 1);
+        s[n][c] = key < L ? __expf(s[n][c] * a.scale - (c < 2 ? ls0 : ls1)) : 0.f;      // P
+        if (c < 2) e0 = fmaf(s[n][c], dp[n][c], e0); else e1 = fmaf(s[n][c], dp[n][c], e1);
+      }
+    const float dl0 = quad_sum(e0), dl1 = quad_sum(e1);
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s[n][c] *= dp[n][c] - (c < 2 ? dl0 : dl1);               // dS
+    const uint32_t da[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
+    pv_product<NT>(da, Ks, lane, 0, acc);
+  } else {
+    // rows = keys g, g + 8; columns = queries n * 8 + 2 t + (c & 1)
+    float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dp[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    qk_product(Ks, Qs, lane, s);
+    if (warp == 1) qk_product(Vs, Gs, lane, dp);
+    float pd[2][4], e[2][2] = {{0.f, 0.f}, {0.f, 0.f}};      // e[n][c & 1]: per-query partial of sum_keys P dP
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int qi = n * 8 + 2 * t + (c & 1);
+        const int key = g + (c >> 1) * 8;
+        const float p = (qi < L && key < L) ? __expf(s[n][c] * a.scale - lse_s[qi]) : 0.f;
+        float pdv = p, dpv = dp[n][c];
+        if (a.drop.thr16 != 0u) {
+          const bool kept = (keep8_attn(a.drop, seg0 + qi, a.heads, h, key >> 3) >> (key & 7)) & 1u;
+          pdv = kept ? p * a.drop.scale : 0.f;
+          dpv = kept ? dpv * a.drop.scale : 0.f;
+        }
+        pd[n][c] = pdv;                       // dropped, rescaled weights: dV += P_dropped^T dO
+        s[n][c] = p;
+        dp[n][c] = dpv;
+        e[n][c & 1] = fmaf(p, dpv, e[n][c & 1]);
+      }
+    if (warp == 1) {
+      // delta of query qi = sum over the 16 keys: this thread holds keys g and g + 8; the other keys sit in the lanes that
+      // differ in g (lane bits 2..4)
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          float v = e[n][b];
+          v += __shfl_xor_sync(0xffffffffu, v, 4);
+          v += __shfl_xor_sync(0xffffffffu, v, 8);
+          v += __shfl_xor_sync(0xffffffffu, v, 16);
+          e[n][b] = v;
+        }
+#pragma unroll
+      for (int n = 0; n < 2; ++n)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) s[n][c] *= dp[n][c] - e[n][c & 1];                       // dS^T
+      const uint32_t da[4] = {pack2(s[0][0], s[0][1]), pack2(s[0][2], s[0][3]), pack2(s[1][0], s[1][1]), pack2(s[1][2], s[1][3])};
+      pv_product<NT>(da, Qs, lane, 0, acc);
+    } else {
+      const uint32_t pa[4] = {pack2(pd[0][0], pd[0][1]), pack2(pd[0][2], pd[0][3]), pack2(pd[1][0], pd[1][1]), pack2(pd[1][2], pd[1][3])};
+      pv_product<NT>(pa, Gs, lane, 0, acc);
+    }
+  }
+  __syncthreads();                                    // every warp has finished reading the four input tiles
+  // each warp transposes its output through a dead tile and stores whole rows
+  if (warp == 0) {
+    acc_to_tile<NT>(Qs, lane, 0, acc, a.scale, a.scale);
+    __syncwarp();
+    store_rows(Qs, dq + col0, lddq, seg0, L, nwords, lane, 0, 1, le);
+  } else if (warp == 1) {
+    acc_to_tile<NT>(Ks, lane, 0, acc, a.scale, a.scale);
+    __syncwarp();
+    store_rows(Ks, dk + col0, lddk, seg0, L, nwords, lane, 0, 1, le);
+  } else {
+    acc_to_tile<NT>(Vs, lane, 0, acc, 1.f, 1.f);
+    __syncwarp();
+    store_rows(Vs, dv + col0, lddv, seg0, L, nwords, lane, 0, 1, le);
+  }
 }
 
 template <typename K> int opt_in_smem(K kern, size_t bytes) {
@@ -388,6 +600,16 @@ bool attn_mma_supported(int hd, int heads, int ld_or) {
   return hd >= 16 && hd <= 256 && (hd & 1) == 0 && (heads & 3) == 0 && (ld_or & 1) == 0;
 }
 
+// 16-byte tile copies need every head-0 pointer and every row stride on a 16-byte boundary and a slice of all heads that ends
+// on one (then no aligned superset of a head leaves its row's slice).  NLV_ATTN_WIDE=0 forces the 4-byte copies.
+static int wide_ok(int hd, int heads, std::initializer_list<const void*> ptrs, std::initializer_list<int> lds) {
+  static const int env = [] { const char* e = getenv("NLV_ATTN_WIDE"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  if (!env || ((hd * heads * 2) & 15) != 0 || ((hd * 2) & 3) != 0) return 0;
+  for (const void* p : ptrs) if ((reinterpret_cast<uintptr_t>(p) & 15) != 0) return 0;
+  for (int ld : lds) if (((ld * 2) & 15) != 0) return 0;
+  return 1;
+}
+
 static DropCfg attn_cfg(const nlv_dropout* d) {
   DropCfg c = drop_off();
   if (d != nullptr && d->thr16 != 0u) { c.thr16 = d->thr16; c.scale = d->scale; c.seed_lo = d->seed_lo; c.seed_hi = d->seed_hi; c.stream = d->stream; }
@@ -396,7 +618,8 @@ static DropCfg attn_cfg(const nlv_dropout* d) {
 
 int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
                         const void* work, int n_work, void* o, int ldo, float* lse, const nlv_dropout* drop, cudaStream_t s) {
-  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop)};
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop), 0,
+          wide_ok(hd, heads, {q, k, v, o}, {ldq, ldk, ldv, ldo})};
   const size_t smem = 4 * 3 * TILE_B;
   int rc = opt_in_smem(attn_fwd_mma_kernel, smem);
   if (rc != NLV_OK) return rc;
@@ -407,10 +630,19 @@ int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const vo
 
 int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
                         const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s) {
-  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop)};
+  // NLV_ATTN_BWD_FUSED=0: every segment through the two-kernel path (debugging switch)
+  static const int fused = [] { const char* e = getenv("NLV_ATTN_BWD_FUSED"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+  MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop), fused,
+          wide_ok(hd, heads, {q, k, v, dout, dq, dk, dv}, {ldq, ldk, ldv, lddo, lddq, lddk, lddv})};
   const size_t s1 = 2 * 4 * TILE_B, s2 = 4 * TILE_B;
   int rc = opt_in_smem(attn_bwd_dq_mma_kernel, s1);
   if (rc != NLV_OK) return rc;
+  if (fused) {
+    MArgs af = a;
+    af.wide = 0;      // measured: the fused kernel is 8% faster with the 4-byte copies (303 vs 328 us on the C2 decoder shape), the forward 6% slower
+    attn_bwd_fused_mma_kernel<<<(unsigned)n_work * heads, 96, s2, s>>>(af, (const bf16*)dout, lddo, lse, (bf16*)dq, lddq, (bf16*)dk, lddk, (bf16*)dv, lddv);
+    NLV_CHECK_LAUNCH();
+  }
   attn_bwd_dq_mma_kernel<<<(unsigned)n_work * (heads / 2), 64, s1, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dq, lddq);
   NLV_CHECK_LAUNCH();
   attn_bwd_dkv_mma_kernel<<<(unsigned)n_work * heads, 64, s2, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dk, lddk, (bf16*)dv, lddv);

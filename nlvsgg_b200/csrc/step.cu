@@ -86,6 +86,10 @@ struct nlv_session {
   std::vector<const float*> params;
   std::vector<const void*> pop;
   std::vector<long long> goff;
+  // called (host side, between kernel enqueues) when every gradient of the temporal / global layers — the tail of the
+  // gradient buffer — has been enqueued: the data-parallel trainer starts their all-reduce under the rest of the backward
+  void (*tail_hook)(void*) = nullptr;
+  void* tail_hook_user = nullptr;
   int flags = 0;
   bool want_ctx = false, training = false, have_fwd = false, xf_only = false;
   int AD = NLV_BF16;
@@ -497,7 +501,9 @@ int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int row_
     T mu = ctx(B.nv, c, NLV_F32), va = ctx(B.nv, c, NLV_F32);
     T ws = tmp((long long)B.nv * 2 * c, 1, NLV_F32, 2);   // double[nv*2*c]
     OOM_CHECK();
+    g_next_units = (double)x.rows * c * x.esz();                    // algorithmic bytes: x read once
     RUN(nlv_bn_stats(x.p, x.dt, x.ld, seg, B.nv, x.rows, c, momentum, reinterpret_cast<double*>(ws.p), mu.f(), va.f(), rm, rv, st));
+    g_next_units = (double)x.rows * c * (x.esz() + y.esz());        // x in, y out
     RUN(nlv_bn_apply(x.p, x.dt, x.ld, B.nv > 1 ? row_seg : nullptr, row_div, mu.f(), va.f(), w, b, 1e-5f, relu ? 1 : 0, x.rows, c, y.p, y.dt, y.ld,
                      nullptr, 0, c, st));
     *mean = mu; *var = va;
@@ -527,6 +533,8 @@ int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, 
   }
   T ws = tmp((long long)nseg * 2 * c, 1, NLV_F32, 2);   // double[nseg*2*c]
   OOM_CHECK();
+  // algorithmic bytes: dy, x (and the ReLU gate) read for the sums and again for dx (the sums are a full reduction), dx out
+  g_next_units = (double)x.rows * c * (2.0 * (dy.esz() + x.esz() + (yout ? yout->esz() : 0)) + dx.esz());
   RUN(nlv_bn_bwd(dy.p, dy.dt, dy.ld, x.p, x.dt, x.ld, yout ? yout->p : nullptr, yout ? yout->dt : 0, yout ? yout->ld : 0, seg, row_seg, row_div, nseg,
                  mean.f(), var.f(), P(slot_w), 1e-5f, training ? 1 : 0, gate_by_x ? 1 : 0, x.rows, c, reinterpret_cast<double*>(ws.p), dx.p, dx.dt,
                  dx.ld, G(slot_w), G(slot_w + 1), st));
@@ -776,6 +784,7 @@ int nlv_session::sttran_transformer_bwd(const T& dout, T* drel) {
       CK(decoder_bwd(M.n_enc + i, dec[i], dg, &dn));
       dg = dn;
     }
+    if (!dry && tail_hook != nullptr) tail_hook(tail_hook_user);
     dlocal = keep(R, D, NLV_F32);
     OOM_CHECK();
     RUN(nlv_gather_sum_rows(dg.f(), D, B.inv, 2, R, D, dlocal.f(), D, 0, st));
@@ -831,6 +840,7 @@ int nlv_session::dsg_transformer_bwd(const T& dout, T* drel) {
     CK(encoder_bwd(1 + i, enc[1 + i], dg, B.cls_work, B.n_cls_work, true, &dn));
     dg = dn;
   }
+  if (!dry && tail_hook != nullptr) tail_hook(tail_hook_user);
   T dx = keep(R, D, NLV_F32);   // the encoding is a constant buffer
   OOM_CHECK();
   if (dropping) {
@@ -1130,6 +1140,13 @@ int nlv_session_set_gradients(nlv_session* s, float* grad_base, long long grad_e
   s->M.grad_base = grad_base;
   s->M.grad_elems = grad_elems;
   s->goff.assign(grad_offset, grad_offset + n_slots);
+  return NLV_OK;
+}
+
+int nlv_session_set_tail_hook(nlv_session* s, void (*fn)(void*), void* user) {
+  NLV_CHECK_ARG(s != nullptr, "session_set_tail_hook: null handle");
+  s->tail_hook = fn;
+  s->tail_hook_user = user;
   return NLV_OK;
 }
 

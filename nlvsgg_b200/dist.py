@@ -49,6 +49,14 @@ def allreduce_sum_(flat: torch.Tensor, flag: torch.Tensor = None, bucket_elems: 
     return flat
 
 
+def allreduce_sum_async(flat: torch.Tensor, bucket_elems: int = 32 * 1024 * 1024) -> list:
+    """Start the in-place SUM over ranks of `flat` (independent async buckets) and return the work handles; the collective is
+    ordered after everything already enqueued on the current stream and runs on NCCL's own stream."""
+    if world() == 1 or flat.numel() == 0:
+        return []
+    return [dist.all_reduce(flat[i:i + bucket_elems], async_op=True) for i in range(0, flat.numel(), bucket_elems)]
+
+
 def gather_frame_results(local_ids: torch.Tensor, local_masks: torch.Tensor):
     """all_gather of (global frame id, u32[3,3,8] match sets) with ragged sizes; returns (ids, masks) sorted by id
     on every rank.  local_ids: int64[F_local]; local_masks: int32[F_local,3,3,8]."""

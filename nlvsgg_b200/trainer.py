@@ -76,6 +76,15 @@ class Trainer:
             dec0 = [n for n in self.param_names if n.startswith("glocal_transformer.global_attention.")]
             if dec0:
                 self._tail_ranges = ((self.offsets[pos], self.offsets[pos] + (self.P[pos].numel() + 7) // 8 * 8), (self.offsets[dec0[0]], total))
+        # gradient all-reduce under the backward pass (world > 1): the temporal / global layers are the tail of the flat gradient
+        # buffer and the first to be finished by the backward pass; the sequencer calls back when their last kernel is enqueued
+        # and their buckets go out while the spatial encoder, the pair-feature stack and the object head are still running
+        tail = [n for n in self.param_names if n.startswith("glocal_transformer.global_attention." if arch == "sttran" else "global_transformer.")]
+        self._tail_off = self.offsets[tail[0]] if tail else None
+        self._tail_works = None
+        self._hook_error = None
+        self._hook_cb = ctypes.CFUNCTYPE(None, ctypes.c_void_p)(self._on_tail_grads)
+        self.overlap_allreduce = True
         self.last = None
         from .plan import Stager
         self.stager = Stager(dev)
@@ -97,6 +106,12 @@ class Trainer:
                 o = self.offsets[n]
                 self.k.mirror[n] = self.flat_pb[o:o + self.P[n].numel()].view(self.P[n].shape[0], -1)
 
+    def _on_tail_grads(self, _user):
+        try:
+            self._tail_works = D.allreduce_sum_async(self.flat_g[self._tail_off:])
+        except Exception as e:      # an exception cannot cross the C frame: re-raised by optimizer_step
+            self._hook_error = e
+
     # ---- one step ------------------------------------------------------------------------------------------------
     def forward_backward(self, batch: M.Batch, plan=None):
         """batch: device-resident collated batch.  Plan + labels are (re)built from its host metadata every call —
@@ -107,6 +122,9 @@ class Trainer:
         self.k.seed += 1
         out, sess = E.run_forward(self.k, self.desc, self.P, batch, plan, True, True, labels=plan.labels, with_loss=True,
                                   with_backward=True, grad_base=self.flat_g, grad_offsets=self._goff)
+        self._tail_works = None
+        if self.overlap_allreduce and self._tail_off is not None and D.world() > 1:
+            _C.check(_C.lib().nlv_session_set_tail_hook(ctypes.c_void_p(sess.h), self._hook_cb, None), "session_set_tail_hook")
         E.run_backward(sess)
         plan.consumed()
         self.last = (out, plan)
@@ -136,7 +154,16 @@ class Trainer:
         w = D.world()
         if out is not None:
             _C.check(lib.nlv_flag_nonfinite(ops._ptr(out["loss"]), 1, ops._ptr(self.skip_flag), st), "flag_nonfinite")
-        D.allreduce_sum_(self.flat_g, flag=self.skip_flag)      # no-op on one rank; the mean's 1/world is folded into AdamW
+        if self._hook_error is not None:
+            e, self._hook_error = self._hook_error, None
+            raise e
+        if self._tail_works is not None:       # the tail is already on its way: reduce the head (+ the skip flag), then wait for both
+            D.allreduce_sum_(self.flat_g[:self._tail_off], flag=self.skip_flag)
+            for wk in self._tail_works:
+                wk.wait()
+            self._tail_works = None
+        else:
+            D.allreduce_sum_(self.flat_g, flag=self.skip_flag)      # no-op on one rank; the mean's 1/world is folded into AdamW
         ops.zero_(self.total_sq)
         ops.sumsq(self.flat_g, self.total_sq)
         ranges = [(0, self.n_params)]

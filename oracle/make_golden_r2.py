@@ -87,7 +87,10 @@ def additive_case(ref):
 
 def main():
     ref = H.load_reference()
-    MG.run_model_case(ref, H.build_reference_sttran, "sttran", "sttran_sgcls_train", "sgcls", 8, 8, 5, 0.0, True)
+    # seed 11: seeds 8 and 10 put one FFN pre-activation of the last decoder layer within rounding of zero, where an fp32 CUDA run
+    # and the fp32 CPU reference legitimately pick different ReLU gates (one flipped gate = 2e-3 relative L2 on every gradient
+    # upstream; forward outputs agree to 2e-6 either way) — tools_dev/diag_grad.py
+    MG.run_model_case(ref, H.build_reference_sttran, "sttran", "sttran_sgcls_train", "sgcls", 11, 8, 5, 0.0, True)
     additive_case(ref)
     sgcls_branch_cases(ref)
 

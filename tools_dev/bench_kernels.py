@@ -31,6 +31,26 @@ h = torch.randn(Mr, 2048, device=dev).bfloat16()
 report("colsum bf16 [22931,2048]", timeit(lambda: ops.colsum(h)), Mr * 2048 * 2)
 q = torch.randn(Mr, 5808, device=dev).bfloat16()
 report("colsum bf16 [22931,5808]", timeit(lambda: ops.colsum(q)), Mr * 5808 * 2)
+# attention: temporal-decoder shape (2-frame windows of ~12 rows), bf16, with dropout masks
+import numpy as np
+from nlvsgg_b200.plan import work_items
+rng = np.random.default_rng(0)
+lens = []
+while sum(lens) < Mr:
+    lens.append(int(rng.integers(8, 17)))
+lens[-1] -= sum(lens) - Mr
+if lens[-1] <= 0: lens.pop(); lens[-1] += Mr - sum(lens)
+starts = np.concatenate(([0], np.cumsum(lens)))[:-1]
+work = torch.from_numpy(work_items(starts, np.asarray(lens))).cuda()
+qkv = (torch.randn(Mr, 3 * D, device=dev) * 0.5).bfloat16()
+qq, kk, vv = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+dd = _C.Dropout.make(0.1, 9, 3)
+o, lse = ops.attn_fwd(qq, kk, vv, 242, 8, work, work.shape[0], torch.bfloat16, drop=dd)
+report("attention fwd (bf16, %d segments)" % len(lens), timeit(lambda: ops.attn_fwd(qq, kk, vv, 242, 8, work, work.shape[0], torch.bfloat16, drop=dd)), Mr * D * 2 * 4)
+do = torch.randn(Mr, D, device=dev).bfloat16()
+dqkv = torch.empty_like(qkv)
+report("attention bwd (bf16)", timeit(lambda: ops.attn_bwd(qq, kk, vv, o, do, lse, 242, 8, work, work.shape[0], dqkv[:, :D], dqkv[:, D:2 * D], dqkv[:, 2 * D:], drop=dd)), Mr * D * 2 * 8)
+if os.environ.get("ATTN_ONLY"): sys.exit(0)
 # conv stack BatchNorm shapes: 64 videos, R = 11855 pairs
 R, nv = 11855, 64
 for rows_per_pair, C in ((196, 128), (49, 256)):

@@ -83,3 +83,28 @@ pipe4(3)
 torch.cuda.synchronize(); t0 = time.perf_counter(); pipe4(8); torch.cuda.synchronize()
 print("resident loop with lagged loss per step: %.1f ms" % ((time.perf_counter() - t0) / 8 * 1e3))
 print("mem allocated %.1f GB reserved %.1f GB" % (torch.cuda.memory_allocated() / 1e9, torch.cuda.memory_reserved() / 1e9))
+# ---- interference test: the resident loop with an unrelated 1.2 GB H2D copy running on a side stream every step
+big_h = host.union_feat
+big_d = torch.empty_like(big_h, device=dev)
+cs = torch.cuda.Stream()
+def pipe5(n, copy=True):
+    tk = None
+    for i in range(n):
+        if copy:
+            with torch.cuda.stream(cs):
+                big_d.copy_(big_h, non_blocking=True)
+        bb = M.Batch(); bb.__dict__.update(res.__dict__)
+        tr.step(bb)
+        if tk is not None: tr.loss_value(tk)
+        tk = tr.last_ticket
+    tr.loss_value(tk)
+for cp in (False, True, False, True):
+    pipe5(3, cp)
+    torch.cuda.synchronize(); t0 = time.perf_counter(); pipe5(10, cp); torch.cuda.synchronize()
+    print("resident loop, unrelated H2D on a side stream = %s: %.1f ms/step" % (cp, (time.perf_counter() - t0) / 10 * 1e3))
+# copy alone into a preallocated buffer
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    with torch.cuda.stream(cs): big_d.copy_(big_h, non_blocking=True)
+torch.cuda.synchronize()
+print("1.19 GB H2D alone: %.1f ms (%.1f GB/s)" % ((time.perf_counter() - t0) / 5 * 1e3, big_h.numel() * 2 / ((time.perf_counter() - t0) / 5) / 1e9))
