@@ -65,9 +65,9 @@ def workload_name(a):
 
 
 def make_videos(a, rank, n, draw_fn=None, with_gt=False):
-    """Frame counts come from ONE generator shared by all ranks (every rank steps through the same number of frames and, up to
-    the per-frame box draw, pairs: the max-over-ranks step time then measures communication, not imbalance); the videos'
-    contents are seeded per rank."""
+    """The STRUCTURE of video i (frames, boxes per frame, pairs, labels) is the same on every rank; its feature tensors are seeded
+    per rank.  Every rank therefore steps through exactly the same number of frames and pairs (equal-size shards, as a
+    length-bucketed sampler would hand out): the max-over-ranks step time measures communication, not load imbalance."""
     from nlvsgg_b200 import synth
     g = torch.Generator().manual_seed(777)
     out = []
@@ -76,8 +76,8 @@ def make_videos(a, rank, n, draw_fn=None, with_gt=False):
             frames = a.frames
         else:
             frames = int(torch.randint(max(2, a.frames - 10), a.frames + 11, (1,), generator=g))
-        e, _ = synth.synth_video(100000 * rank + i, frames, a.boxes, "sgdet", draw_fn=draw_fn, with_gt=with_gt,
-                                 fixed_boxes=a.boxes if a.config == "c4" else None)
+        e, _ = synth.synth_video(i, frames, a.boxes, "sgdet", draw_fn=draw_fn, with_gt=with_gt,
+                                 fixed_boxes=a.boxes if a.config == "c4" else None, content_seed=100000 * rank + i + 1)
         out.append(e)
     return out
 

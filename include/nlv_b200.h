@@ -122,6 +122,8 @@ int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, void* 
 int nlv_gather_rows(const void* src, int src_dtype, int lds, const int* idx, const float* add, const int* add_idx,
                     int ld_add, long long n_out, int cols, void* dst, int dst_dtype, int ldd, void* dst2,
                     int dst2_dtype, int ldd2, void* stream);
+/* dst[r,:] = src[r,:] * row_scale[r] (fp32; dst may alias src) */
+int nlv_scale_rows(const float* src, int lds, const float* row_scale, long long rows, int cols, float* dst, int ldd, void* stream);
 /* dst[i,:] (+)= sum_j src[idx[i*fan+j],:] (idx<0 skipped): adjoint of a bounded-fan-out gather */
 int nlv_gather_sum_rows(const float* src, int lds, const int* idx, int fan, long long n_out, int cols, float* dst,
                         int ldd, int accumulate, void* stream);
@@ -159,6 +161,12 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
                const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx,
                float* dw, float* db, void* stream);
+/* nlv_bn_bwd that also accumulates the column sums of dx into dx_colsum (nullable): the bias gradient of the conv / linear layer
+ * in front of the BatchNorm, produced by the kernel that writes dx instead of a separate pass */
+int nlv_bn_bwd_colsum(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
+               const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
+               int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx,
+               float* dw, float* db, float* dx_colsum, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused variable-length attention over contiguous segments (nn.MultiheadAttention core of
@@ -368,6 +376,8 @@ typedef struct nlv_model {
                                   lib/transformer_wk.py:154 under torch 1.10.1 (+1 added to padded keys' logits; the number of
                                   padded keys of a frame travels in the 4th field of its local work items; inference only) */
   int pe_rows;                 /* DSG-DETR: rows of the positional-encoding buffer */
+  int transformer_both;        /* STTran temporal decoder output: 0 = mode 'latter' (lib/transformer_wk.py:209-215, what lib/sttran.py:358
+                                  uses), 1 = mode 'both' (:197-207: a frame inside the video is the mean of its two windows) */
 } nlv_model;
 
 typedef struct nlv_batch {
@@ -396,6 +406,7 @@ typedef struct nlv_batch {
   /* fused-loss labels (tools/train_STTran.py:143-167), NULL for inference */
   const long long* lab_att; const float* w_att; const unsigned* spa_bits; const float* w_spa;
   const unsigned* con_bits; const float* w_con; const float* w_obj;
+  const float* both_w;          /* mode 'both': f32[R] = 1 / (windows the token appears in), 0 for tokens without a window */
 } nlv_batch;
 
 typedef struct nlv_outputs {

@@ -88,7 +88,7 @@ class Model(ctypes.Structure):
     """nlv_model (include/nlv_b200.h)."""
     _fields_ = [("arch", _i), ("mode", _i), ("precision", _i), ("n_enc", _i), ("n_dec", _i), ("training", _i), ("n_slots", _i),
                 ("params", _vp), ("params_op", _vp), ("grad_base", _vp), ("grad_elems", _ll), ("grad_offset", _vp),
-                ("dropout_p", _f), ("seed", ctypes.c_ulonglong), ("additive_mask", _i), ("pe_rows", _i)]
+                ("dropout_p", _f), ("seed", ctypes.c_ulonglong), ("additive_mask", _i), ("pe_rows", _i), ("transformer_both", _i)]
 
 
 class BatchDesc(ctypes.Structure):
@@ -102,7 +102,8 @@ class BatchDesc(ctypes.Structure):
                 ("has_passthrough", _i),
                 ("cls_perm", _ip), ("cls_iperm", _ip), ("cls_pos", _ip), ("cls_work", _ip), ("n_cls_work", _i),
                 ("union_bitmap", _vp), ("union_off", _vp), ("dist_conf", _vp), ("dist_other", _vp), ("dist_idx", _vp),
-                ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp)]
+                ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp),
+                ("both_w", _vp)]
 
 
 class Outputs(ctypes.Structure):

@@ -280,6 +280,15 @@ __global__ void gather_sum_rows_kernel(const float* __restrict__ src, int lds, c
   dst[(size_t)r * ldd + c] = acc;
 }
 
+__global__ void scale_rows_kernel(const float* __restrict__ src, int lds, const float* __restrict__ w, long long rows, int cols,
+                                  float* __restrict__ dst, int ldd) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const long long r = i / cols;
+  const int c = (int)(i - r * cols);
+  dst[(size_t)r * ldd + c] = src[(size_t)r * lds + c] * w[r];
+}
+
 // scatter-add rows with atomics: dst[idx[i],:] += src[i,:]  (embedding / feature-row gradients)
 __global__ void scatter_add_rows_kernel(const float* __restrict__ src, int lds, const long long* __restrict__ idx,
                                         int idx_stride, long long n, int cols, float* __restrict__ dst, int ldd) {
@@ -505,6 +514,15 @@ int nlv_gather_sum_rows(const float* src, int lds, const int* idx, int fan, long
   if (n_out * cols == 0) return NLV_OK;
   NLV_CHECK_ARG(src && idx && dst, "gather_sum_rows: null pointer");
   gather_sum_rows_kernel<<<GRID1D(n_out * cols)>>>(src, lds, idx, fan, n_out, cols, dst, ldd, accumulate);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_scale_rows(const float* src, int lds, const float* row_scale, long long rows, int cols, float* dst, int ldd, void* stream) {
+  NLV_CHECK_ARG(rows >= 0 && cols >= 0, "scale_rows: bad sizes");
+  if (rows * cols == 0) return NLV_OK;
+  NLV_CHECK_ARG(src && row_scale && dst, "scale_rows: null pointer");
+  scale_rows_kernel<<<GRID1D(rows * cols)>>>(src, lds, row_scale, rows, cols, dst, ldd);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -292,7 +292,7 @@ int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, int 
 int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
                            const int* row_seg, int row_div, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
-                           cudaStream_t s);
+                           float* dx_colsum, cudaStream_t s);
 int launch_layernorm_fwd_v4(const float* x, long long rows, int cols, const float* w, const float* b, float eps, float* y, void* y2,
                             int y2dt, float* mean, float* rstd, cudaStream_t s);
 int launch_layernorm_bwd_dx_v4(const float* dy, const float* x, const float* mean, const float* rstd, const float* w, long long rows,
@@ -416,6 +416,16 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
                const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
                int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
                float* db, void* stream) {
+  return nlv_bn_bwd_colsum(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, row_seg, row_div, nseg, mean, var, w, eps, use_batch_stats,
+                           gate_by_x, rows, c, sums_ws, dx, dx_dtype, lddx, dw, db, nullptr, stream);
+}
+
+/* dx_colsum (nullable): += column sums of dx, accumulated by the kernel that writes dx (the bias gradient of the conv / linear
+ * layer in front of the BatchNorm, otherwise a separate pass over dx) */
+int nlv_bn_bwd_colsum(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtype, int ldx, const void* yout, int y_dtype, int ldy,
+                      const int* seg, const int* row_seg, int row_div, int nseg, const float* mean, const float* var, const float* w, float eps,
+                      int use_batch_stats, int gate_by_x, long long rows, int c, double* sums_ws, void* dx, int dx_dtype, int lddx, float* dw,
+                      float* db, float* dx_colsum, void* stream) {
   NLV_CHECK_ARG(nseg >= 1 && c > 0 && rows >= 0, "bn_bwd: bad sizes");
   NLV_CHECK_ARG(dy && x && seg && mean && var && w && sums_ws && dx && dw && db, "bn_bwd: null pointer");
   if (row_div < 1) row_div = 1;
@@ -428,7 +438,7 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
     int rc = launch_bn_sums_bwd_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, seg, nseg, mean, var, eps, rows, c, sums_ws, STREAM);
     if (rc != NLV_OK) return rc;
     rc = launch_bn_bwd_apply_v8(dy, dy_dtype, lddy, x, x_dtype, ldx, yout, y_dtype, ldy, row_seg, row_div, seg, mean, var, w, eps, sums_ws, use_batch_stats,
-                                gate_by_x, rows, c, dx, dx_dtype, lddx, STREAM);
+                                gate_by_x, rows, c, dx, dx_dtype, lddx, dx_colsum, STREAM);
     if (rc != NLV_OK) return rc;
   } else {
     dim3 grid(cdiv(c, 32), nseg, bn_splits(seg, rows, nseg)), block(32, 8);
@@ -441,6 +451,7 @@ int nlv_bn_bwd(const void* dy, int dy_dtype, int lddy, const void* x, int x_dtyp
   }
   bn_bwd_param_kernel<<<cdiv(c, 128), 128, 0, STREAM>>>(sums_ws, nseg, c, dw, db);
   NLV_CHECK_LAUNCH();
+  if (!vec && dx_colsum != nullptr) return nlv_colsum(dx, dx_dtype, lddx, rows, c, nullptr, 1, dx_colsum, stream);
   return NLV_OK;
 }
 }

@@ -240,16 +240,19 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const
                        const void* __restrict__ yout, int ydt_rt, int ldy, const int* __restrict__ row_seg, int row_div,
                        const int* __restrict__ seg, const float* __restrict__ mean, const float* __restrict__ var,
                        const float* __restrict__ w, float eps, const double* __restrict__ sums, int use_batch_stats,
-                       int gate_by_x, long long rows, long long rows_per_block, int C, void* __restrict__ dx, int dxdt, int lddx) {
+                       int gate_by_x, long long rows, long long rows_per_block, int C, void* __restrict__ dx, int dxdt, int lddx,
+                       float* __restrict__ dx_colsum) {
   const int dydt = BF ? NLV_BF16 : dydt_rt, xdt = BF ? NLV_BF16 : xdt_rt, ydt = BF ? NLV_BF16 : ydt_rt;
   const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c8 >= (C >> 3)) return;
-  const int c0 = c8 * 8;
+  const bool active = c8 < (C >> 3);
+  if (!active && dx_colsum == nullptr) return;
+  const int c0 = active ? c8 * 8 : 0;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};     // column sums of dx: the bias gradient of the layer in front of this BatchNorm
   const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
   const V8 ww = nv_ld8(w, NLV_F32, c0);
   int cur = -1;
   float m[8], k[8], s1[8], t2[8];   // k = w*rstd, s1 = sum_dy/n, t2 = rstd*sum_dy_xhat/n
-  for (long long r = r0 + threadIdx.y; r < r1; r += (long long)blockDim.y * U) {
+  for (long long r = r0 + threadIdx.y; active && r < r1; r += (long long)blockDim.y * U) {
     R8 xr[U], gr[U], yr[U];
     int sg[U];
 #pragma unroll
@@ -291,8 +294,24 @@ bn_bwd_apply_v8_kernel(const void* __restrict__ dy, int dydt_rt, int lddy, const
         if (yout != nullptr && !(yo1.v[q] > 0.f)) gq = 0.f;
         o.v[q] = k[q] * (gq - s1[q] - (xv1.v[q] - m[q]) * t2[q]);
         if (gate_by_x && !(xv1.v[q] > 0.f)) o.v[q] = 0.f;
+        cs[q] += o.v[q];
       }
       nv_st8(dx, dxdt, (size_t)rr * lddx + c0, o);
+    }
+  }
+  if (dx_colsum != nullptr) {      // reduce over the block's row lanes, then one atomic per channel per block
+    __shared__ float red[128 * 8];
+    float* mine = red + (threadIdx.y * blockDim.x + threadIdx.x) * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) mine[q] = cs[q];
+    __syncthreads();
+    if (threadIdx.y == 0 && active) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float t = 0.f;
+        for (int yy = 0; yy < (int)blockDim.y; ++yy) t += red[(yy * blockDim.x + threadIdx.x) * 8 + q];
+        atomicAdd(dx_colsum + c0 + q, t);
+      }
     }
   }
 }
@@ -353,15 +372,15 @@ int launch_bn_apply_v8(const void* x, int xdt, int ldx, const int* row_seg, int 
 int launch_bn_bwd_apply_v8(const void* dy, int dydt, int lddy, const void* x, int xdt, int ldx, const void* yout, int ydt, int ldy,
                            const int* row_seg, int row_div, const int* seg, const float* mean, const float* var, const float* w, float eps,
                            const double* sums, int use_batch_stats, int gate_by_x, long long rows, int C, void* dx, int dxdt, int lddx,
-                           cudaStream_t s) {
+                           float* dx_colsum, cudaStream_t s) {
   if (dydt == NLV_BF16 && xdt == NLV_BF16 && (yout == nullptr || ydt == NLV_BF16)) {
     const ApplyGeom g = apply_geometry(C, rows, 4);
     bn_bwd_apply_v8_kernel<4, true><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, row_div, seg, mean, var, w, eps, sums,
-                                                              use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+                                                              use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx, dx_colsum);
   } else {
     const ApplyGeom g = apply_geometry(C, rows, 2);
     bn_bwd_apply_v8_kernel<2, false><<<g.grid, g.block, 0, s>>>(dy, dydt, lddy, x, xdt, ldx, yout, ydt, ldy, row_seg, row_div, seg, mean, var, w, eps, sums,
-                                                               use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx);
+                                                               use_batch_stats, gate_by_x, rows, g.rows_per_block, C, dx, dxdt, lddx, dx_colsum);
   }
   NLV_CHECK_LAUNCH();
   return NLV_OK;

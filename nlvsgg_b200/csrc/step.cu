@@ -179,7 +179,7 @@ struct nlv_session {
   }
   int bn_fwd(const T& x, const int* seg, const int* row_seg, int row_div, int slot_w, float momentum, bool relu, const T& y, T* mean, T* var);
   int bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int row_div, int slot_w, const T& mean, const T& var,
-             bool gate_by_x, const T& dx);
+             bool gate_by_x, const T& dx, float* dx_colsum = nullptr);
   int lin_grads(const T& dy_op, const T& x_op, const T& dy_bias, int wslot, int bslot);
   int encoder_fwd(int layer, const T& x, const T& xop, const int* work, int n_work, bool out_op, T* x2, T* x2op, EncCtx* c);
   int encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int* work, int n_work, bool need_dx, T* dx);
@@ -518,7 +518,7 @@ int nlv_session::bn_fwd(const T& x, const int* seg, const int* row_seg, int row_
 // BatchNorm backward (+ the ReLU that follows (yout) or precedes (gate_by_x) it).  Training: per-video statistics.
 // Eval (running statistics): one segment over all rows, dx = w * rstd * dy.
 int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int row_div, int slot_w, const T& mean, const T& var,
-                        bool gate_by_x, const T& dx) {
+                        bool gate_by_x, const T& dx, float* dx_colsum) {
   const int c = x.cols;
   int nseg = B.nv;
   if (!training) {
@@ -535,9 +535,9 @@ int nlv_session::bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, 
   OOM_CHECK();
   // algorithmic bytes: dy, x (and the ReLU gate) read for the sums and again for dx (the sums are a full reduction), dx out
   g_next_units = (double)x.rows * c * (2.0 * (dy.esz() + x.esz() + (yout ? yout->esz() : 0)) + dx.esz());
-  RUN(nlv_bn_bwd(dy.p, dy.dt, dy.ld, x.p, x.dt, x.ld, yout ? yout->p : nullptr, yout ? yout->dt : 0, yout ? yout->ld : 0, seg, row_seg, row_div, nseg,
-                 mean.f(), var.f(), P(slot_w), 1e-5f, training ? 1 : 0, gate_by_x ? 1 : 0, x.rows, c, reinterpret_cast<double*>(ws.p), dx.p, dx.dt,
-                 dx.ld, G(slot_w), G(slot_w + 1), st));
+  RUN(nlv_bn_bwd_colsum(dy.p, dy.dt, dy.ld, x.p, x.dt, x.ld, yout ? yout->p : nullptr, yout ? yout->dt : 0, yout ? yout->ld : 0, seg, row_seg, row_div,
+                        nseg, mean.f(), var.f(), P(slot_w), 1e-5f, training ? 1 : 0, gate_by_x ? 1 : 0, x.rows, c, reinterpret_cast<double*>(ws.p), dx.p,
+                        dx.dt, dx.ld, G(slot_w), G(slot_w + 1), dx_colsum, st));
   return NLV_OK;
 }
 
@@ -690,7 +690,8 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   CK(mm(dvr_in, MN_, pt.uf_op, MN_, mk(G(NLV_P_UNION_W), NLV_F32, 256, 2048)));
   RUN(nlv_colsum(dvr_in.p, dvr_in.dt, dvr_in.ld, R * 49, 256, nullptr, 1, G(NLV_P_UNION_B), st));
   T dc2 = tmp(R * 49, 256, AD);
-  CK(bn_bwd(dvr_in, pt.c2, nullptr, B.seg49, B.pair_row, 49, NLV_P_BN6_W, pt.mean6, pt.var6, true, dc2));   // BN backward + ReLU backward fused
+  // BN backward + ReLU backward fused; the kernel also accumulates the column sums of dc2 = the bias gradient of the 3x3 conv
+  CK(bn_bwd(dvr_in, pt.c2, nullptr, B.seg49, B.pair_row, 49, NLV_P_BN6_W, pt.mean6, pt.var6, true, dc2, G(NLV_P_CONV4_B)));
   {
     Scope s2(this);
     T gtap = tmp(256, 1152, NLV_F32);
@@ -698,7 +699,6 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
     OOM_CHECK();
     RUN(nlv_permute_021(gtap.p, NLV_F32, 256, 9, 128, G(NLV_P_CONV4_W), NLV_F32, st));  // (tap, c) -> (c, tap)
   }
-  RUN(nlv_colsum(dc2.p, dc2.dt, dc2.ld, R * 49, 256, nullptr, 1, G(NLV_P_CONV4_B), st));
   T dcol2 = tmp(R * 49, 1152, AD);
   CK(mm(dc2, K_, w_c4, MN_, dcol2));
   T dp1 = tmp(R * 49, 128, NLV_F32), db1 = tmp(R * 196, 128, AD);
@@ -706,7 +706,7 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   RUN(nlv_col2im_3x3(dcol2.p, dcol2.dt, (int)R, 7, 7, 128, dp1.f(), st));
   RUN(nlv_maxpool_bwd(dp1.f(), reinterpret_cast<const uint8_t*>(pt.arg.p), (int)R, 128, db1.p, db1.dt, st));
   T dc1 = tmp(R * 196, 128, AD);
-  CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.pair_row, 196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1));
+  CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.pair_row, 196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1, G(NLV_P_CONV0_B)));   // + 7x7 conv bias gradient
   {
     Scope s2(this);
     T g0 = tmp(128, 104, NLV_F32);
@@ -714,7 +714,6 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
     OOM_CHECK();
     RUN(nlv_convert(g0.p, NLV_F32, 104, G(NLV_P_CONV0_W), NLV_F32, 98, 128, 98, st));
   }
-  RUN(nlv_colsum(dc1.p, dc1.dt, dc1.ld, R * 196, 128, nullptr, 1, G(NLV_P_CONV0_B), st));
   T dfo_op;
   CK(opnd(dfo, &dfo_op));
   CK(mm(dfo_op.cs(0, 512), MN_, pt.feat_op, MN_, mk(G(NLV_P_SUBJ_W), NLV_F32, 512, 2048)));
@@ -766,7 +765,13 @@ int nlv_session::sttran_transformer_fwd(const T& rel_in, T* out_) {
   }
   T out = keep(R, D, NLV_F32);
   OOM_CHECK();
-  RUN(nlv_gather_rows(g.p, NLV_F32, D, B.out_src, nullptr, nullptr, 0, R, D, out.p, NLV_F32, D, nullptr, 0, D, st));
+  if (M.transformer_both) {      // mean over the windows a token appears in (lib/transformer_wk.py:197-207)
+    NLV_CHECK_ARG(dry || B.both_w != nullptr, "session: transformer mode 'both' needs the per-token window weights");
+    RUN(nlv_gather_sum_rows(g.f(), D, B.inv, 2, R, D, out.f(), D, 0, st));
+    RUN(nlv_scale_rows(out.f(), D, B.both_w, R, D, out.f(), D, st));
+  } else {
+    RUN(nlv_gather_rows(g.p, NLV_F32, D, B.out_src, nullptr, nullptr, 0, R, D, out.p, NLV_F32, D, nullptr, 0, D, st));
+  }
   if (B.has_passthrough)
     RUN(nlv_gather_sum_rows(local_out.f(), D, B.passthrough, 1, R, D, out.f(), D, 1, st));
   *out_ = out;
@@ -778,7 +783,14 @@ int nlv_session::sttran_transformer_bwd(const T& dout, T* drel) {
   if (Mg != 0) {
     T dg = keep(Mg, D, NLV_F32);
     OOM_CHECK();
-    RUN(nlv_gather_rows(dout.p, NLV_F32, dout.ld, B.out_inv, nullptr, nullptr, 0, Mg, D, dg.p, NLV_F32, D, nullptr, 0, D, st));
+    if (M.transformer_both) {    // every stream row takes its token's gradient, weighted by 1 / (windows of the token)
+      T dw = tmp(R, D, NLV_F32);
+      OOM_CHECK();
+      RUN(nlv_scale_rows(dout.f(), dout.ld, B.both_w, R, D, dw.f(), D, st));
+      RUN(nlv_gather_rows(dw.p, NLV_F32, D, B.stream_src, nullptr, nullptr, 0, Mg, D, dg.p, NLV_F32, D, nullptr, 0, D, st));
+    } else {
+      RUN(nlv_gather_rows(dout.p, NLV_F32, dout.ld, B.out_inv, nullptr, nullptr, 0, Mg, D, dg.p, NLV_F32, D, nullptr, 0, D, st));
+    }
     for (int i = M.n_dec - 1; i >= 0; --i) {
       T dn;
       CK(decoder_bwd(M.n_enc + i, dec[i], dg, &dn));

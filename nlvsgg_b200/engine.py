@@ -89,6 +89,7 @@ class Kernels:
         self.precision = precision
         self.dropout = dropout
         self.additive_mask = False
+        self.transformer_both = False      # temporal decoder output mode 'both' (standalone lib/transformer_wk.py module only)
         self.AD = BF16 if precision == "bf16" else F32
         self.mirror: Dict[str, torch.Tensor] = {}      # name -> bf16 operand copy kept current by the caller (trainer)
         self._ws: Optional[torch.Tensor] = None
@@ -195,6 +196,7 @@ class ModelDesc:
         m.dropout_p = float(self.k.dropout) if training else 0.0
         m.seed = self.k.seed
         m.additive_mask = 1 if self.k.additive_mask else 0
+        m.transformer_both = 1 if self.k.transformer_both else 0
         pe = P.get("positional_encoder.pe")
         m.pe_rows = int(pe.shape[-2]) if pe is not None else 0
         m._keep = (pa, po, grad_offsets)
@@ -206,7 +208,7 @@ def plan_desc(plan: Plan, dsg: bool = False) -> "_C.BatchDesc":
     b = _C.BatchDesc()
     b.nv, b.n_boxes, b.n_pairs, b.n_stream = plan.nv, plan.N, plan.R, plan.Mg
     for name in ("box_seg", "seg196", "seg49", "box_row", "pair_row", "local_work", "glob_work", "stream_src", "stream_slot",
-                 "inv", "out_src", "out_inv", "passthrough"):
+                 "inv", "out_src", "out_inv", "passthrough", "both_w"):
         setattr(b, name, _ptr(getattr(plan, name, None)))
     b.n_local_work, b.n_glob_work, b.has_passthrough = plan.n_local_work, plan.n_glob_work, 1 if plan.has_passthrough else 0
     if dsg:

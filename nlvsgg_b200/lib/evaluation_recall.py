@@ -125,6 +125,57 @@ def _bits(words: np.ndarray) -> List[int]:
     return idx
 
 
+class _FloatList(list):
+    """A python list of floats (what the reference's mean-recall collectors are) that can be FED with numpy chunks: the chunks
+    are turned into list items only when somebody looks at the list; the mean the evaluator itself needs is taken from the
+    arrays (creating ~9 M python floats per evaluation of the test split cost more than the kernel and all other booking)."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self._chunks = []
+
+    def add_array(self, arr):
+        self._chunks.append(np.asarray(arr, dtype=np.float64))
+
+    def _flush(self):
+        if self._chunks:
+            ch, self._chunks = self._chunks, []
+            super().extend(np.concatenate(ch).tolist())
+
+    def mean_or_zero(self):
+        """np.mean over the items in order (0.0 when empty), without materialising them."""
+        parts = ([np.asarray([x for x in list.__iter__(self)], dtype=np.float64)] if list.__len__(self) else []) + self._chunks
+        if not parts:
+            return 0.0
+        return np.mean(parts[0] if len(parts) == 1 else np.concatenate(parts))
+
+    def __len__(self):
+        return list.__len__(self) + sum(len(c) for c in self._chunks)
+
+    def __iter__(self):
+        self._flush(); return list.__iter__(self)
+
+    def __getitem__(self, i):
+        self._flush(); return list.__getitem__(self, i)
+
+    def __eq__(self, other):
+        self._flush()
+        if isinstance(other, _FloatList):
+            other._flush()
+        return list.__eq__(self, other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._flush(); return list.__repr__(self)
+
+    def append(self, x):
+        self._flush(); list.append(self, x)
+
+    def extend(self, xs):
+        self._flush(); list.extend(self, xs)
+
+
 class SceneGraphEvaluator:
     def __init__(self, mode, AG_object_classes, AG_all_predicates, AG_attention_predicates, AG_spatial_predicates,
                  AG_contacting_predicates, iou_threshold=0.5, constraint=False, semithreshold=None):
@@ -150,7 +201,7 @@ class SceneGraphEvaluator:
             self.result_dict[m + t] = {k: [] for k in KS}
         for t in ("_mean_recall", "_ng_mean_recall"):
             self.result_dict[m + t] = {k: 0.0 for k in KS}
-            self.result_dict[m + t + "_collect"] = {k: [[] for _ in range(self.num_rel)] for k in KS}
+            self.result_dict[m + t + "_collect"] = {k: [_FloatList() for _ in range(self.num_rel)] for k in KS}
             self.result_dict[m + t + "_list"] = {k: [] for k in KS}
 
     # ---- evaluation ----
@@ -224,29 +275,42 @@ class SceneGraphEvaluator:
         pred_of = gtd["rel"][:, 2].astype(np.int64)                       # predicate of every GT relation
         frame_of = np.repeat(np.arange(F), G)
         local = np.arange(len(pred_of)) - rel_off[frame_of]               # index of the relation inside its frame
-        bits = np.unpackbits(masks.reshape(F, 3, 3, 8).view(np.uint8), axis=-1, bitorder="little").reshape(F, 3, 3, 256)
-        pop = bits.sum(-1).astype(np.float64)                             # |matched set| per (frame, protocol, K)
+        words = masks.reshape(F, 3, 3, 8)
+        pop = np.bitwise_count(words).sum(-1).astype(np.float64)          # |matched set| per (frame, protocol, K): popcount of the 256-bit set
         Gf = G.astype(np.float64)
         for pi, key in enumerate(("_recall", "_recall_nogc", "_semi_recall")):
             for ki, k in enumerate(KS):
                 self.result_dict[m + key][k].extend((pop[:, pi, ki] / Gf).tolist())
         # mean-recall collectors (:69-87 / :146-165): per frame and predicate n, hits / count for predicates present in the
         # frame; index 0 additionally counts every relation (the reference's `[0] += 1` alongside `[predicate] += 1`)
-        cnt = np.zeros((F, self.num_rel), dtype=np.int64)
-        np.add.at(cnt, (frame_of, pred_of), 1)
-        cnt[:, 0] += G
+        # Sparse over the (frame, predicate) buckets that exist (frame-major, so a predicate's buckets are in frame order, the
+        # order the reference appends in); predicate 0 is the special one: it is present in every frame with relations.
+        flat = frame_of * self.num_rel + pred_of                          # (frame, predicate) bucket of every GT relation
+        order = np.argsort(flat, kind="stable")
+        fs = flat[order]
+        first = np.ones(len(fs), dtype=bool)
+        first[1:] = fs[1:] != fs[:-1]
+        starts = np.nonzero(first)[0]                                     # one entry per existing bucket
+        b_frame, b_pred = fs[starts] // self.num_rel, fs[starts] % self.num_rel
+        b_cnt = np.diff(np.append(starts, len(fs))).astype(np.float64)
+        sel_of = [np.nonzero(b_pred == n)[0] for n in range(1, self.num_rel)]       # buckets of predicate n >= 1, in frame order
+        has_rel = G > 0
+        cnt0 = G.astype(np.float64)                                       # predicate 0: every relation + the relations of predicate 0
+        z = b_pred == 0
+        cnt0[b_frame[z]] += b_cnt[z]
+        wsel, bsel = local >> 5, (local & 31).astype(np.uint32)           # word / bit of a relation inside its frame's match set
         for pi, key in ((0, "_mean_recall"), (1, "_ng_mean_recall")):
             for ki, k in enumerate(KS):
-                matched = bits[frame_of, pi, ki, local].astype(np.int64)
-                hit = np.zeros((F, self.num_rel), dtype=np.int64)
-                np.add.at(hit, (frame_of, pred_of), matched)
-                hit[:, 0] += hit.sum(1) - 0                                # every hit also counts for index 0
-                ratio = hit.astype(np.float64) / np.maximum(cnt, 1).astype(np.float64)
+                matched = ((words[frame_of, pi, ki, wsel] >> bsel) & np.uint32(1)).astype(np.float64)
+                b_hit = np.add.reduceat(matched[order], starts) if len(starts) else np.zeros(0)
                 coll = self.result_dict[m + key + "_collect"][k]
-                for n in range(self.num_rel):
-                    sel = cnt[:, n] > 0
-                    if sel.any():
-                        coll[n].extend(ratio[sel, n].tolist())
+                hit0 = np.bincount(frame_of, weights=matched, minlength=F)
+                hit0[b_frame[z]] += b_hit[z]
+                coll[0].add_array((hit0 / np.maximum(cnt0, 1.0))[has_rel])
+                ratio = b_hit / b_cnt
+                for n in range(1, self.num_rel):
+                    if len(sel_of[n - 1]):
+                        coll[n].add_array(ratio[sel_of[n - 1]])
 
     def calculate_mean_recall(self):
         for t in ("_mean_recall", "_ng_mean_recall"):      # :89-109 / :167-187
@@ -254,7 +318,7 @@ class SceneGraphEvaluator:
                 s = 0
                 for n in range(self.num_rel):
                     lst = self.result_dict[self.mode + t + "_collect"][k][n]
-                    r = 0.0 if len(lst) == 0 else np.mean(lst)
+                    r = lst.mean_or_zero() if isinstance(lst, _FloatList) else (0.0 if len(lst) == 0 else np.mean(lst))
                     self.result_dict[self.mode + t + "_list"][k].append(r)
                     s += r
                 self.result_dict[self.mode + t][k] = s / float(self.num_rel)

@@ -57,15 +57,15 @@ class _TransformerFn(torch.autograd.Function):
 
 
 class transformer_wk(nn.Module):
-    """lib/transformer_wk.py:104-217 (mode 'latter'; frames / windows without pairs are skipped; a single-frame video
-    returns the spatial-encoder output)."""
+    """lib/transformer_wk.py:104-217 (modes 'latter' and 'both'; frames / windows without pairs are skipped; a single-frame
+    video returns the spatial-encoder output)."""
 
     def __init__(self, enc_layer_num=1, dec_layer_num=3, embed_dim=1936, nhead=8, dim_feedforward=2048, dropout=0.1,
                  mode=None, precision=None):
         super().__init__()
         assert embed_dim == 1936 and nhead == 8 and dim_feedforward == 2048, "kernels are specialised for d=1936, 8 heads"
-        if mode not in (None, "latter"):
-            raise NotImplementedError("only mode='latter' (the one lib/sttran.py:359 uses) is built")
+        if mode not in (None, "latter", "both"):
+            raise ValueError("mode must be 'latter' or 'both' (lib/transformer_wk.py:197-215)")
         self.mode = mode
         self.local_attention = _Stack(TransformerEncoderLayer(embed_dim, nhead, dim_feedforward, dropout), enc_layer_num)
         self.global_attention = _Stack(TransformerDecoderLayer(embed_dim, nhead, dim_feedforward, dropout), dec_layer_num)
@@ -80,6 +80,7 @@ class transformer_wk(nn.Module):
             raise RuntimeError("nlvsgg_b200 transformer runs on CUDA only; there is no CPU fallback")
         if self._kernels is None:
             self._kernels = E.Kernels(self._precision or os.environ.get("NLV_PRECISION", "bf16"))
+            self._kernels.transformer_both = self.mode == "both"
         fid = im_idx.detach().cpu().numpy()
         plan = E.Plan([0], [fid], features.device)
         params = dict(self.named_parameters())

@@ -164,8 +164,10 @@ class Plan:
         self.has_passthrough = bool((passthrough >= 0).any())
         gw = work_items(wbase, wlen)
 
+        both_w = (inv >= 0).sum(1).astype(np.float32)          # windows a token appears in (0, 1 or 2) -> 1 / count
+        both_w = np.where(both_w > 0, 1.0 / np.maximum(both_w, 1.0), 0.0).astype(np.float32)
         arrays = {
-            "box_seg": box_seg, "pair_seg": pair_seg, "seg196": (pair_seg.astype(np.int64) * 196).astype(np.int32),
+            "both_w": both_w, "box_seg": box_seg, "pair_seg": pair_seg, "seg196": (pair_seg.astype(np.int64) * 196).astype(np.int32),
             "seg49": (pair_seg.astype(np.int64) * 49).astype(np.int32),
             "local_work": lw, "glob_work": gw, "stream_src": stream_src.astype(np.int32), "stream_slot": slot,
             "inv": inv, "out_src": out_src, "out_inv": out_inv, "passthrough": passthrough,

@@ -36,13 +36,16 @@ def _create_dis(conf: float, idx: int) -> torch.Tensor:
 def synth_video(seed: int, frames: int = 20, mean_boxes: int = 6, mode: str = "sgdet",
                 draw_fn: Optional[Callable[[np.ndarray, int], np.ndarray]] = None,
                 empty_frame_prob: float = 0.0, fixed_boxes: Optional[int] = None,
-                with_gt: bool = True, feat_dim: int = 2048, union_feat: bool = True):
+                with_gt: bool = True, feat_dim: int = 2048, union_feat: bool = True, content_seed: Optional[int] = None):
     """One synthetic video.  Returns (entry, gt_annotation).
 
     entry tensors live on the CPU; callers move them.  ``spatial_masks`` is omitted when
     draw_fn is None (the product path rasterises on device from ``boxes``/``pair_idx``).
+    content_seed: the two feature tensors are drawn from their own generator, so that videos of the same `seed` share their
+    structure (boxes, pairs, labels: identical work) and differ in content — equal-size shards for data-parallel ranks.
     """
     g = torch.Generator().manual_seed(int(seed))
+    gc = g if content_seed is None else torch.Generator().manual_seed(int(content_seed))
 
     def U(n=1):
         return torch.rand(n, generator=g)
@@ -101,7 +104,7 @@ def synth_video(seed: int, frames: int = 20, mean_boxes: int = 6, mode: str = "s
         "boxes": torch.tensor(boxes, dtype=torch.float32).reshape(N, 5),
         "labels": torch.tensor(labels, dtype=torch.int64),
         "scores": torch.tensor(scores, dtype=torch.float32),
-        "features": torch.relu(torch.randn(N, feat_dim, generator=g)),
+        "features": torch.relu(torch.randn(N, feat_dim, generator=gc)),
         "pair_idx": torch.tensor(pair_idx, dtype=torch.int64).reshape(R, 2),
         "im_idx": torch.tensor(im_idx, dtype=torch.float32 if mode == "predcls" else torch.int64),
         "attention_gt": att_gt, "spatial_gt": spa_gt, "contacting_gt": con_gt,
@@ -109,7 +112,7 @@ def synth_video(seed: int, frames: int = 20, mean_boxes: int = 6, mode: str = "s
     if mode != "predcls":
         entry["distribution"] = torch.stack(dist) if N else torch.zeros(0, 36)
     if union_feat:
-        entry["union_feat"] = torch.relu(torch.randn(R, feat_dim, 7, 7, generator=g))
+        entry["union_feat"] = torch.relu(torch.randn(R, feat_dim, 7, 7, generator=gc))
     if draw_fn is not None:
         pr = pair_rois(entry)
         entry["spatial_masks"] = torch.from_numpy(draw_fn(pr, 27) - 0.5)

@@ -84,7 +84,8 @@ class Trainer:
         self._tail_works = None
         self._hook_error = None
         self._hook_cb = ctypes.CFUNCTYPE(None, ctypes.c_void_p)(self._on_tail_grads)
-        self.overlap_allreduce = True
+        import os
+        self.overlap_allreduce = os.environ.get("NLV_ALLREDUCE_OVERLAP", "1") != "0"      # debugging switch: 0 = one all-reduce after backward
         self.last = None
         from .plan import Stager
         self.stager = Stager(dev)

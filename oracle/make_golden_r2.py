@@ -85,8 +85,27 @@ def additive_case(ref):
     print("wrote", name)
 
 
+def transformer_both_case(ref):
+    """lib/transformer_wk.py:transformer_wk(mode='both') as a standalone module (forward + input / position-embedding gradients)."""
+    seed = 13
+    m = ref.transformer_wk.transformer_wk(enc_layer_num=1, dec_layer_num=3, embed_dim=1936, nhead=8, dim_feedforward=2048, dropout=0.1, mode="both")
+    sd_full = synth.make_state_dict({"glocal_transformer." + k: v for k, v in m.state_dict().items()}, seed)
+    m.load_state_dict({k[len("glocal_transformer."):]: v for k, v in sd_full.items()})
+    MG._no_dropout(m)
+    m.eval()
+    g = torch.Generator().manual_seed(seed)
+    im_idx = torch.tensor([0, 0, 0, 1, 1, 3, 3, 3, 3, 4, 6, 6, 7], dtype=torch.int64)        # frames 2 and 5 have no pairs
+    x = torch.randn(len(im_idx), 1936, generator=g).requires_grad_(True)
+    out, _, _ = m(x, im_idx)
+    out.square().sum().backward()
+    torch.save({"seed": seed, "im_idx": im_idx, "out": out.detach().clone(), "dx": x.grad.clone(),
+                "dpos": m.position_embedding.weight.grad.clone()}, os.path.join(GOLDEN, "transformer_both.pt"))
+    print("wrote transformer_both")
+
+
 def main():
     ref = H.load_reference()
+    transformer_both_case(ref)
     # seed 11: seeds 8 and 10 put one FFN pre-activation of the last decoder layer within rounding of zero, where an fp32 CUDA run
     # and the fp32 CPU reference legitimately pick different ReLU gates (one flipped gate = 2e-3 relative L2 on every gradient
     # upstream; forward outputs agree to 2e-6 either way) — tools_dev/diag_grad.py

@@ -104,7 +104,7 @@ def _num_layers(sd, prefix):
     return n
 
 
-def glocal_transformer(features, im_idx, sd, prefix="glocal_transformer", additive_mask=False):
+def glocal_transformer(features, im_idx, sd, prefix="glocal_transformer", additive_mask=False, mode="latter"):
     """transformer_wk.forward, mode='latter' (lib/transformer_wk.py:130-217).  additive_mask: the spatial encoder's int
     key_padding_mask as torch 1.10.1 read it (see mha_segment; one encoder layer, as the reference configures it)."""
     fid = im_idx.to(torch.int64)
@@ -127,16 +127,24 @@ def glocal_transformer(features, im_idx, sd, prefix="glocal_transformer", additi
         return local
     pe = sd[f"{prefix}.position_embedding.weight"]
     out = torch.zeros_like(features)
-    for j in windows:
+    seen = torch.zeros(features.shape[0])          # mode 'both' (lib/transformer_wk.py:197-207): a frame inside the video is the
+    for j in windows:                              # mean of its two windows' outputs, the first / last frame have one window
         n0, n1 = rows[j].numel(), rows[j + 1].numel()
         x = torch.cat((local[rows[j]], local[rows[j + 1]]), 0)
         pos = torch.cat((pe[0].expand(n0, -1), pe[1].expand(n1, -1)), 0)
         for i in range(n_dec):
             x = decoder_layer(x, pos, sd, f"{prefix}.global_attention.layers.{i}")
+        if mode == "both":
+            both = torch.cat((rows[j], rows[j + 1]))
+            out = out.index_add(0, both, x)
+            seen[both] += 1
+            continue
         if j == 0 and n0:
             out[rows[0]] = x[:n0]
         if n1:
             out[rows[j + 1]] = x[n0:]
+    if mode == "both":
+        out = out / seen.clamp(min=1)[:, None]
     return out
 
 

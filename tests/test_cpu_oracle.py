@@ -118,3 +118,18 @@ def test_oracle_sgcls_test_branch_matches_reference_golden(name):
     assert G.rel_err(got["distribution"], want["distribution"]) < 1e-5 and G.rel_err(got["pred_scores"], want["pred_scores"]) < 1e-5
     assert tuple(got["union_feat"].shape) == tuple(want["union_feat_shape"])
     assert abs(got["union_feat"].double().sum().item() - want["union_feat_digest"][0].item()) <= 1e-6 * want["union_feat_digest"][1].item()
+
+
+def test_oracle_transformer_mode_both_matches_reference_golden():
+    """lib/transformer_wk.py mode='both' (:197-207; lib/sttran.py itself only uses 'latter'): golden written by the reference module."""
+    z = G.load_case("transformer_both")
+    sd = synth.make_state_dict({k: v for k, v in G.sttran_template().items() if k.startswith("glocal_transformer.")}, z["seed"])
+    g = torch.Generator().manual_seed(z["seed"])
+    x = torch.randn(len(z["im_idx"]), 1936, generator=g).requires_grad_(True)
+    pe = sd["glocal_transformer.position_embedding.weight"].requires_grad_(True)
+    out = omodel.glocal_transformer(x, z["im_idx"], sd, mode="both")
+    out.square().sum().backward()
+    assert G.rel_err(out.detach(), z["out"]) < 2e-5
+    assert G.rel_err(x.grad, z["dx"]) < 2e-4 and G.rel_err(pe.grad, z["dpos"]) < 2e-4
+    latter = omodel.glocal_transformer(x.detach(), z["im_idx"], sd)
+    assert G.rel_err(latter, z["out"]) > 1e-3                     # the two modes differ on the frames inside the video

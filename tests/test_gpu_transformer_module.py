@@ -32,3 +32,23 @@ def test_transformer_wk_module_matches_oracle(cuda_lib, im_dtype):
     assert G.rel_err(xc.grad.cpu(), xr.grad) < 1e-3
     pe = m.position_embedding.weight.grad
     assert pe is not None and pe.abs().sum().item() > 0
+
+
+def test_transformer_wk_mode_both_matches_reference_golden(cuda_lib):
+    """mode='both' (lib/transformer_wk.py:197-207): forward, input gradient and position-embedding gradient against a golden
+    written by the reference module itself (oracle/make_golden_r2.py)."""
+    from nlvsgg_b200.lib.transformer_wk import transformer_wk
+    z = G.load_case("transformer_both")
+    sd = synth.make_state_dict({k: v for k, v in G.sttran_template().items() if k.startswith("glocal_transformer.")}, z["seed"])
+    m = transformer_wk(enc_layer_num=1, dec_layer_num=3, embed_dim=1936, nhead=8, dim_feedforward=2048, dropout=0.1, mode="both", precision="fp32")
+    m.load_state_dict({k[len("glocal_transformer."):]: v for k, v in sd.items()})
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(z["seed"])
+    x = torch.randn(len(z["im_idx"]), 1936, generator=g).cuda().requires_grad_(True)
+    out, _, _ = m(x, z["im_idx"].cuda())
+    assert G.rel_err(out.detach().cpu(), z["out"]) < 1e-4
+    out.square().sum().backward()
+    assert G.rel_err(x.grad.cpu(), z["dx"]) < 1e-3
+    assert G.rel_err(m.position_embedding.weight.grad.cpu(), z["dpos"]) < 1e-3
+    with pytest.raises(ValueError):
+        transformer_wk(mode="neither")

@@ -10,6 +10,7 @@ import collections, csv, gzip, json, os, re, shutil, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
+RND = os.environ.get("ROUND", "r2")     # file-name prefix of this round
 STEPS_IN_RUN = 3   # bench.py --steps 1 --warmup 1: warm-up, timed, instrumented roofline step
 os.makedirs(OUT, exist_ok=True)
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6,
@@ -57,7 +58,7 @@ def wide_rows(path):
 
 
 def launches():
-    path = os.path.join(GO, "launches_r1.csv")
+    path = os.path.join(GO, f"launches_{RND}.csv")
     rows = long_rows(path)
     # the last step of the run = everything after the second-to-last AdamW launch (AdamW is the final kernel of a step)
     ad = [i for i, d in enumerate(rows) if "adamw_kernel" in d["kernel"]]
@@ -68,23 +69,23 @@ def launches():
         a = agg[short(d["kernel"])]
         a[0] += 1; a[1] += d.get("gpu__time_duration.sum", 0.0)
     tot = sum(v for _, v in agg.values())
-    md = ["# ncu launch list, round 1 — one training step (BASELINE C2: 64 videos, 1976 frames, 11,855 pairs, bf16)", "",
-          "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --videos 64 --steps 1 --warmup 1 --no-e2e --no-cpu-baseline`",
-          f"(tools_dev/ncu_capture.sh); last step of the run: {n} launches, {tot/1e6:.2f} ms of kernel time.",
+    md = [f"# ncu launch list, {RND} — one training step (BASELINE C2: 64 videos, 1976 frames, 11,855 pairs, bf16)", "",
+          "`ncu --metrics gpu__time_duration.sum --clock-control none` over `bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-extras`",
+          f"(tools_dev/ncu_r2.sh); last step of the run: {n} launches, {tot/1e6:.2f} ms of kernel time.",
           "Per-launch times under ncu are cold-cache and serialised: compare SHARES with bench.py's live CUDA-event numbers, not absolutes.", "",
           "| kernel | launches | ms | share |", "|---|---:|---:|---:|"]
     for k, (c, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         md.append(f"| `{k}` | {c} | {v/1e6:.3f} | {100*v/tot:.1f}% |")
     gem = sum(v for k, (c, v) in agg.items() if "gemm_tc_kernel" in k)
     md += ["", f"tcgen05 GEMM share of the step under ncu: {100*gem/tot:.1f}% (bench.py `roofline.kernel_share_of_step` measures the same share live with CUDA events)."]
-    open(os.path.join(OUT, "r1_launches_by_kernel.md"), "w").write("\n".join(md) + "\n")
-    with open(path, "rb") as f, gzip.open(os.path.join(OUT, "r1_launches.csv.gz"), "wb") as g:
+    open(os.path.join(OUT, f"{RND}_launches_by_kernel.md"), "w").write("\n".join(md) + "\n")
+    with open(path, "rb") as f, gzip.open(os.path.join(OUT, f"{RND}_launches.csv.gz"), "wb") as g:
         shutil.copyfileobj(f, g)
     print("\n".join(md[:16]))
 
 
 def gemm_dram():
-    rows = long_rows(os.path.join(GO, "gemm_dram.csv"))
+    rows = long_rows(os.path.join(GO, f"gemm_dram_{RND}.csv"))
     n = len(rows) // STEPS_IN_RUN
     last = rows[-n:]
     tot_b = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in last)
@@ -94,16 +95,16 @@ def gemm_dram():
           "tensor_pipe_active_pct_time_weighted": sum(d.get(tp, 0) * d.get("gpu__time_duration.sum", 0) for d in last) / tot_t,
           "tensor_pipe_active_pct_max": max(d.get(tp, 0) for d in last),
           "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,sm__pipe_tensor_cycles_active... "
-                    "--clock-control none -k regex:gemm_tc (every tcgen05 GEMM launch of the last training step; tools_dev/ncu_capture.sh)"}
+                    "--clock-control none -k regex:gemm_tc (every tcgen05 GEMM launch of the last training step; tools_dev/ncu_r2.sh)"}
     json.dump(js, open(os.path.join(OUT, "gemm_traffic.json"), "w"), indent=1)
-    md = ["# DRAM traffic of every tcgen05 GEMM launch of one training step (round 1)", "", "```", json.dumps(js, indent=1), "```", "",
+    md = [f"# DRAM traffic of every tcgen05 GEMM launch of one training step ({RND})", "", "```", json.dumps(js, indent=1), "```", "",
           "tensor pipe % is of the 2.25 PFLOP/s nominal peak (100 % = every cycle a tcgen05.mma slice active).", "",
-          "| # | template <BN,A_MN,B_MN,CM> | grid | time us | DRAM read MB | DRAM write MB | tensor pipe % |", "|---:|---|---|---:|---:|---:|---:|"]
+          "| # | template <BN,A_MN,B_MN,MODE> (MODE 2 = cta_group::2 pair) | grid | time us | DRAM read MB | DRAM write MB | tensor pipe % |", "|---:|---|---|---:|---:|---:|---:|"]
     for i, d in enumerate(last):
         t = re.search(r"gemm_tc_kernel<([^>]*)>", d["kernel"])
         md.append(f"| {i} | {t.group(1) if t else '?'} | {d['grid']} | {d.get('gpu__time_duration.sum', 0)/1e3:.1f} | "
                   f"{d.get('dram__bytes_read.sum', 0)/1e6:.1f} | {d.get('dram__bytes_write.sum', 0)/1e6:.1f} | {d.get(tp, 0):.1f} |")
-    open(os.path.join(OUT, "r1_gemm_dram.md"), "w").write("\n".join(md) + "\n")
+    open(os.path.join(OUT, f"{RND}_gemm_dram.md"), "w").write("\n".join(md) + "\n")
     print(json.dumps(js, indent=1))
 
 
@@ -132,14 +133,19 @@ def wide_table(src, dst, title, note):
 
 
 if __name__ == "__main__":
-    if os.path.exists(os.path.join(GO, "launches_r1.csv")):
+    if os.path.exists(os.path.join(GO, f"launches_{RND}.csv")):
         launches()
-    if os.path.exists(os.path.join(GO, "gemm_dram.csv")):
+    if os.path.exists(os.path.join(GO, f"gemm_dram_{RND}.csv")):
         gemm_dram()
-    if os.path.exists(os.path.join(GO, "gemm_full_raw.csv")):
-        wide_table("gemm_full_raw.csv", "r1_gemm_ncu.md", "ncu --set full, a window of tcgen05 GEMM launches of one training step (round 1)",
-                   "`ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 176 -c 8` (tools_dev/ncu_capture.sh); raw page exported on the box.")
-    if os.path.exists(os.path.join(GO, "attn_full_raw.csv")):
-        wide_table("attn_full_raw.csv", "r1_attn_ncu.md", "ncu --set full, varlen attention kernels of one training step (round 1)",
-                   "`ncu --set full --clock-control none --import-source on -k regex:attn_ -s 24 -c 8`: spatial encoder forward, three temporal decoder "
-                   "forwards, then the backward (query-side, key-side) kernels of two decoder layers.")
+    if os.path.exists(os.path.join(GO, f"gemm_full_raw_{RND}.csv")):
+        wide_table(f"gemm_full_raw_{RND}.csv", f"{RND}_gemm_ncu.md", f"ncu --set full, a window of tcgen05 GEMM launches of one training step ({RND})",
+                   "`ncu --set full --clock-control none --import-source on -k regex:gemm_tc` over a window of the last step's launches (tools_dev/ncu_r2.sh); "
+                   "raw page exported on the box.  gemm_tc_kernel<BN, A_MN, B_MN, MODE>: MODE 2 = CTA pair issuing tcgen05.mma.cta_group::2.")
+    if os.path.exists(os.path.join(GO, f"attn_full_raw_{RND}.csv")):
+        wide_table(f"attn_full_raw_{RND}.csv", f"{RND}_attn_ncu.md", f"ncu --set full, varlen attention kernels of one training step ({RND})",
+                   "`ncu --set full --clock-control none --import-source on -k regex:attn_`: forward kernels, the fused single-tile backward and the "
+                   "two-kernel backward (which exits at once for segments the fused kernel took).")
+    if os.path.exists(os.path.join(GO, f"tail_full_raw_{RND}.csv")):
+        wide_table(f"tail_full_raw_{RND}.csv", f"{RND}_tail_ncu.md", f"ncu --set full, the memory-bound kernels of one training step ({RND})",
+                   "`ncu --set full --clock-control none -k regex:'bn_|colsum|layernorm|union_unpack|maxpool|im2col|col2im|gather|split3|convert'` "
+                   "(first step of the run).")
