@@ -261,9 +261,10 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
     extra = {
         "gather_union_rows": hbm(("nlv_union_unpack", "nlv_nchw_to_rows"), 2.0 * n_stored_values),
         "attention_fwd": hbm(("nlv_attn_fwd", "nlv_attn_fwd_drop", "nlv_attn_fwd_padkeys")),
-        "attention_bwd": hbm(("nlv_attn_bwd", "nlv_attn_bwd_drop")),
+        "attention_bwd": hbm(("nlv_attn_bwd", "nlv_attn_bwd_drop", "nlv_attn_bwd_sorted")),
         "layernorm": hbm(("nlv_layernorm_fwd", "nlv_layernorm_bwd", "nlv_layernorm_bwd_drop", "nlv_layernorm_bwd_fused")),
-        "batchnorm": hbm(("nlv_bn_stats", "nlv_bn_apply", "nlv_bn_bwd")),
+        "batchnorm": hbm(("nlv_bn_stats", "nlv_bn_apply", "nlv_bn_bwd", "nlv_bn_bwd_colsum")),
+        "mask_conv1": hbm(("nlv_mask_conv1_fwd", "nlv_bn_apply_maxpool", "nlv_mask_conv1_dw")),
         "bias_grad_colsum": hbm(("nlv_colsum",)),
     }
     if adamw_ms:

@@ -116,6 +116,29 @@ int nlv_col2im_3x3(const void* dcol, int dtype, int r, int h, int w, int c, floa
 /* MaxPool2d(3,2,1) (lib/sttran.py:341) on NHWC [r,14,14,c] -> [r,7,7,c]; argmax u8 per output */
 int nlv_maxpool_fwd(const void* x, int x_dtype, int r, int c, void* y, int y_dtype, uint8_t* argmax, void* stream);
 int nlv_maxpool_bwd(const float* dy, const uint8_t* argmax, int r, int c, void* dx, int dx_dtype, void* stream);
+/* First stage of the spatial-mask branch on the bf16 path without the im2col matrix (csrc/maskconv.cu; lib/sttran.py:337-341):
+ * nlv_mask_conv1_fwd: Conv2d(2,128,k7,s2,p3) + bias + ReLU over masks [r,2,27,27] (fp32) with w [128,98] fp32 (c,ky,kx) -> out bf16
+ *   [r*196,128] (NHWC), plus the training-mode BatchNorm statistics of that map per video: pair_video[pair] = video, seg196 =
+ *   int[nv+1] row offsets (as nlv_bn_stats), sums_ws = double[nv*2*128]; mean/var [nv,128] out, running statistics updated.
+ *   mean == NULL: no statistics (eval mode).
+ * nlv_bn_apply_maxpool: BatchNorm apply + MaxPool2d(3,2,1) in one pass, x bf16 [r*196,128] -> y bf16 [r*49,128] + argmax taps;
+ *   same values as nlv_bn_apply (bf16 out) followed by nlv_maxpool_fwd (taps differ only where outputs tie after rounding).
+ *   pair_video NULL: segment 0.  xmax (nullable):
+ *   bf16 [r*49,128], the activation at every argmax.
+ * nlv_mask_conv1_dw: dw[128,98] (assigned) = weight gradient from dy bf16 [r*196,128]; ws = float[nlv_mask_conv1_dw_ws_floats()]. */
+int nlv_mask_conv1_fwd(const float* masks, const float* w, const float* bias, long long r, const int* pair_video, const int* seg196,
+                       int nv, void* out, float momentum, double* sums_ws, float* mean, float* var, float* running_mean,
+                       float* running_var, void* stream);
+int nlv_bn_apply_maxpool(const void* x, const int* pair_video, const float* mean, const float* var, const float* w, const float* b,
+                         float eps, long long r, void* y, uint8_t* argmax, void* xmax, void* stream);
+/* backward of that stage from the pooled gradient dp fp32 [r*49,128]: dx bf16 [r*196,128] at the conv output (ReLU applied); dw / db
+ * (BatchNorm parameter gradients) and dx_colsum (conv bias gradient, nullable) are accumulated.  xmax: the activation at every argmax
+ * (bf16 [r*49,128], written by nlv_bn_apply_maxpool).  Replaces nlv_maxpool_bwd + nlv_bn_bwd_colsum(gate_by_x = 1). */
+int nlv_pool_bn_bwd(const float* dp, const uint8_t* argmax, const void* x, const void* xmax, const int* pair_video, const int* seg196,
+                    const int* seg49, int nv, const float* mean, const float* var, const float* w, float eps, int use_batch_stats,
+                    long long r, double* sums_ws, void* dx, float* dw, float* db, float* dx_colsum, void* stream);
+long long nlv_mask_conv1_dw_ws_floats(void);
+int nlv_mask_conv1_dw(const void* dy, const float* masks, long long r, float* ws, float* dw, void* stream);
 /* dst[i,:] = src[idx[i],:] (+ add[add_idx[i],:]); idx null = identity, idx<0 = zero row; optional 2nd output.
  * Builds the sliding-window token stream + frame position embedding (lib/transformer_wk.py:163-171) and the
  * DSG-DETR class sequences + sinusoidal encoding (lib/dsg_detr.py:545-559). */
@@ -193,6 +216,12 @@ int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void
                       float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
                       int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                       int dqkv_dtype, const nlv_dropout* drop, void* stream);
+/* nlv_attn_bwd_drop for a work list ordered long-first: items [0, n_long_work) are those of segments longer than 16 rows, the
+ * only ones the two-kernel backward has work for (plan.py orders the lists; n_long_work < 0: unknown, every item is visited) */
+int nlv_attn_bwd_sorted(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                        float scale, const void* work, int n_work, int n_long_work, const void* o, int ldo, int o_dtype, const void* dout,
+                        int lddo, int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                        int dqkv_dtype, const nlv_dropout* drop, void* stream);
 /* forward with the torch-1.10.1 reading of the INT key_padding_mask of lib/transformer_wk.py:154 (the mask value is ADDED to
  * the logits instead of masking): every segment keeps work[i].w padded keys in its softmax, each with logit
  * q . kpad * scale + 1 and value vpad, where kpad / vpad (f32[heads*hd]) are the K / V slices of in_proj_bias (a padded row
@@ -407,6 +436,8 @@ typedef struct nlv_batch {
   const long long* lab_att; const float* w_att; const unsigned* spa_bits; const float* w_spa;
   const unsigned* con_bits; const float* w_con; const float* w_obj;
   const float* both_w;          /* mode 'both': f32[R] = 1 / (windows the token appears in), 0 for tokens without a window */
+  /* work_sorted != 0: the three work lists are ordered long-first and n_*_long = their items of segments longer than 16 rows */
+  int work_sorted, n_local_long, n_glob_long, n_cls_long;
 } nlv_batch;
 
 typedef struct nlv_outputs {

@@ -472,8 +472,8 @@ bool attn_mma_supported(int hd, int heads, int ld_or);
 int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
                         const void* work, int n_work, void* o, int ldo, float* lse, const nlv_dropout* drop, cudaStream_t s);
 int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
-                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq,
-                        void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s);
+                        const void* work, int n_work, int n_long, const void* dout, int lddo, const float* lse, float* delta, void* dq,
+                        int lddq, void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s);
 static bool use_mma() {
   const char* e = getenv("NLV_ATTN_SIMT");
   return !(e != nullptr && e[0] == '1');
@@ -542,6 +542,14 @@ int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void
                       float scale, const void* work, int n_work, const void* o, int ldo, int o_dtype, const void* dout, int lddo,
                       int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
                       int dqkv_dtype, const nlv_dropout* drop, void* stream) {
+  return nlv_attn_bwd_sorted(q, ldq, k, ldk, v, ldv, in_dtype, hd, heads, scale, work, n_work, -1, o, ldo, o_dtype, dout, lddo, do_dtype, lse,
+                             delta, dq, lddq, dk, lddk, dv, lddv, dqkv_dtype, drop, stream);
+}
+
+int nlv_attn_bwd_sorted(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int in_dtype, int hd, int heads,
+                        float scale, const void* work, int n_work, int n_long_work, const void* o, int ldo, int o_dtype, const void* dout,
+                        int lddo, int do_dtype, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv,
+                        int dqkv_dtype, const nlv_dropout* drop, void* stream) {
   int rc = check_common(hd, heads, n_work, ((ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv) & 1) == 0);
   if (rc != NLV_OK) return rc;
   if (n_work == 0) return NLV_OK;
@@ -549,8 +557,8 @@ int nlv_attn_bwd_drop(const void* q, int ldq, const void* k, int ldk, const void
   NLV_CHECK_ARG(in_dtype == o_dtype && in_dtype == dqkv_dtype, "attn_bwd: q/k/v, o and dq/dk/dv must share one dtype");
   if (in_dtype == NLV_BF16 && do_dtype == NLV_BF16 && use_mma() &&
       attn_mma_supported(hd, heads, ldq | ldk | ldv | ldo | lddo | lddq | lddk | lddv))
-    return launch_attn_bwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, dout, lddo, lse, delta, dq, lddq, dk, lddk, dv,
-                               lddv, drop, STREAM);
+    return launch_attn_bwd_mma(q, ldq, k, ldk, v, ldv, hd, heads, scale, work, n_work, n_long_work, dout, lddo, lse, delta, dq, lddq, dk, lddk,
+                               dv, lddv, drop, STREAM);
   if (drop != nullptr && drop->thr16 != 0u) {
     nlv::set_error("attn_bwd: attention-weight dropout is implemented on the bf16 tensor-core path only");
     return NLV_ERR_UNSUPPORTED;

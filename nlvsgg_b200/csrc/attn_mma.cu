@@ -629,7 +629,7 @@ int launch_attn_fwd_mma(const void* q, int ldq, const void* k, int ldk, const vo
 }
 
 int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const void* v, int ldv, int hd, int heads, float scale,
-                        const void* work, int n_work, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s) {
+                        const void* work, int n_work, int n_long, const void* dout, int lddo, const float* lse, float* delta, void* dq, int lddq, void* dk, int lddk, void* dv, int lddv, const nlv_dropout* drop, cudaStream_t s) {
   // NLV_ATTN_BWD_FUSED=0: every segment through the two-kernel path (debugging switch)
   static const int fused = [] { const char* e = getenv("NLV_ATTN_BWD_FUSED"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
   MArgs a{(const bf16*)q, (const bf16*)k, (const bf16*)v, ldq, ldk, ldv, hd, heads, scale, (const int4*)work, attn_cfg(drop), fused,
@@ -643,9 +643,13 @@ int launch_attn_bwd_mma(const void* q, int ldq, const void* k, int ldk, const vo
     attn_bwd_fused_mma_kernel<<<(unsigned)n_work * heads, 96, s2, s>>>(af, (const bf16*)dout, lddo, lse, (bf16*)dq, lddq, (bf16*)dk, lddk, (bf16*)dv, lddv);
     NLV_CHECK_LAUNCH();
   }
-  attn_bwd_dq_mma_kernel<<<(unsigned)n_work * (heads / 2), 64, s1, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dq, lddq);
+  // the two-kernel path only has work for segments of more than 16 rows: with a long-first work list (n_long >= 0, plan.py) it
+  // is launched over those items alone — usually none — instead of over every item to exit at once
+  const int n_two = (fused && n_long >= 0) ? (n_long < n_work ? n_long : n_work) : n_work;
+  if (n_two == 0) return NLV_OK;
+  attn_bwd_dq_mma_kernel<<<(unsigned)n_two * (heads / 2), 64, s1, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dq, lddq);
   NLV_CHECK_LAUNCH();
-  attn_bwd_dkv_mma_kernel<<<(unsigned)n_work * heads, 64, s2, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dk, lddk, (bf16*)dv, lddv);
+  attn_bwd_dkv_mma_kernel<<<(unsigned)n_two * heads, 64, s2, s>>>(a, (const bf16*)dout, lddo, lse, delta, (bf16*)dk, lddk, (bf16*)dv, lddv);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

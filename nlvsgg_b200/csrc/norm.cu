@@ -303,6 +303,21 @@ int launch_layernorm_bwd_fused(const float* dy, const float* x, const float* mea
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 }  // namespace nlv
 
+namespace nlv {
+int launch_bn_bwd_param(const double* sums, int nseg, int c, float* dw, float* db, cudaStream_t s) {
+  bn_bwd_param_kernel<<<cdiv(c, 128), 128, 0, s>>>(sums, nseg, c, dw, db);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+// the finalize pass alone, for producers that accumulate the (segment, channel) sums themselves (maskconv.cu)
+int launch_bn_finalize(const double* sums, const int* seg, int nseg, int c, float momentum, float* mean, float* var, float* running_mean,
+                       float* running_var, cudaStream_t s) {
+  bn_finalize_kernel<<<cdiv(c, 128), 128, 0, s>>>(sums, seg, nseg, c, momentum, mean, var, running_mean, running_var);
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+}  // namespace nlv
+
 using namespace nlv;
 #define STREAM ((cudaStream_t)stream)
 

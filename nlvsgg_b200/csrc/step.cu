@@ -40,7 +40,7 @@ inline T mk(const void* p, int dt, long long rows, int cols) {
 struct EncCtx { T xop, qkv, o, lse, y1, m1, r1, x1op, h, y2, m2, r2; };
 struct DecCtx { T xop, xpop, qkv, o, lse, y, m3, r3, top, h; };
 struct OcCtx { T objfeat, cs, pos_bn, mean0, var0, h1, h2, mean1, var1; };
-struct PtCtx { T feat_op, uf_op, col1, c1, mean2, var2, arg, col2, c2, mean6, var6, vr_in; };
+struct PtCtx { T feat_op, uf_op, col1, c1, mean2, var2, arg, xmax, col2, c2, mean6, var6, vr_in; };
 
 // ---- optional per-call timing (bench.py roofline legs): CUDA events around every kernel entry the sequencer makes --------
 struct ProfRec { char name[40]; cudaEvent_t e0, e1; double flops; double units; int m, n, k; int dt; };
@@ -98,6 +98,7 @@ struct nlv_session {
   T w_c0, w_c4, w_vr, w26, b26;
   OcCtx oc;
   PtCtx pt;
+  bool pool_fused = false;
   std::vector<EncCtx> enc;    // STTran: spatial encoder layers; DSG: [local, global0..2]
   std::vector<DecCtx> dec;
   T masks, rel, local_out, xf_out, logits26, obj_logits, att, spa, con, loss, d26, dobj, dx_in;
@@ -176,6 +177,11 @@ struct nlv_session {
   T W(int slot, long long rows, int cols) const {
     if (AD == NLV_BF16 && wop[slot].ok()) return wop[slot];
     return mk(params[slot], NLV_F32, rows, cols);
+  }
+  // bf16 path: the first stage of the mask branch runs on the fused kernels of maskconv.cu (NLV_MASKCONV=0: the im2col + GEMM route)
+  bool fused_mask_conv() const {
+    static const int env = [] { const char* e = getenv("NLV_MASKCONV"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    return AD == NLV_BF16 && env != 0;
   }
   int bn_fwd(const T& x, const int* seg, const int* row_seg, int row_div, int slot_w, float momentum, bool relu, const T& y, T* mean, T* var);
   int bn_bwd(const T& dy, const T& x, const T* yout, const int* seg, const int* row_seg, int row_div, int slot_w, const T& mean, const T& var,
@@ -389,8 +395,9 @@ int nlv_session::encoder_bwd(int layer, const EncCtx& c, const T& dx2, const int
   const T& q = c.qkv;
   const size_t e = q.esz();
   g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
-  RUN(nlv_attn_bwd_drop(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work,
-                        c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e, dqkv.ld,
+  const int n_long = !B.work_sorted ? -1 : (work == B.local_work ? B.n_local_long : (work == B.cls_work ? B.n_cls_long : -1));
+  RUN(nlv_attn_bwd_sorted(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), work, n_work,
+                        n_long, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e, dqkv.ld,
                         (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, &d3, st));
   CK(lin_grads(dqkv, c.xop, dqkv, LS(layer, NLV_L_INPROJ_W), LS(layer, NLV_L_INPROJ_B)));
   if (need_dx) {
@@ -469,8 +476,8 @@ int nlv_session::decoder_bwd(int layer, const DecCtx& c, const T& dout, T* dx_ou
   const T& q = c.qkv;
   const size_t e = q.esz();
   g_next_units = 8.0 * (double)Mr * D * q.esz(); g_next_dt = q.dt;   // Q, K, V, O, dO in; dQ, dK, dV out
-  RUN(nlv_attn_bwd_drop(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work,
-                        B.n_glob_work, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e,
+  RUN(nlv_attn_bwd_sorted(q.p, q.ld, (char*)q.p + D * e, q.ld, (char*)q.p + 2 * D * e, q.ld, q.dt, HD, HEADS, 1.0f / sqrtf((float)HD), B.glob_work,
+                        B.n_glob_work, B.work_sorted ? B.n_glob_long : -1, c.o.p, c.o.ld, c.o.dt, d_o.p, d_o.ld, d_o.dt, c.lse.f(), delta.f(), dqkv.p, dqkv.ld, (char*)dqkv.p + D * e,
                         dqkv.ld, (char*)dqkv.p + 2 * D * e, dqkv.ld, dqkv.dt, &d3, st));
   const T gw = mk(G(LS(layer, NLV_L_INPROJ_W)), NLV_F32, 3 * D, D);
   CK(mm(dqkv.cs(0, 2 * D), MN_, c.xpop, MN_, gw.rs(0, 2 * D)));
@@ -642,15 +649,42 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
                            uf.dt, st));
     }
   }
-  T col1 = ctx(R * 196, 104, AD), c1 = ctx(R * 196, 128, AD), b1 = tmp(R * 196, 128, AD);
-  OOM_CHECK();
-  RUN(nlv_im2col_mask(masks.f(), (int)R, col1.p, col1.dt, 104, st));
-  CK(mm(col1, K_, w_c0, K_, c1, P(NLV_P_CONV0_B), nullptr, true));                                     // conv 7x7 s2 + ReLU
-  CK(bn_fwd(c1, B.seg196, B.pair_row, 196, NLV_P_BN2_W, 0.01f, false, b1, &pt.mean2, &pt.var2));
+  T col1, c1 = ctx(R * 196, 128, AD), xmax_keep;
   T p1 = tmp(R * 49, 128, AD), arg = ctx(R * 49, 128, NLV_BF16 /*u8 payload*/, 64);
   arg.dt = NLV_BF16;
-  OOM_CHECK();
-  RUN(nlv_maxpool_fwd(b1.p, b1.dt, (int)R, 128, p1.p, p1.dt, reinterpret_cast<uint8_t*>(arg.p), st));
+  if (fused_mask_conv()) {
+    // conv 7x7 s2 + ReLU (+ BatchNorm statistics) straight from the masks, then BatchNorm + pooling in one pass (maskconv.cu)
+    T ws = tmp((long long)B.nv * 2 * 128, 1, NLV_F32, 2);   // double[nv*2*128]
+    T mu = training ? ctx(B.nv, 128, NLV_F32) : T(), va = training ? ctx(B.nv, 128, NLV_F32) : T();
+    pool_fused = want_ctx && training;                       // the backward then runs nlv_pool_bn_bwd (batch statistics only)
+    T xmax = pool_fused ? ctx(R * 49, 128, AD) : T();        // the activation at every argmax: input of its reduction pass
+    OOM_CHECK();
+    float *rm = const_cast<float*>(P(NLV_P_BN2_W + 2)), *rv = const_cast<float*>(P(NLV_P_BN2_W + 3));
+    g_next_units = (double)R * (2 * 27 * 27 * 4 + 196 * 128 * 2);
+    RUN(nlv_mask_conv1_fwd(masks.f(), P(NLV_P_CONV0_W), P(NLV_P_CONV0_B), R, B.pair_row, B.seg196, B.nv, c1.p, 0.01f,
+                           reinterpret_cast<double*>(ws.p), training ? mu.f() : nullptr, training ? va.f() : nullptr, rm, rv, st));
+    g_next_units = (double)R * (196 * 128 * 2 + 49 * 128 * (pool_fused ? 5 : 3));
+    if (training) {
+      RUN(nlv_bn_apply_maxpool(c1.p, B.nv > 1 ? B.pair_row : nullptr, mu.f(), va.f(), P(NLV_P_BN2_W), P(NLV_P_BN2_W + 1), 1e-5f, R, p1.p,
+                               reinterpret_cast<uint8_t*>(arg.p), xmax.p, st));
+      pt.mean2 = mu; pt.var2 = va;
+    } else {
+      RUN(nlv_bn_apply_maxpool(c1.p, nullptr, rm, rv, P(NLV_P_BN2_W), P(NLV_P_BN2_W + 1), 1e-5f, R, p1.p, reinterpret_cast<uint8_t*>(arg.p), xmax.p,
+                               st));
+      pt.mean2 = mk(rm, NLV_F32, 1, 128); pt.var2 = mk(rv, NLV_F32, 1, 128);
+    }
+    xmax_keep = xmax;
+  } else {
+    pool_fused = false;
+    col1 = ctx(R * 196, 104, AD);
+    T b1 = tmp(R * 196, 128, AD);
+    OOM_CHECK();
+    RUN(nlv_im2col_mask(masks.f(), (int)R, col1.p, col1.dt, 104, st));
+    CK(mm(col1, K_, w_c0, K_, c1, P(NLV_P_CONV0_B), nullptr, true));                                     // conv 7x7 s2 + ReLU
+    CK(bn_fwd(c1, B.seg196, B.pair_row, 196, NLV_P_BN2_W, 0.01f, false, b1, &pt.mean2, &pt.var2));
+    OOM_CHECK();
+    RUN(nlv_maxpool_fwd(b1.p, b1.dt, (int)R, 128, p1.p, p1.dt, reinterpret_cast<uint8_t*>(arg.p), st));
+  }
   T col2 = ctx(R * 49, 1152, AD), c2 = ctx(R * 49, 256, AD), b2 = tmp(R * 49, 256, AD);
   OOM_CHECK();
   RUN(nlv_im2col_3x3(p1.p, p1.dt, (int)R, 7, 7, 128, col2.p, col2.dt, st));
@@ -661,7 +695,7 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
   CK(mm(uf, K_, W(NLV_P_UNION_W, 256, 2048), K_, vr_in, P(NLV_P_UNION_B), &b2));
   CK(mm(vr_in.view(R, 12544), K_, w_vr, K_, rel.cs(1024, 512), P(NLV_P_VR_B)));
   RUN(nlv_assemble_tokens(fo.f(), B.pair_idx, B.labels, P(NLV_P_EMB1), P(NLV_P_EMB2), R, rel.f(), st));
-  pt.uf_op = uf; pt.col1 = col1; pt.c1 = c1; pt.arg = arg; pt.col2 = col2; pt.c2 = c2; pt.vr_in = vr_in;
+  pt.uf_op = uf; pt.col1 = col1; pt.c1 = c1; pt.arg = arg; pt.xmax = xmax_keep; pt.col2 = col2; pt.c2 = c2; pt.vr_in = vr_in;
   return NLV_OK;
 }
 
@@ -701,13 +735,31 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   }
   T dcol2 = tmp(R * 49, 1152, AD);
   CK(mm(dc2, K_, w_c4, MN_, dcol2));
-  T dp1 = tmp(R * 49, 128, NLV_F32), db1 = tmp(R * 196, 128, AD);
+  T dp1 = tmp(R * 49, 128, NLV_F32);
   OOM_CHECK();
   RUN(nlv_col2im_3x3(dcol2.p, dcol2.dt, (int)R, 7, 7, 128, dp1.f(), st));
-  RUN(nlv_maxpool_bwd(dp1.f(), reinterpret_cast<const uint8_t*>(pt.arg.p), (int)R, 128, db1.p, db1.dt, st));
   T dc1 = tmp(R * 196, 128, AD);
-  CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.pair_row, 196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1, G(NLV_P_CONV0_B)));   // + 7x7 conv bias gradient
-  {
+  if (fused_mask_conv() && pool_fused) {
+    // pooling + BatchNorm + ReLU backward in one sweep over the pooled gradient (maskconv.cu); + the 7x7 conv bias gradient
+    T ws = tmp((long long)B.nv * 2 * 128, 1, NLV_F32, 2);
+    OOM_CHECK();
+    g_next_units = (double)R * (49 * 128 * (4 + 2) + 49 * 128 * (4 + 1) + 196 * 128 * (2 + 2));
+    RUN(nlv_pool_bn_bwd(dp1.f(), reinterpret_cast<const uint8_t*>(pt.arg.p), pt.c1.p, pt.xmax.p, B.nv > 1 ? B.pair_row : nullptr, B.seg196, B.seg49,
+                        B.nv, pt.mean2.f(), pt.var2.f(), P(NLV_P_BN2_W), 1e-5f, training ? 1 : 0, R, reinterpret_cast<double*>(ws.p), dc1.p,
+                        G(NLV_P_BN2_W), G(NLV_P_BN2_W + 1), G(NLV_P_CONV0_B), st));
+  } else {
+    T db1 = tmp(R * 196, 128, AD);
+    OOM_CHECK();
+    RUN(nlv_maxpool_bwd(dp1.f(), reinterpret_cast<const uint8_t*>(pt.arg.p), (int)R, 128, db1.p, db1.dt, st));
+    CK(bn_bwd(db1, pt.c1, nullptr, B.seg196, B.pair_row, 196, NLV_P_BN2_W, pt.mean2, pt.var2, true, dc1, G(NLV_P_CONV0_B)));   // + 7x7 conv bias gradient
+  }
+  if (fused_mask_conv()) {
+    Scope s2(this);
+    T ws = tmp(nlv_mask_conv1_dw_ws_floats(), 1, NLV_F32);
+    OOM_CHECK();
+    g_next_units = (double)R * (2 * 27 * 27 * 4 + 196 * 128 * 2);
+    RUN(nlv_mask_conv1_dw(dc1.p, masks.f(), R, ws.f(), G(NLV_P_CONV0_W), st));
+  } else {
     Scope s2(this);
     T g0 = tmp(128, 104, NLV_F32);
     CK(mm(dc1, MN_, pt.col1, MN_, g0));

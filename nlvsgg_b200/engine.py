@@ -211,10 +211,12 @@ def plan_desc(plan: Plan, dsg: bool = False) -> "_C.BatchDesc":
                  "inv", "out_src", "out_inv", "passthrough", "both_w"):
         setattr(b, name, _ptr(getattr(plan, name, None)))
     b.n_local_work, b.n_glob_work, b.has_passthrough = plan.n_local_work, plan.n_glob_work, 1 if plan.has_passthrough else 0
+    b.work_sorted, b.n_local_long, b.n_glob_long = 1, plan.n_local_long, plan.n_glob_long
     if dsg:
         b.cls_perm, b.cls_iperm, b.cls_pos, b.cls_work = (plan.cls_perm.data_ptr(), plan.cls_iperm.data_ptr(),
                                                           plan.cls_pos.data_ptr(), plan.cls_work.data_ptr())
         b.n_cls_work = plan.n_cls_work
+        b.n_cls_long = plan.n_cls_long
     return b
 
 

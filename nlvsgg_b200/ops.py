@@ -417,3 +417,46 @@ def sumsq(x, out):
 def adamw_step(p, g, m, v, lr, beta1, beta2, eps, wd, step, total_sq=None, max_norm=0.0, p_bf16=None):
     _call("nlv_adamw_step", _ptr(p), _ptr(g), _ptr(m), _ptr(v), _LL(p.numel()), _F(lr), _F(beta1), _F(beta2), _F(eps), _F(wd),
           int(step), _ptr(total_sq), _F(max_norm), _ptr(p_bf16))
+
+
+# ---- spatial-mask branch, first stage without the im2col matrix (csrc/maskconv.cu; bf16 path) ----
+def mask_conv1_fwd(masks, w, bias, pair_video, seg196, nv, momentum=0.01, running_mean=None, running_var=None, want_stats=True):
+    """relu(conv7x7/2(masks) + bias) as bf16 [r*196,128] and, for training, its per-video BatchNorm statistics."""
+    _need_cuda(masks, w, bias)
+    r = masks.shape[0]
+    out = torch.empty(r * 196, 128, device=masks.device, dtype=torch.bfloat16)
+    ws = torch.empty(nv * 2 * 128, device=masks.device, dtype=torch.float64)
+    mean = torch.empty(nv, 128, device=masks.device, dtype=torch.float32) if want_stats else None
+    var = torch.empty(nv, 128, device=masks.device, dtype=torch.float32) if want_stats else None
+    _call("nlv_mask_conv1_fwd", _ptr(masks.contiguous()), _ptr(w.contiguous()), _ptr(bias), _LL(r), _ptr(pair_video), _ptr(seg196), nv,
+          _ptr(out), _F(momentum), _ptr(ws), _ptr(mean), _ptr(var), _ptr(running_mean), _ptr(running_var))
+    return out, mean, var
+
+
+def bn_apply_maxpool(x, pair_video, mean, var, w, b, r, eps=1e-5, want_xmax=False):
+    y = torch.empty(r * 49, 128, device=x.device, dtype=torch.bfloat16)
+    arg = torch.empty(r * 49, 128, device=x.device, dtype=torch.uint8)
+    xmax = torch.empty(r * 49, 128, device=x.device, dtype=torch.bfloat16) if want_xmax else None
+    _call("nlv_bn_apply_maxpool", _ptr(x), _ptr(pair_video), _ptr(mean), _ptr(var), _ptr(w), _ptr(b), _F(eps), _LL(r), _ptr(y), _ptr(arg),
+          _ptr(xmax))
+    return (y, arg, xmax) if want_xmax else (y, arg)
+
+
+def pool_bn_bwd(dp, arg, x, xmax, pair_video, seg196, seg49, nv, mean, var, w, r, use_batch_stats=True, eps=1e-5):
+    """dx (bf16, at the conv output), BatchNorm dw / db and the column sums of dx from the pooled gradient."""
+    ws = torch.empty(nv * 2 * 128, device=x.device, dtype=torch.float64)
+    dx = torch.empty(r * 196, 128, device=x.device, dtype=torch.bfloat16)
+    dw, db, cs = (torch.zeros(128, device=x.device, dtype=torch.float32) for _ in range(3))
+    _call("nlv_pool_bn_bwd", _ptr(dp), _ptr(arg), _ptr(x), _ptr(xmax), _ptr(pair_video), _ptr(seg196), _ptr(seg49), nv, _ptr(mean), _ptr(var),
+          _ptr(w), _F(eps), 1 if use_batch_stats else 0, _LL(r), _ptr(ws), _ptr(dx), _ptr(dw), _ptr(db), _ptr(cs))
+    return dx, dw, db, cs
+
+
+def mask_conv1_dw(dy, masks):
+    r = masks.shape[0]
+    f = _C.lib().nlv_mask_conv1_dw_ws_floats
+    f.restype = ctypes.c_longlong
+    ws = torch.empty(int(f()), device=dy.device, dtype=torch.float32)
+    dw = torch.empty(128, 98, device=dy.device, dtype=torch.float32)
+    _call("nlv_mask_conv1_dw", _ptr(dy), _ptr(masks.contiguous()), _LL(r), _ptr(ws), _ptr(dw))
+    return dw

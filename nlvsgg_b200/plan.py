@@ -95,6 +95,16 @@ def work_items(seg_start: np.ndarray, seg_len: np.ndarray, seg_pad: Optional[np.
     return out
 
 
+def long_first(work: np.ndarray):
+    """Work list with the items of segments longer than 16 rows in front (stable), and their count: the two-kernel attention
+    backward is launched over those alone (nlv_attn_bwd_sorted)."""
+    is_long = work[:, 1] > 16
+    n_long = int(is_long.sum())
+    if n_long == 0 or n_long == len(work):
+        return work, n_long
+    return np.ascontiguousarray(work[np.argsort(~is_long, kind="stable")]), n_long
+
+
 def _ranges(starts: np.ndarray, lens: np.ndarray) -> np.ndarray:
     """Concatenation of arange(starts[i], starts[i]+lens[i])."""
     total = int(lens.sum())
@@ -133,7 +143,7 @@ class Plan:
         # padded keys of a frame = longest frame of its video (l, lib/transformer_wk.py:133) - its own pairs
         has = nfr > 0
         lmax = np.repeat(np.maximum.reduceat(cnt, fbase[:-1][has]), nfr[has]) if F else np.zeros(0, dtype=np.int64)
-        lw = work_items(start[:-1][nz], cnt[nz], (lmax - cnt)[nz])
+        lw, self.n_local_long = long_first(work_items(start[:-1][nz], cnt[nz], (lmax - cnt)[nz]))
         # ---- windows {j, j+1} inside each video (lib/transformer_wk.py:163-185): keep those with any token
         is_last = np.zeros(F, dtype=bool)
         is_last[fbase[1:][nfr > 0] - 1] = True
@@ -162,7 +172,7 @@ class Plan:
         # videos without any window (single frame): output = spatial-encoder output (:187-188)
         passthrough = np.where(out_src < 0, np.arange(self.R), -1).astype(np.int32)
         self.has_passthrough = bool((passthrough >= 0).any())
-        gw = work_items(wbase, wlen)
+        gw, self.n_glob_long = long_first(work_items(wbase, wlen))
 
         both_w = (inv >= 0).sum(1).astype(np.float32)          # windows a token appears in (0, 1 or 2) -> 1 / count
         both_w = np.where(both_w > 0, 1.0 / np.maximum(both_w, 1.0), 0.0).astype(np.float32)
@@ -204,7 +214,7 @@ class Plan:
                 pos = np.arange(self.R) - np.repeat(s_start, s_len)
             iperm = np.empty(self.R, dtype=np.int64)
             iperm[perm] = np.arange(self.R)
-            cw = work_items(s_start, s_len)
+            cw, self.n_cls_long = long_first(work_items(s_start, s_len))
             arrays.update(cls_perm=perm.astype(np.int32), cls_iperm=iperm.astype(np.int32), cls_pos=pos.astype(np.int32), cls_work=cw)
             self.n_cls_work = len(cw)
         if extra:
