@@ -179,8 +179,12 @@ def run_reference(a):
     print(json.dumps(line), flush=True)
 
 
+PROFILE_STEPS = 5      # instrumented steps behind the roofline numbers (a single step's per-call times wander by a few percent)
+
+
 def profile_one_step(step_fn):
-    """Run `step_fn` once with the sequencer's per-call CUDA-event timing on -> [(entry, ms, flops, bytes, m, n, k, dtype)]."""
+    """Run `step_fn` (PROFILE_STEPS steps) with the sequencer's per-call CUDA-event timing on
+    -> [(entry, ms, flops, bytes, m, n, k, dtype)] of all of them."""
     import ctypes
     from nlvsgg_b200 import _C
     lib = _C.lib()
@@ -189,7 +193,7 @@ def profile_one_step(step_fn):
     lib.nlv_profile(1)
     step_fn()
     lib.nlv_profile(0)
-    buf = ctypes.create_string_buffer(1 << 20)
+    buf = ctypes.create_string_buffer(4 << 20)
     lib.nlv_profile_read(buf, ctypes.c_longlong(len(buf)))
     recs = []
     for line in buf.value.decode().splitlines():
@@ -236,7 +240,9 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
     tpeak = pk.get("bf16_tflops_sustained") or 1400.0
     hpeak = pk.get("hbm_gbs") or 6650.0
     src = "MEASURED_PEAKS.json" if pk else "fallback (B200_PROFILING.md)"
-    g = [r for r in recs if r[0] == "nlv_gemm" and r[7] == 1 and r[2] > 0]
+    reps = PROFILE_STEPS
+    recs = [(r[0], r[1] / reps, r[2] / reps, r[3] / reps) + tuple(r[4:]) for r in recs]     # per-step shares of every record
+    g = [r for r in recs if r[0] in ("nlv_gemm", "nlv_conv3x3_dgrad") and r[7] == 1 and r[2] > 0]      # every launch of the tcgen05 kernel
     roof = None
     if g:
         tsum, fsum = sum(r[1] for r in g) / 1e3, sum(r[2] for r in g)
@@ -247,8 +253,8 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
             pass
         ach = fsum / tsum / 1e12
         roof = {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05)", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s",
-                "frac": ach / tpeak, "traffic": traffic, "launches_per_step": len(g), "algorithmic_flop_per_step": fsum,
-                "algorithmic_flop_per_launch_avg": fsum / len(g), "avg_launch_ms": tsum * 1e3 / len(g),
+                "frac": ach / tpeak, "traffic": traffic, "launches_per_step": len(g) // reps, "algorithmic_flop_per_step": fsum,
+                "algorithmic_flop_per_launch_avg": fsum * reps / len(g), "avg_launch_ms": tsum * 1e3 * reps / len(g),
                 "kernel_share_of_step": tsum * 1e3 / step_ms, "peak_source": f"{src} bf16_tflops_sustained (kernel timed inside a long step)"}
 
     def hbm(names, extra_bytes=0.0):
@@ -256,7 +262,7 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
         if not rs:
             return None
         ms, by = sum(r[1] for r in rs), sum(r[3] for r in rs) + extra_bytes
-        return {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hpeak, "unit": "GB/s", "frac": by / ms / 1e6 / hpeak, "launches": len(rs),
+        return {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hpeak, "unit": "GB/s", "frac": by / ms / 1e6 / hpeak, "launches": len(rs) // reps,
                 "ms_per_step": ms, "algorithmic_bytes_per_step": by}
     extra = {
         "gather_union_rows": hbm(("nlv_union_unpack", "nlv_nchw_to_rows"), 2.0 * n_stored_values),
@@ -277,7 +283,7 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
         c = by_entry.setdefault(r[0], [0, 0.0])
         c[0] += 1
         c[1] += r[1]
-    return roof, extra, {k: {"calls": v[0], "ms": round(v[1], 4)} for k, v in sorted(by_entry.items(), key=lambda kv: -kv[1][1])}
+    return roof, extra, {k: {"calls": v[0] // reps, "ms": round(v[1], 4)} for k, v in sorted(by_entry.items(), key=lambda kv: -kv[1][1])}
 
 
 def dropin_legs(dev, precision):
@@ -602,7 +608,8 @@ def main():
 
     def instrumented():
         step_s.record()
-        resident_step()
+        for _ in range(PROFILE_STEPS):
+            resident_step()
         step_e.record()
     if rank == 0:
         recs = profile_one_step(instrumented)
@@ -621,7 +628,7 @@ def main():
             o1.record()
             torch.cuda.synchronize()
             adamw_ms = o0.elapsed_time(o1)
-        roof, extra, by_entry = rooflines(recs, step_s.elapsed_time(step_e), n_stored, adamw_ms, trainer.n_params)
+        roof, extra, by_entry = rooflines(recs, step_s.elapsed_time(step_e) / PROFILE_STEPS, n_stored, adamw_ms, trainer.n_params)
 
     if world > 1:
         torch.distributed.barrier()

@@ -78,6 +78,10 @@ typedef struct nlv_gemm_args {
 } nlv_gemm_args;
 
 int nlv_gemm(const nlv_gemm_args* args, void* stream);
+/* Data gradient of the 3x3 / pad 1 convolution over NHWC [r,7,7,c] maps (lib/sttran.py:342) as one implicit GEMM (the taps are 4-D TMA
+ * boxes with a zero-filled halo; no column-gradient matrix, no col2im pass): dx[r*49, c_in] (fp32 or bf16) from dy bf16 [r*49, c_out]
+ * and wt bf16 [c_in, 9*c_out] with k = (ky*3 + kx) * c_out + channel.  c_out % 64 == 0, c_in <= 128. */
+int nlv_conv3x3_dgrad(const void* dy, long long r, int c_out, const void* wt, int c_in, void* dx, int dx_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Box / mask kernels

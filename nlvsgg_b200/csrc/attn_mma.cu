@@ -87,13 +87,15 @@ __device__ __forceinline__ float quad_sum(float x) {
 // after the copy in the K and V tiles (`fix_junk`) — every product contracting over the columns has K or V as one operand
 // — and are never stored.  lw = 0 with 4-byte copies when the pointers / strides are not 16-byte aligned.
 
-// zero the words outside [lw, lw + nwords) of a 16-row tile that copies never touch (lw + nwords rounded up to a chunk .. 127)
+// zero the words outside [lw, lw + nwords) of a 16-row tile that copies never touch (lw + nwords rounded up to a chunk .. 127).
+// Lane l owns row l & 15 and every second 4-word group of the pad: no index divisions (the pad is 0..4 groups wide per row).
 __device__ __forceinline__ void zero_pad(uint32_t tile, int nwords, int lane, Lead ld = Lead{0, false}) {
   const int first = ld.wide ? ((ld.lw + nwords + 3) & ~3) : nwords;
-  const int npad = 128 - first;
-  for (int i = lane; i < 16 * npad; i += 32) {
-    const int r = i / npad, w = first + i % npad;
-    asm volatile("st.shared.b32 [%0], %1;" ::"r"(tile + r * ROWB + w * 4), "r"(0u) : "memory");
+  const uint32_t row = tile + (lane & 15) * ROWB;
+  for (int w = first + (lane >> 4) * 4; w < 128; w += 8) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (w + j < 128) asm volatile("st.shared.b32 [%0], %1;" ::"r"(row + (w + j) * 4), "r"(0u) : "memory");
   }
 }
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
@@ -273,10 +275,12 @@ attn_fwd_mma_kernel(MArgs a, bf16* __restrict__ o, int ldo, float* __restrict__ 
     }
     l0 = l0 * corr0 + ps0; l1 = l1 * corr1 + ps1;     // per-thread partial row sums; combined over the quad at the end
     if (a.drop.thr16 != 0u) {   // O accumulates the dropped weights; the normaliser l keeps all of them
+      // one Philox call per lane = (query row lane & 15, key group lane >> 4); the fragment's rows / groups come by shuffle
+      const uint32_t mine = keep8_attn(a.drop, seg0 + q0 + (lane & 15), a.heads, h, (k0 >> 3) + (lane >> 4));
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        const uint32_t kp0 = keep8_attn(a.drop, seg0 + q0 + g, a.heads, h, (k0 >> 3) + n) >> (2 * t);
-        const uint32_t kp1 = keep8_attn(a.drop, seg0 + q0 + g + 8, a.heads, h, (k0 >> 3) + n) >> (2 * t);
+        const uint32_t kp0 = __shfl_sync(0xffffffffu, mine, g + 16 * n) >> (2 * t);
+        const uint32_t kp1 = __shfl_sync(0xffffffffu, mine, g + 8 + 16 * n) >> (2 * t);
         s[n][0] = (kp0 & 1u) ? s[n][0] * a.drop.scale : 0.f; s[n][1] = (kp0 & 2u) ? s[n][1] * a.drop.scale : 0.f;
         s[n][2] = (kp1 & 1u) ? s[n][2] * a.drop.scale : 0.f; s[n][3] = (kp1 & 2u) ? s[n][3] * a.drop.scale : 0.f;
       }
@@ -469,6 +473,7 @@ attn_bwd_fused_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, cons
                           bf16* __restrict__ dk, int lddk, bf16* __restrict__ dv, int lddv) {
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float lse_s[16];
+  __shared__ uint8_t keep_s[16][2];                     // [query row][key group]: keep bits of 8 keys
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int4 w = a.work[blockIdx.x / a.heads];
   const int L = w.y;
@@ -485,6 +490,9 @@ attn_bwd_fused_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, cons
   load_rows(Vs, a.v + col0, a.ldv, seg0, L, r0, nr, nwords, lane, le);
   load_rows(Gs, dout + col0, lddo, seg0, L, r0, nr, nwords, lane, le);
   if (threadIdx.x < 16) lse_s[threadIdx.x] = (int)threadIdx.x < L ? lse[(seg0 + threadIdx.x) * a.heads + h] : 0.f;
+  // dropout: the keep bits of all 16 x 16 weights, one Philox call per (query row, key group) — 32 calls on warp 2 instead of every
+  // thread of every warp regenerating the bits of its own fragment elements (640 calls)
+  if (a.drop.thr16 != 0u && warp == 2) keep_s[lane & 15][lane >> 4] = (uint8_t)keep8_attn(a.drop, seg0 + (lane & 15), a.heads, h, lane >> 4);
   cp_async_wait_all();
   if (le.wide) { __syncwarp(); fix_junk(Ks, nwords, lane, le, r0, nr); fix_junk(Vs, nwords, lane, le, r0, nr); }   // own rows
   __syncthreads();
@@ -501,8 +509,8 @@ attn_bwd_fused_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, cons
     if (a.drop.thr16 != 0u) {
 #pragma unroll
       for (int n = 0; n < 2; ++n) {
-        const uint32_t kp0 = keep8_attn(a.drop, seg0 + g, a.heads, h, n) >> (2 * t);
-        const uint32_t kp1 = keep8_attn(a.drop, seg0 + g + 8, a.heads, h, n) >> (2 * t);
+        const uint32_t kp0 = (uint32_t)keep_s[g][n] >> (2 * t);
+        const uint32_t kp1 = (uint32_t)keep_s[g + 8][n] >> (2 * t);
         dp[n][0] = (kp0 & 1u) ? dp[n][0] * a.drop.scale : 0.f; dp[n][1] = (kp0 & 2u) ? dp[n][1] * a.drop.scale : 0.f;
         dp[n][2] = (kp1 & 1u) ? dp[n][2] * a.drop.scale : 0.f; dp[n][3] = (kp1 & 2u) ? dp[n][3] * a.drop.scale : 0.f;
       }
@@ -538,7 +546,7 @@ attn_bwd_fused_mma_kernel(MArgs a, const bf16* __restrict__ dout, int lddo, cons
         const float p = (qi < L && key < L) ? __expf(s[n][c] * a.scale - lse_s[qi]) : 0.f;
         float pdv = p, dpv = dp[n][c];
         if (a.drop.thr16 != 0u) {
-          const bool kept = (keep8_attn(a.drop, seg0 + qi, a.heads, h, key >> 3) >> (key & 7)) & 1u;
+          const bool kept = ((uint32_t)keep_s[qi][key >> 3] >> (key & 7)) & 1u;
           pdv = kept ? p * a.drop.scale : 0.f;
           dpv = kept ? dpv * a.drop.scale : 0.f;
         }

@@ -5,6 +5,8 @@
 namespace nlv {
 
 int gemm_tc(const nlv_gemm_args& g, cudaStream_t stream);  // gemm_tc.cu
+int gemm_tc_conv3x3(const void* x, long long pairs, int c, const void* b, int ldb, int n, int flip, void* d, int d_dtype, int ldd,
+                    const float* bias, int relu, cudaStream_t stream);
 
 namespace {
 
@@ -131,4 +133,13 @@ extern "C" int nlv_gemm(const nlv_gemm_args* g, void* stream) {
   nlv_gemm_args t = *g;
   t.ab_dtype = dt;
   return gemm_simt(t, s);
+}
+
+/* Data gradient of the 3x3 / pad 1 convolution of the mask branch (lib/sttran.py:342) as ONE implicit GEMM on the tcgen05 kernel:
+ * dx[r*49, c_in] = sum over taps, c_out of dy[r, y + 1 - ky, x + 1 - kx, c_out] * w[c_out, c_in, ky, kx], with
+ * dy bf16 NHWC [r,7,7,c_out] and wt bf16 [c_in, 9 * c_out] (k = (ky*3 + kx) * c_out + channel: the [c_out, c_in*9] weight
+ * transposed).  Replaces the [r*49, 9*c_in] column-gradient product + nlv_col2im_3x3. */
+extern "C" int nlv_conv3x3_dgrad(const void* dy, long long r, int c_out, const void* wt, int c_in, void* dx, int dx_dtype, void* stream) {
+  NLV_CHECK_ARG(dy && wt && dx, "conv3x3_dgrad: null pointer");
+  return nlv::gemm_tc_conv3x3(dy, r, c_out, wt, 9 * c_out, c_in, 1, dx, dx_dtype, c_in, nullptr, 0, (cudaStream_t)stream);
 }

@@ -22,6 +22,7 @@
 // lib/transformer.py:9-13,38-42.
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 #include "philox.cuh"
@@ -120,6 +121,20 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
       ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// 4-D boxes [channels, x, y, pair] of an NHWC map: the A operand of the implicit 3x3 convolution products.  Coordinates are signed;
+// elements outside the map (the halo of a shifted tap) are zero-filled by the TMA unit.
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
@@ -205,6 +220,12 @@ struct Params {
   DropCfg drop;
   int num_m_blocks, num_n_blocks;
   int k_splits, kb_per_split;  // split-K: work item = (tile, k range); partial sums are atomically added to a zeroed fp32 D
+  // implicit 3x3 convolution (conv_c > 0; A K-major only): A is an NHWC map [pairs, 7, 7, conv_c]; an m-tile is TWO pairs = 98 rows
+  // of the 128-row instruction (rows 98.. compute on stale shared memory and are never stored); k-block kb = tap kb / (conv_c / 64),
+  // channels (kb % (conv_c / 64)) * 64, loaded as the 4-D box [64, 7, 7, 2] at (c0, 1 - kx, 1 - ky, pair) (conv_flip) or
+  // (c0, kx - 1, ky - 1, pair).  tile_rows = rows of D per m-tile (128, or 98), a_tx = bytes of one A box.
+  int conv_c, conv_flip, tile_rows;
+  uint32_t a_tx;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -220,7 +241,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   constexpr int CM = MODE == 0 ? 1 : 2;          // CTAs per cluster
   constexpr bool PAIR = MODE == 2;               // one cta_group::2 MMA over both CTAs
   constexpr int STAGES = C::STAGES;
-  constexpr uint32_t STAGE_TX = (A_STAGE_BYTES + C::B_STAGE_BYTES) * (PAIR ? 2 : 1);   // pair: both CTAs' boxes complete on the leader's barrier
+  const uint32_t STAGE_TX = (p.a_tx + C::B_STAGE_BYTES) * (PAIR ? 2 : 1);   // pair: both CTAs' boxes complete on the leader's barrier
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -293,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         // n-block fastest: the ~74 clusters running at any moment cover a band of ~9 m-pairs x all n-blocks, so an A
         // row block is fetched from DRAM once and re-read from L2 by the other n-blocks (m-fastest order streamed all
         // of A once per n-block: 3x the algorithmic DRAM traffic on the [22931 x 1936 x 1936] products)
-        const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+        const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * p.tile_rows;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
         const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
         const int nb0 = PAIR ? n0 + cta_rank * (n_inst_of(n0) / 2) : n0;     // first B row this CTA stages (pair mode)
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -308,6 +329,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             if constexpr (A_MN) {
 #pragma unroll
               for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d_pair(sa + i * ATOM_BYTES, &tmap_a, lbar, m0 + 64 * i, k0);
+            } else if (p.conv_c > 0) {
+              const int kpt = p.conv_c >> 6, tap = kb / kpt, ky = tap / 3, kx = tap - 3 * ky;
+              tma_load_4d_pair(sa, &tmap_a, lbar, (kb - tap * kpt) << 6, p.conv_flip ? 1 - kx : kx - 1, p.conv_flip ? 1 - ky : ky - 1, m0 / 49);
             } else {
               tma_load_2d_pair(sa, &tmap_a, lbar, k0, m0);
             }
@@ -324,6 +348,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           if constexpr (A_MN) {
 #pragma unroll
             for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * ATOM_BYTES, &tmap_a, full_bar(stage), m0 + 64 * i, k0);
+          } else if (p.conv_c > 0) {
+            const int kpt = p.conv_c >> 6, tap = kb / kpt, ky = tap / 3, kx = tap - 3 * ky;
+            tma_load_4d(sa, &tmap_a, full_bar(stage), (kb - tap * kpt) << 6, p.conv_flip ? 1 - kx : kx - 1, p.conv_flip ? 1 - ky : ky - 1, m0 / 49);
           } else {
             tma_load_2d(sa, &tmap_a, full_bar(stage), k0, m0);
           }
@@ -414,15 +441,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const bool bias_vec = ((uintptr_t)p.bias & 15) == 0;
     const bool res_fast = p.residual != nullptr && p.r_dtype != NLV_BF16 && !split && !d_bf16 && vec_ok && (p.ldr & 3) == 0 &&
                           ((uintptr_t)p.residual & 15) == 0;
+    // bf16 residual rows are requested one chunk ahead too (same registers), each thread its own row
+    const bool res_b16 = p.residual != nullptr && p.r_dtype == NLV_BF16 && !split && (p.ldr & 7) == 0 && ((uintptr_t)p.residual & 15) == 0 &&
+                         (p.n & 7) == 0;
     uint8_t* const stg = smem_raw + (bar_base + 256u - smem_u32(smem_raw)) + (warp - 2) * 4096;   // this warp's staging tile
     for (int work = work0; work < num_work; work += work_stride, ++iter) {
       const int tile = work / p.k_splits;
-      const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * BLOCK_M;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
+      const int m0 = ((tile / p.num_n_blocks) * CM + cta_rank) * p.tile_rows;   // may lie beyond M for the odd tile of a pair: loads zero-fill, stores are skipped
       const int n0 = (tile % p.num_n_blocks) * BLOCK_N;
       const int acc = iter % ACC;
       const uint32_t acc_phase = (iter / ACC) & 1;
       const int row = m0 + quarter * 32 + lane;
-      const bool row_ok = row < p.m;
+      const int rows_here = min(p.tile_rows, p.m - m0) - quarter * 32;      // rows of this warp's quarter that exist in D (may be <= 0)
+      const bool row_ok = lane < rows_here;
       constexpr int CSTEP = 32 * (NUM_EPI_WARPS / 4);
       // fp32 residual rows are requested one chunk AHEAD of their use — the first chunk's before the accumulator is even
       // ready — so that the DRAM latency of the residual stream overlaps the MMAs / the previous chunk's stores instead of
@@ -430,11 +461,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       float4 rcur[8];
       // (mapping of the transposed store below: register `it` = row it * 4 + lane / 8 of the warp's 32, columns 4 (lane % 8) ..)
       auto prefetch_res = [&](int c0, float4 (&dst)[8]) -> bool {
+        if (res_b16) {      // bf16 residual (the mask-branch map under the union 1x1 conv): this thread's own row, 32 columns = 64 bytes
+          if (c0 >= BLOCK_N || n0 + c0 + 32 > p.n) return false;                 // warp-uniform
+          const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.residual) + (size_t)row * p.ldr + n0 + c0);
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint4 t = row_ok ? src[it] : make_uint4(0u, 0u, 0u, 0u);
+            dst[it] = make_float4(__uint_as_float(t.x), __uint_as_float(t.y), __uint_as_float(t.z), __uint_as_float(t.w));
+          }
+          return true;
+        }
         if (!res_fast || c0 >= BLOCK_N || n0 + c0 + 32 > p.n) return false;      // warp-uniform
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int grow = m0 + quarter * 32 + it * 4 + (lane >> 3);
-          dst[it] = grow < p.m ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)grow * p.ldr + n0 + c0 + (lane & 7) * 4)
+          dst[it] = (it * 4 + (lane >> 3) < rows_here) ? *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + (size_t)grow * p.ldr + n0 + c0 + (lane & 7) * 4)
                                : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         return true;
@@ -546,7 +587,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const bool res_late = fast && !d_bf16 && res_fast;          // fp32 residual added after the transposition (coalesced)
         if (p.residual != nullptr && !res_late && row_ok) {
           const size_t roff = (size_t)row * p.ldr + n0 + c0;
-          if (p.r_dtype == NLV_BF16) {
+          if (p.r_dtype == NLV_BF16 && res_b16 && have_now) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const uint32_t wv[4] = {__float_as_uint(rnow[it].x), __float_as_uint(rnow[it].y), __float_as_uint(rnow[it].z), __float_as_uint(rnow[it].w)};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wv[q]));
+                f[it * 8 + 2 * q] += t.x; f[it * 8 + 2 * q + 1] += t.y;
+              }
+            }
+          } else if (p.r_dtype == NLV_BF16) {
             const __nv_bfloat16* r = reinterpret_cast<const __nv_bfloat16*>(p.residual) + roff;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
@@ -569,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int rr = it * 4 + sub;
             float4 o = *reinterpret_cast<const float4*>(stg + rr * 128 + ((piece ^ (rr & 7)) << 4));
             const int grow = m0 + quarter * 32 + rr;
-            if (grow < p.m) {
+            if (rr < rows_here) {
               if (res_late) {
                 float4 t;
                 if (have_now) t = rnow[it];
@@ -599,7 +650,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             const int rr = it * 8 + sub;
             const uint4 o = *reinterpret_cast<const uint4*>(stg + rr * 64 + ((piece ^ ((rr >> 1) & 3)) << 4));
             const int grow = m0 + quarter * 32 + rr;
-            if (grow < p.m) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)grow * p.ldd + n0 + c0 + piece * 8) = o;
+            if (rr < rows_here) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.d) + (size_t)grow * p.ldd + n0 + c0 + piece * 8) = o;
           }
           __syncwarp();
         } else if (row_ok) {
@@ -680,43 +731,9 @@ int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, 
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int MODE>
-int launch(const nlv_gemm_args& g, cudaStream_t stream) {
+int run_kernel(const CUtensorMap& ta, const CUtensorMap& tb, const Params& p, cudaStream_t stream) {
   using C = Cfg<BLOCK_N, MODE>;
   constexpr int CM = MODE == 0 ? 1 : 2;
-  CUtensorMap ta, tb;
-  int rc;
-  if (A_MN) rc = make_tmap(&ta, g.a, g.k, g.m, g.lda, 64, BLOCK_K);
-  else      rc = make_tmap(&ta, g.a, g.m, g.k, g.lda, BLOCK_K, BLOCK_M);
-  if (rc != NLV_OK) return rc;
-  if (B_MN) rc = make_tmap(&tb, g.b, g.k, g.n, g.ldb, 64, BLOCK_K);
-  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N / CM);   // MODE 1: the half this CTA multicasts; MODE 2: the half it stages
-  if (rc != NLV_OK) return rc;
-  Params p;
-  p.d = g.d; p.bias = g.bias; p.residual = g.residual;
-  p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.ldr = g.ldr;
-  p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
-  p.gate = g.gate; p.ldg = g.ldg; p.gate_dtype = g.gate_dtype;
-  p.gate_scale = g.gate_scale == 0.f ? 1.f : g.gate_scale;
-  p.drop.thr16 = g.drop.thr16; p.drop.scale = g.drop.scale; p.drop.seed_lo = g.drop.seed_lo; p.drop.seed_hi = g.drop.seed_hi;
-  p.drop.stream = g.drop.stream;
-  p.num_m_blocks = cdiv(g.m, BLOCK_M);
-  p.num_n_blocks = cdiv(g.n, BLOCK_N);
-  // split-K when the output has too few tiles to fill the GPU and the reduction is long (weight gradients of the
-  // conv / union layers reduce over R*49..R*196 rows into one or a handful of tiles)
-  const int nkb = cdiv(g.k, BLOCK_K);
-  const int tiles0 = p.num_m_blocks * p.num_n_blocks;
-  p.k_splits = 1;
-  p.kb_per_split = nkb;
-  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu && g.gate == nullptr &&
-      g.drop.thr16 == 0u) {
-    int want = sm_count() / tiles0;
-    if (want > nkb / 8) want = nkb / 8;
-    if (want > 1) {
-      p.kb_per_split = cdiv(nkb, want);
-      p.k_splits = cdiv(nkb, p.kb_per_split);
-      { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, stream); if (zrc != NLV_OK) return zrc; }
-    }
-  }
   auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, MODE>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -745,6 +762,95 @@ int launch(const nlv_gemm_args& g, cudaStream_t stream) {
   return NLV_OK;
 }
 
+template <int BLOCK_N, bool A_MN, bool B_MN, int MODE>
+int launch(const nlv_gemm_args& g, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N, MODE>;
+  constexpr int CM = MODE == 0 ? 1 : 2;
+  CUtensorMap ta, tb;
+  int rc;
+  if (A_MN) rc = make_tmap(&ta, g.a, g.k, g.m, g.lda, 64, BLOCK_K);
+  else      rc = make_tmap(&ta, g.a, g.m, g.k, g.lda, BLOCK_K, BLOCK_M);
+  if (rc != NLV_OK) return rc;
+  if (B_MN) rc = make_tmap(&tb, g.b, g.k, g.n, g.ldb, 64, BLOCK_K);
+  else      rc = make_tmap(&tb, g.b, g.n, g.k, g.ldb, BLOCK_K, BLOCK_N / CM);   // MODE 1: the half this CTA multicasts; MODE 2: the half it stages
+  if (rc != NLV_OK) return rc;
+  Params p;
+  p.d = g.d; p.bias = g.bias; p.residual = g.residual;
+  p.m = g.m; p.n = g.n; p.k = g.k; p.ldd = g.ldd; p.ldr = g.ldr;
+  p.d_dtype = g.d_dtype; p.r_dtype = g.r_dtype; p.relu = g.relu;
+  p.gate = g.gate; p.ldg = g.ldg; p.gate_dtype = g.gate_dtype;
+  p.gate_scale = g.gate_scale == 0.f ? 1.f : g.gate_scale;
+  p.drop.thr16 = g.drop.thr16; p.drop.scale = g.drop.scale; p.drop.seed_lo = g.drop.seed_lo; p.drop.seed_hi = g.drop.seed_hi;
+  p.drop.stream = g.drop.stream;
+  p.num_m_blocks = cdiv(g.m, BLOCK_M);
+  p.num_n_blocks = cdiv(g.n, BLOCK_N);
+  p.conv_c = 0; p.conv_flip = 0; p.tile_rows = BLOCK_M; p.a_tx = A_STAGE_BYTES;
+  // split-K when the output has too few tiles to fill the GPU and the reduction is long (weight gradients of the
+  // conv / union layers reduce over R*49..R*196 rows into one or a handful of tiles)
+  const int nkb = cdiv(g.k, BLOCK_K);
+  const int tiles0 = p.num_m_blocks * p.num_n_blocks;
+  p.k_splits = 1;
+  p.kb_per_split = nkb;
+  if (tiles0 * 2 <= sm_count() && nkb >= 32 && g.d_dtype == NLV_F32 && g.bias == nullptr && g.residual == nullptr && !g.relu && g.gate == nullptr &&
+      g.drop.thr16 == 0u) {
+    int want = sm_count() / tiles0;
+    if (want > nkb / 8) want = nkb / 8;
+    if (want > 1) {
+      p.kb_per_split = cdiv(nkb, want);
+      p.k_splits = cdiv(nkb, p.kb_per_split);
+      { int zrc = zero_fill(reinterpret_cast<float*>(g.d), g.m, g.n, g.ldd, stream); if (zrc != NLV_OK) return zrc; }
+    }
+  }
+  return run_kernel<BLOCK_N, A_MN, B_MN, MODE>(ta, tb, p, stream);
+}
+
+// 4-D tensor map over an NHWC bf16 map [pairs, 7, 7, c]: box = 64 channels x 7 x 7 x 2 pairs (98 rows of 128 bytes, 128B-swizzled)
+int make_tmap_nhwc7(CUtensorMap* tm, const void* ptr, long long pairs, int c) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled entry point unavailable");
+    return NLV_ERR_CUDA;
+  }
+  cuuint64_t gdim[4] = {(cuuint64_t)c, 7, 7, (cuuint64_t)pairs};
+  cuuint64_t gstride[3] = {(cuuint64_t)c * 2, (cuuint64_t)c * 2 * 7, (cuuint64_t)c * 2 * 49};
+  cuuint32_t box[4] = {64, 7, 7, 2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D) failed (%d) pairs=%lld c=%d ptr=%p", (int)r, pairs, c, ptr);
+    return NLV_ERR_CUDA;
+  }
+  return NLV_OK;
+}
+
+}  // namespace
+
+// D[pairs*49, n] = sum over taps / channels of the shifted NHWC map x[pairs,7,7,c] (bf16) times B[n, 9*c] (bf16, K-major, k = tap*c + channel):
+// flip = 0: x[p, y + ky - 1, x + kx - 1] (the forward 3x3 convolution, pad 1); flip = 1: x[p, y + 1 - ky, x + 1 - kx] (its data gradient).
+// n <= 128.  No im2col / col2im matrices: the taps are 4-D TMA boxes with a zero-filled halo.
+int gemm_tc_conv3x3(const void* x, long long pairs, int c, const void* b, int ldb, int n, int flip, void* d, int d_dtype, int ldd,
+                    const float* bias, int relu, cudaStream_t stream) {
+  NLV_CHECK_ARG(pairs >= 0 && c >= 64 && (c & 63) == 0 && n >= 8 && n <= 128 && (n & 7) == 0, "conv3x3: bad sizes (c %% 64, n <= 128)");
+  NLV_CHECK_ARG(pairs * 49 < 0x7fffffffll, "conv3x3: too many rows");
+  if (pairs == 0) return NLV_OK;
+  NLV_CHECK_ARG(((uintptr_t)x & 15) == 0 && ((uintptr_t)b & 15) == 0 && (ldb & 7) == 0, "conv3x3: operands must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  int rc = make_tmap_nhwc7(&ta, x, pairs, c);
+  if (rc != NLV_OK) return rc;
+  const bool pair_mode = pairs > 2;
+  rc = make_tmap(&tb, b, n, 9ll * c, ldb, BLOCK_K, pair_mode ? 64 : 128);
+  if (rc != NLV_OK) return rc;
+  Params p;
+  memset(&p, 0, sizeof(p));
+  p.d = d; p.bias = bias; p.m = (int)(pairs * 49); p.n = n; p.k = 9 * c; p.ldd = ldd; p.d_dtype = d_dtype; p.r_dtype = NLV_F32; p.relu = relu;
+  p.gate_scale = 1.f;
+  p.num_m_blocks = cdiv(pairs, 2); p.num_n_blocks = 1; p.k_splits = 1; p.kb_per_split = cdiv(p.k, BLOCK_K);
+  p.conv_c = c; p.conv_flip = flip; p.tile_rows = 98; p.a_tx = 98 * BLOCK_K * 2;
+  return pair_mode ? run_kernel<128, false, false, 2>(ta, tb, p, stream) : run_kernel<128, false, false, 0>(ta, tb, p, stream);
+}
+
+namespace {
 template <int BLOCK_N, int MODE>
 int dispatch_major(const nlv_gemm_args& g, cudaStream_t s) {
   if (g.a_major == NLV_MAJOR_K && g.b_major == NLV_MAJOR_K) return launch<BLOCK_N, false, false, MODE>(g, s);

@@ -63,6 +63,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -178,9 +181,9 @@ mask_conv1_fwd_kernel(const float* __restrict__ masks, const float* __restrict__
       const int oy0 = q0 / 14, ox0 = q0 - oy0 * 14, oy1 = q1 / 14, ox1 = q1 - oy1 * 14;
       const uint32_t* r0 = mw + (2 * oy0) * MPW + ox0 + t;
       const uint32_t* r1 = mw + (2 * oy1) * MPW + ox1 + t;
-      float acc[4][4];
+      float acc[4][4];                                 // accumulators start at the bias
 #pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
+      for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][2] = bs[j][0]; acc[j][1] = acc[j][3] = bs[j][1]; }
 #pragma unroll
       for (int s = 0; s < 7; ++s) {
         const int h0 = 2 * s, h1 = 2 * s + 1;
@@ -193,8 +196,8 @@ mask_conv1_fwd_kernel(const float* __restrict__ masks, const float* __restrict__
       uint32_t u0[4], u1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        u0[j] = ok0 ? pack2(fmaxf(acc[j][0] + bs[j][0], 0.f), fmaxf(acc[j][1] + bs[j][1], 0.f)) : 0u;
-        u1[j] = ok1 ? pack2(fmaxf(acc[j][2] + bs[j][0], 0.f), fmaxf(acc[j][3] + bs[j][1], 0.f)) : 0u;
+        u0[j] = ok0 ? pack2(fmaxf(acc[j][0], 0.f), fmaxf(acc[j][1], 0.f)) : 0u;
+        u1[j] = ok1 ? pack2(fmaxf(acc[j][2], 0.f), fmaxf(acc[j][3], 0.f)) : 0u;
         const float2 f0 = unpack2(u0[j]), f1 = unpack2(u1[j]);       // statistics of the stored (rounded) values; 0 for padding rows
         ssum[j][0] += f0.x + f1.x; ssum[j][1] += f0.y + f1.y;
         ssq[j][0] = fmaf(f0.x, f0.x, fmaf(f1.x, f1.x, ssq[j][0])); ssq[j][1] = fmaf(f0.y, f0.y, fmaf(f1.y, f1.y, ssq[j][1]));
@@ -230,7 +233,7 @@ mask_conv1_fwd_kernel(const float* __restrict__ masks, const float* __restrict__
 // BatchNorm apply + MaxPool2d(3, 2, 1): block = one pair, thread = (output position, 8 channels)
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int XT_BYTES = 196 * 128 * 2;          // a pair's activation map: 50176 contiguous bytes
-constexpr int F2_SMEM = 2 * XT_BYTES + 64;
+constexpr int F2_SMEM = 2 * XT_BYTES + 64;      // two stages + four mbarriers
 
 // Persistent blocks; the activation maps arrive by bulk copy, double-buffered: the next pair's 50 KB are in flight while this
 // one is pooled out of shared memory (the kernel is a pure stream: 595 MB in, 340 MB out).
@@ -241,18 +244,15 @@ bn_apply_maxpool_kernel(const bf16* __restrict__ x /*[R*196,128]*/, const int* _
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t buf0 = smem_addr(smem), bar0 = buf0 + 2 * XT_BYTES;
   const int c8 = threadIdx.x & 15, c0 = c8 * 8;
+  // full[s] (bar0 + 8 s): the stage's bytes have landed; empty[s] (bar0 + 16 + 8 s): all 8 warps are done reading it.  No block-wide
+  // barrier in the loop: warps drift, thread 0 refills a stage one pair ahead once its readers have arrived.
   if (threadIdx.x == 0) {
-    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 8); mbar_init(bar0 + 24, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   const long long first = blockIdx.x, stride = gridDim.x;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      const long long p = first + s * stride;
-      if (p < R) { mbar_expect_tx(bar0 + 8 * s, XT_BYTES); bulk_load(buf0 + s * XT_BYTES, x + p * (196 * 128), XT_BYTES, bar0 + 8 * s); }
-    }
-  }
+  if (threadIdx.x == 0 && first < R) { mbar_expect_tx(bar0, XT_BYTES); bulk_load(buf0, x + first * (196 * 128), XT_BYTES, bar0); }
   float m[8], k[8], bb[8];
   uint32_t sgn[4] = {0u, 0u, 0u, 0u};           // sign bits of the scales, on the packed bf16 pairs
   int cur_vid = -1, it = 0;
@@ -269,6 +269,12 @@ bn_apply_maxpool_kernel(const bf16* __restrict__ x /*[R*196,128]*/, const int* _
       }
 #pragma unroll
       for (int h = 0; h < 4; ++h) sgn[h] = (k[2 * h] < 0.f ? 0x00008000u : 0u) | (k[2 * h + 1] < 0.f ? 0x80000000u : 0u);
+    }
+    if (threadIdx.x == 0 && p + stride < R) {        // refill the other stage for the next pair
+      if (it >= 1) mbar_wait(bar0 + 16 + 8 * (s ^ 1), ((it - 1) >> 1) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_expect_tx(bar0 + 8 * (s ^ 1), XT_BYTES);
+      bulk_load(buf0 + (s ^ 1) * XT_BYTES, x + (p + stride) * (196 * 128), XT_BYTES, bar0 + 8 * (s ^ 1));
     }
     mbar_wait(bar0 + 8 * s, (it >> 1) & 1);
     const uint4* tile = reinterpret_cast<const uint4*>(smem + s * XT_BYTES) + c8;
@@ -313,15 +319,8 @@ bn_apply_maxpool_kernel(const bf16* __restrict__ x /*[R*196,128]*/, const int* _
       reinterpret_cast<uint2*>(arg)[e] = pk;
       if (xmax != nullptr) reinterpret_cast<uint4*>(xmax)[e] = xm;
     }
-    __syncthreads();                                 // everyone is done reading stage s
-    if (threadIdx.x == 0) {
-      const long long pn = p + 2 * stride;
-      if (pn < R) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(bar0 + 8 * s, XT_BYTES);
-        bulk_load(buf0 + s * XT_BYTES, x + pn * (196 * 128), XT_BYTES, bar0 + 8 * s);
-      }
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 16 + 8 * s);     // this warp is done reading stage s
   }
 }
 
@@ -343,8 +342,9 @@ pool_bn_bwd_apply_kernel(const float* __restrict__ dp /*[R*49,128]*/, const uint
   float (*prm)[128] = reinterpret_cast<float (*)[128]>(smem + 2 * BW_STAGE + 64);   // mean, w * rstd, sum_dy / n, rstd * sum_dy_xhat / n
   float (*red)[128] = reinterpret_cast<float (*)[128]>(smem + 2 * BW_STAGE + 64 + 4 * 128 * 4);
   const int c8 = threadIdx.x & 15, c0 = c8 * 8, lane_pos = threadIdx.x >> 4;        // 32 positions per sweep
+  const int hsel = (c8 >> 2) & 1;
   if (threadIdx.x == 0) {
-    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1);
+    mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); mbar_init(bar0 + 16, 16); mbar_init(bar0 + 24, 16);   // full[2], empty[2] (16 warps)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -356,11 +356,9 @@ pool_bn_bwd_apply_kernel(const float* __restrict__ dp /*[R*49,128]*/, const uint
     bulk_load(d + XT_BYTES, dp + p * (49 * 128), DP_BYTES, bar);
     bulk_load(d + XT_BYTES + DP_BYTES, arg + p * (49 * 128), ARG_BYTES, bar);
   };
-  if (threadIdx.x == 0) {
-    if (first < R) issue(0, first);
-    if (first + stride < R) issue(1, first + stride);
-  }
+  if (threadIdx.x == 0 && first < R) issue(0, first);
   float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  float m[8], k[8], s1[8], t2[8];
   int cur = -1, it = 0;
   for (long long p = first; p < R; p += stride, ++it) {
     const int s = it & 1;
@@ -378,16 +376,22 @@ pool_bn_bwd_apply_kernel(const float* __restrict__ dp /*[R*49,128]*/, const uint
         prm[3][c] = use_batch_stats ? rs * ((float)(sums[((size_t)vid * 2 + 1) * 128 + c]) / n) : 0.f;
       }
       __syncthreads();
-    }
-    float m[8], k[8], s1[8], t2[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { m[q] = prm[0][c0 + q]; k[q] = prm[1][c0 + q]; s1[q] = prm[2][c0 + q]; t2[q] = prm[3][c0 + q]; }
+      for (int q = 0; q < 8; ++q) { m[q] = prm[0][c0 + q]; k[q] = prm[1][c0 + q]; s1[q] = prm[2][c0 + q]; t2[q] = prm[3][c0 + q]; }
+    }
+    if (threadIdx.x == 0 && p + stride < R) {        // refill the other stage for the next pair once its 16 readers have arrived
+      if (it >= 1) mbar_wait(bar0 + 16 + 8 * (s ^ 1), ((it - 1) >> 1) & 1);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(s ^ 1, p + stride);
+    }
     mbar_wait(bar0 + 8 * s, (it >> 1) & 1);
     const uint8_t* st = smem + s * BW_STAGE;
     const uint4* xs = reinterpret_cast<const uint4*>(st) + c8;
     const float4* dps = reinterpret_cast<const float4*>(st + XT_BYTES) + c8 * 2;
     const uint2* as = reinterpret_cast<const uint2*>(st + XT_BYTES + DP_BYTES) + c8;
-    for (int pos = lane_pos; pos < 196; pos += 32) {
+    // 196 positions over 32 slots = 6.125 sweeps: the slots rotate with the pair so that the extra sweep does not always fall to the
+    // same warps (there is no block barrier to hide behind)
+    for (int pos = (lane_pos + 4 * it) & 31; pos < 196; pos += 32) {
       const int iy = pos / 14, ix = pos - iy * 14;
       const uint4 xr = xs[pos * 16];
       float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -402,7 +406,10 @@ pool_bn_bwd_apply_kernel(const float* __restrict__ dp /*[R*49,128]*/, const uint
             const int cell = oy * 7 + ox;
             const unsigned tap = (unsigned)((iy - (2 * oy - 1)) * 3 + (ix - (2 * ox - 1)));
             const uint2 t = as[cell * 16];
-            const float4 d0 = dps[cell * 32], d1 = dps[cell * 32 + 1];
+            // a lane's 8 gradients are two 16-byte pieces 32 bytes apart from its neighbour's: lanes 4..7 of a quarter warp take the
+            // pieces in the other order, so that one instruction touches every bank once
+            const float4 da = dps[cell * 32 + hsel], db = dps[cell * 32 + (hsel ^ 1)];
+            const float4 d0 = hsel ? db : da, d1 = hsel ? da : db;
             if (((t.x) & 0xffu) == tap) g[0] += d0.x;
             if (((t.x >> 8) & 0xffu) == tap) g[1] += d0.y;
             if (((t.x >> 16) & 0xffu) == tap) g[2] += d0.z;
@@ -427,11 +434,8 @@ pool_bn_bwd_apply_kernel(const float* __restrict__ dp /*[R*49,128]*/, const uint
       }
       reinterpret_cast<uint4*>(dx)[(p * 196 + pos) * 16 + c8] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
-    __syncthreads();                                 // everyone is done reading stage s
-    if (threadIdx.x == 0 && p + 2 * stride < R) {
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      issue(s, p + 2 * stride);
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar0 + 16 + 8 * s);     // this warp is done reading stage s
   }
   if (dx_colsum != nullptr) {                        // = the bias gradient of the 7x7 conv
     __syncthreads();

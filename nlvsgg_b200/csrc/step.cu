@@ -95,7 +95,7 @@ struct nlv_session {
   int AD = NLV_BF16;
   // ---- per-step state ----------------------------------------------------------------------------------
   std::vector<T> wop;
-  T w_c0, w_c4, w_vr, w26, b26;
+  T w_c0, w_c4, w_c4t, w_vr, w26, b26;
   OcCtx oc;
   PtCtx pt;
   bool pool_fused = false;
@@ -177,6 +177,11 @@ struct nlv_session {
   T W(int slot, long long rows, int cols) const {
     if (AD == NLV_BF16 && wop[slot].ok()) return wop[slot];
     return mk(params[slot], NLV_F32, rows, cols);
+  }
+  // bf16 path: the data gradient of the 3x3 conv is an implicit GEMM (NLV_CONV_IMPLICIT=0: column-gradient product + col2im)
+  bool implicit_dgrad() const {
+    static const int env = [] { const char* e = getenv("NLV_CONV_IMPLICIT"); return (e != nullptr && e[0] == '0') ? 0 : 1; }();
+    return AD == NLV_BF16 && env != 0;
   }
   // bf16 path: the first stage of the mask branch runs on the fused kernels of maskconv.cu (NLV_MASKCONV=0: the im2col + GEMM route)
   bool fused_mask_conv() const {
@@ -733,11 +738,19 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
     OOM_CHECK();
     RUN(nlv_permute_021(gtap.p, NLV_F32, 256, 9, 128, G(NLV_P_CONV4_W), NLV_F32, st));  // (tap, c) -> (c, tap)
   }
-  T dcol2 = tmp(R * 49, 1152, AD);
-  CK(mm(dc2, K_, w_c4, MN_, dcol2));
   T dp1 = tmp(R * 49, 128, NLV_F32);
-  OOM_CHECK();
-  RUN(nlv_col2im_3x3(dcol2.p, dcol2.dt, (int)R, 7, 7, 128, dp1.f(), st));
+  if (implicit_dgrad()) {
+    // data gradient of the 3x3 conv as one implicit GEMM over the nine shifted views of dc2 (4-D TMA boxes, zero halo)
+    OOM_CHECK();
+    g_next_flops = 2.0 * (double)R * 49 * 128 * 2304; g_next_m = (int)(R * 49); g_next_n = 128; g_next_k = 2304; g_next_dt = 1;
+    RUN(nlv_conv3x3_dgrad(dc2.p, R, 256, w_c4t.p, 128, dp1.p, dp1.dt, st));
+  } else {
+    Scope s3(this);
+    T dcol2 = tmp(R * 49, 1152, AD);
+    CK(mm(dc2, K_, w_c4, MN_, dcol2));
+    OOM_CHECK();
+    RUN(nlv_col2im_3x3(dcol2.p, dcol2.dt, (int)R, 7, 7, 128, dp1.f(), st));
+  }
   T dc1 = tmp(R * 196, 128, AD);
   if (fused_mask_conv() && pool_fused) {
     // pooling + BatchNorm + ReLU backward in one sweep over the pooled gradient (maskconv.cu); + the 7x7 conv bias gradient
@@ -981,6 +994,7 @@ int nlv_session::prepare_weights() {
   // im2col; vr_fc columns (hw,c) to match the NHWC union tensor
   w_c0 = keep(128, 104, AD);
   w_c4 = keep(256, 1152, AD);
+  if (implicit_dgrad()) w_c4t = keep(128, 2304, AD);
   w_vr = keep(512, 12544, AD);
   w26 = keep(26, D, NLV_F32);
   b26 = keep(1, 32, NLV_F32);
@@ -988,6 +1002,7 @@ int nlv_session::prepare_weights() {
   RUN(nlv_zero_bytes(w_c0.p, 128ll * 104 * w_c0.esz(), st));
   RUN(nlv_convert(P(NLV_P_CONV0_W), NLV_F32, 98, w_c0.p, w_c0.dt, 104, 128, 98, st));
   RUN(nlv_permute_021(P(NLV_P_CONV4_W), NLV_F32, 256, 128, 9, w_c4.p, w_c4.dt, st));
+  if (implicit_dgrad()) RUN(nlv_permute_021(P(NLV_P_CONV4_W), NLV_F32, 1, 256, 1152, w_c4t.p, w_c4t.dt, st));   // [co, ci*9] -> [ci][tap][co]
   RUN(nlv_permute_021(P(NLV_P_VR_W), NLV_F32, 512, 256, 49, w_vr.p, w_vr.dt, st));
   const void* src[6] = {P(NLV_P_A_W), P(NLV_P_S_W), P(NLV_P_C_W), P(NLV_P_A_B), P(NLV_P_S_B), P(NLV_P_C_B)};
   void* dst[6] = {w26.f(), w26.f() + 3 * D, w26.f() + 9 * D, b26.f(), b26.f() + 3, b26.f() + 9};

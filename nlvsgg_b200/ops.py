@@ -460,3 +460,10 @@ def mask_conv1_dw(dy, masks):
     dw = torch.empty(128, 98, device=dy.device, dtype=torch.float32)
     _call("nlv_mask_conv1_dw", _ptr(dy), _ptr(masks.contiguous()), _LL(r), _ptr(ws), _ptr(dw))
     return dw
+
+
+def conv3x3_dgrad(dy, wt, r, c_out, c_in, out_dtype=torch.float32):
+    """dx [r*49, c_in] of the 3x3 / pad 1 conv from dy bf16 [r*49, c_out] and wt bf16 [c_in, 9*c_out] (implicit GEMM)."""
+    dx = torch.empty(r * 49, c_in, device=dy.device, dtype=out_dtype)
+    _call("nlv_conv3x3_dgrad", _ptr(dy), _LL(r), c_out, _ptr(wt), c_in, _ptr(dx), _dt(dx))
+    return dx

@@ -73,6 +73,23 @@ def test_gemm_tc_epilogue(cuda_lib, m, n, k, d_dtype):
     assert wide[:, :8].abs().max().item() == 0 and wide[:, 8 + n:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("d_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("m,n,k", [(1000, 256, 2048), (300, 264, 128), (129, 40, 64)])
+def test_gemm_tc_bf16_residual(cuda_lib, m, n, k, d_dtype):
+    """bf16 residual (the mask-branch map added under the union 1x1 conv, lib/sttran.py:386): prefetched row pieces in the epilogue."""
+    from nlvsgg_b200 import ops
+    torch.manual_seed(2)
+    a = _mk(m, k, 0, torch.bfloat16)
+    b = _mk(n, k, 0, torch.bfloat16)
+    bias = torch.randn(n, device="cuda")
+    res = torch.randn(m, n, device="cuda").bfloat16()
+    out = torch.empty(m, n, device="cuda", dtype=d_dtype)
+    ops.gemm(a, b, out, bias=bias, residual=res)
+    ref = _ref(a, b, 0, 0, bias, res, False)
+    tol = 1e-2 if d_dtype == torch.bfloat16 else 2e-5
+    assert (out.double() - ref).abs().max().item() <= tol * ref.abs().max().item() + 1e-4
+
+
 @pytest.mark.parametrize("a_major,b_major", [(0, 0), (0, 1), (1, 0), (1, 1)])
 @pytest.mark.parametrize("m,n,k", [(130, 37, 1024), (50, 26, 1936), (33, 65, 17), (200, 300, 129)])
 def test_gemm_simt_fp32(cuda_lib, m, n, k, a_major, b_major):

@@ -149,3 +149,27 @@ def test_pool_bn_bwd_matches_the_two_kernels(cuda_lib, r, nv):
     assert (db - db2).abs().max().item() <= 1e-4 * db2.abs().max().item() + 1e-5
     want = dx2.double().sum(0)
     assert (cs.double() - want).abs().max().item() <= 1e-4 * want.abs().max().item() + 1e-4 * scale
+
+
+@pytest.mark.parametrize("r", [1, 2, 3, 64, 777])
+@pytest.mark.parametrize("out_dtype", [torch.float32, torch.bfloat16])
+def test_conv3x3_dgrad_implicit_gemm(cuda_lib, r, out_dtype):
+    """Data gradient of Conv2d(128, 256, 3, 1, 1) as one implicit tcgen05 GEMM (4-D TMA boxes, zero halo) vs torch and vs the
+    column-gradient product + col2im it replaces."""
+    from nlvsgg_b200 import ops
+    from nlvsgg_b200._C import MAJOR_MN
+    g = torch.Generator().manual_seed(r)
+    w = (0.05 * torch.randn(256, 128, 3, 3, generator=g)).cuda()
+    dy = torch.randn(r * 49, 256, generator=g).bfloat16().cuda()                 # NHWC rows
+    wt = w.view(256, 128 * 9).t().contiguous().view(128, 9, 256).bfloat16().view(128, 2304).contiguous()   # [ci][tap][co]
+    dx = ops.conv3x3_dgrad(dy, wt, r, 256, 128, out_dtype)
+    want = torch.nn.grad.conv2d_input((r, 128, 7, 7), w.bfloat16().float(), dy.float().view(r, 7, 7, 256).permute(0, 3, 1, 2), padding=1)
+    want = want.permute(0, 2, 3, 1).reshape(r * 49, 128)
+    tol = 1e-2 if out_dtype == torch.bfloat16 else 2e-5
+    assert (dx.float() - want).abs().max().item() <= tol * want.abs().max().item() + 1e-5
+    # the replaced route
+    w_op = w.permute(0, 2, 3, 1).reshape(256, 1152).bfloat16().contiguous()      # [co][tap][ci]
+    dcol = torch.empty(r * 49, 1152, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(dy, w_op, dcol, b_major=MAJOR_MN)
+    ref = ops.col2im_3x3(dcol, r, 7, 7, 128)
+    assert (dx.float() - ref).abs().max().item() <= 1.5e-2 * ref.abs().max().item()       # that route rounds the column gradient to bf16

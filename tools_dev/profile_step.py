@@ -46,7 +46,7 @@ for k, (n, ms) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 print("--- top individual GEMMs")
 g = {}
 for name, ms, flops, units, m, n, k, dt in recs:
-    if name == "nlv_gemm":
+    if name in ("nlv_gemm", "nlv_conv3x3_dgrad"):
         c = g.setdefault((m, n, k, dt), [0, 0.0, flops]); c[0] += 1; c[1] += ms
 for (m, n, k, dt), (cnt, ms, fl) in sorted(g.items(), key=lambda kv: -kv[1][1])[:30]:
     print(f"{ms:8.3f} ms n={cnt:3d} m={m} n={n} k={k} dt={dt}  {fl*cnt/ms/1e9:8.1f} TFLOP/s")
