@@ -265,7 +265,7 @@ def rooflines(recs, step_ms, n_stored_values, adamw_ms, n_params):
         return {"bound": "hbm", "achieved": by / ms / 1e6, "peak": hpeak, "unit": "GB/s", "frac": by / ms / 1e6 / hpeak, "launches": len(rs) // reps,
                 "ms_per_step": ms, "algorithmic_bytes_per_step": by}
     extra = {
-        "gather_union_rows": hbm(("nlv_union_unpack", "nlv_nchw_to_rows"), 2.0 * n_stored_values),
+        "gather_union_rows": hbm(("nlv_union_unpack", "nlv_union_unpack12", "nlv_nchw_to_rows"), float(n_stored_values)),
         "attention_fwd": hbm(("nlv_attn_fwd", "nlv_attn_fwd_drop", "nlv_attn_fwd_padkeys")),
         "attention_bwd": hbm(("nlv_attn_bwd", "nlv_attn_bwd_drop", "nlv_attn_bwd_sorted")),
         "layernorm": hbm(("nlv_layernorm_fwd", "nlv_layernorm_bwd", "nlv_layernorm_bwd_drop", "nlv_layernorm_bwd_fused")),
@@ -521,9 +521,13 @@ def main():
         paths = featfile.write_videos(tmpdir, entries)
         host = featfile.Loader(pin=True, depth=1).load(paths)
         density = float(sum(featfile.read_header(p)["union_nnz"] for p in paths)) / max(1, sum(host.n_pairs) * 49 * 2048)
-        n_stored = int(host.union_feat.numel()) if host.union_rows == 2 else 0
+        # bytes of the stored union values (what the unpack kernel reads besides bitmap + offsets)
+        n_stored = {2: 2 * int(host.union_feat.numel()), 3: int(host.union_feat.numel()) + int(host.union_hx.numel()) if host.union_rows == 3 else 0
+                    }.get(host.union_rows, 0)
+        enc = {2: "zero-suppressed (density %.3f), 16-bit values" % density,
+               3: "zero-suppressed (density %.3f), 12-bit values (low byte + 4-bit high-byte code over a per-row base; lossless)" % density}
         in_fmt = (f"packed per-video feature files (featfile.py): bf16 features, channels-last union rows, "
-                  f"{'zero-suppressed (density %.3f)' % density if host.union_rows == 2 else 'dense'}, create_dis pairs; decoded inside the step")
+                  f"{enc.get(host.union_rows, 'dense')}, create_dis pairs; decoded inside the step")
     else:
         host = M.collate(entries, "sgdet", pin=True)
         n_stored = 0
@@ -592,12 +596,32 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item()), lv
 
+    def h2d_alone(hb, reps=4):
+        """the step's host->device copies alone (every rank at once): the link rate the e2e step is measured against"""
+        warm = [M.upload(hb, dev, rasterise=False) for _ in range(reps)]      # device blocks come from the caching allocator afterwards
+        torch.cuda.synchronize()
+        del warm
+        barrier()
+        torch.cuda.synchronize()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        keep = [M.upload(hb, dev, rasterise=False) for _ in range(reps)]
+        c1.record()
+        torch.cuda.synchronize()
+        del keep
+        t = torch.tensor([c0.elapsed_time(c1) / reps], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return float(t.item())
+
     e2e = None
     if not a.no_e2e:
         ems, lv = e2e_loop(host)
+        copy_ms = h2d_alone(host)
         e2e = {"value": total_frames / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                "ms_per_step": ems, "last_loss": lv, "input_pipelining": "H2D copies run up to two steps ahead of the compute on a side stream; each loss is read one step late from its own pinned copy",
                "host_format": in_fmt, "cpu_binding": numa,
+               "h2d_alone_ms_per_step": copy_ms, "h2d_alone_gb_per_s_per_gpu": h2d_bytes / copy_ms / 1e6,
                "h2d_gb_per_s_if_copy_bound": h2d_bytes / ems / 1e6}
     sampler.stop_flag = True
     sampler.join(timeout=2)

@@ -343,6 +343,10 @@ int nlv_zero_bytes(void* p, long long nbytes, void* stream);
  * bitmap u64[rows,32] (bit c of word w = channel 64 w + c is stored), off u32[rows+1] = first value of each row, vals bf16
  * (16-byte aligned, padded by 16 bytes). */
 int nlv_union_unpack(const void* bitmap, const unsigned* off, const void* vals, long long rows, void* dst_bf16, void* stream);
+/* the same for 12-bit stored values (featfile.py "sparse12"): value i = (base[row] + code_i) << 8 | lo[i], code_i = nibble i & 1 of
+ * hx[i >> 1]; lo / hx 16-byte aligned and readable 32 bytes past their ends */
+int nlv_union_unpack12(const void* bitmap, const unsigned* off, const void* lo, const void* hx, const unsigned char* base, long long rows,
+                       void* dst_bf16, void* stream);
 /* lib/assign_pseudo_label.py:934-938 create_dis on device: out f32[n,36] = conf at idx, `other` elsewhere (and at idx when
  * conf == 0); other NULL -> (1 - conf) / 35 in fp32 arithmetic */
 int nlv_create_dis(const float* conf, const float* other, const int* idx, long long n, float* out, void* stream);
@@ -422,7 +426,8 @@ typedef struct nlv_batch {
   const float* distribution;              /* [N,36] (sgdet / sgcls) */
   const void* union_feat; int union_dtype;
   int union_rows;                         /* 0: NCHW [R,2048,7,7] (entry contract); 1: channels-last rows [R*49,2048];
-                                             2: zero-suppressed rows: union_feat = bf16 values, + union_bitmap / union_off */
+                                             2: zero-suppressed rows: union_feat = bf16 values, + union_bitmap / union_off;
+                                             3: the same with 12-bit values (union_hx / union_base below) */
   const float* spatial_masks;             /* [R,2,27,27] or NULL -> rasterised from boxes + pair_idx */
   const long long* pair_idx;              /* [R,2] */
   /* host-built descriptors (nlvsgg_b200/plan.py), int32 device arrays */
@@ -442,6 +447,9 @@ typedef struct nlv_batch {
   const float* both_w;          /* mode 'both': f32[R] = 1 / (windows the token appears in), 0 for tokens without a window */
   /* work_sorted != 0: the three work lists are ordered long-first and n_*_long = their items of segments longer than 16 rows */
   int work_sorted, n_local_long, n_glob_long, n_cls_long;
+  /* union_rows == 3: zero-suppressed rows with 12-bit stored values: union_feat = low bytes u8 [nnz], union_hx = 4-bit codes
+   * (two per byte; high byte = union_base[row] + code), union_base = u8 [R*49] */
+  const void* union_hx; const unsigned char* union_base;
 } nlv_batch;
 
 typedef struct nlv_outputs {

@@ -103,7 +103,8 @@ class BatchDesc(ctypes.Structure):
                 ("cls_perm", _ip), ("cls_iperm", _ip), ("cls_pos", _ip), ("cls_work", _ip), ("n_cls_work", _i),
                 ("union_bitmap", _vp), ("union_off", _vp), ("dist_conf", _vp), ("dist_other", _vp), ("dist_idx", _vp),
                 ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp),
-                ("both_w", _vp), ("work_sorted", _i), ("n_local_long", _i), ("n_glob_long", _i), ("n_cls_long", _i)]
+                ("both_w", _vp), ("work_sorted", _i), ("n_local_long", _i), ("n_glob_long", _i), ("n_cls_long", _i),
+                ("union_hx", _vp), ("union_base", _vp)]
 
 
 class Outputs(ctypes.Structure):

@@ -622,12 +622,14 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
   CK(mm(feat_op, K_, W(NLV_P_OBJ_W, 512, 2048), K_, fo.cs(512, 512), P(NLV_P_OBJ_B)));
   // union features as [R*49, 2048] rows (operand of the 1x1 conv)
   T uf;
-  if (B.union_rows == 2) {          // zero-suppressed rows from a packed feature file
+  if (B.union_rows == 2 || B.union_rows == 3) {          // zero-suppressed rows from a packed feature file
     NLV_CHECK_ARG(B.union_bitmap != nullptr && B.union_off != nullptr, "session: sparse union features need bitmap and offsets");
+    NLV_CHECK_ARG(B.union_rows == 2 || (B.union_hx != nullptr && B.union_base != nullptr), "session: 12-bit union features need codes and row bases");
     T d = AD == NLV_BF16 ? ctx(R * 49, 2048, NLV_BF16) : tmp(R * 49, 2048, NLV_BF16);
     OOM_CHECK();
-    g_next_units = (double)R * 49 * (256 + 4 + 4096);   // + 2 bytes per stored value (added by the reader of the profile)
-    RUN(nlv_union_unpack(B.union_bitmap, B.union_off, B.union_feat, R * 49, d.p, st));
+    g_next_units = (double)R * 49 * (256 + 4 + 4096);   // + the bytes of the stored values (added by the reader of the profile)
+    if (B.union_rows == 3) RUN(nlv_union_unpack12(B.union_bitmap, B.union_off, B.union_feat, B.union_hx, B.union_base, R * 49, d.p, st));
+    else RUN(nlv_union_unpack(B.union_bitmap, B.union_off, B.union_feat, R * 49, d.p, st));
     uf = d;
     if (AD != NLV_BF16) {
       T t = ctx(R * 49, 2048, AD);
@@ -727,10 +729,12 @@ int nlv_session::pair_tokens_bwd(const T& drel) {
   CK(mm(dvr, K_, w_vr, MN_, dvr_in2d));
   const T dvr_in = dvr_in2d.view(R * 49, 256);
   CK(mm(dvr_in, MN_, pt.uf_op, MN_, mk(G(NLV_P_UNION_W), NLV_F32, 256, 2048)));
-  RUN(nlv_colsum(dvr_in.p, dvr_in.dt, dvr_in.ld, R * 49, 256, nullptr, 1, G(NLV_P_UNION_B), st));
   T dc2 = tmp(R * 49, 256, AD);
   // BN backward + ReLU backward fused; the kernel also accumulates the column sums of dc2 = the bias gradient of the 3x3 conv
   CK(bn_bwd(dvr_in, pt.c2, nullptr, B.seg49, B.pair_row, 49, NLV_P_BN6_W, pt.mean6, pt.var6, true, dc2, G(NLV_P_CONV4_B)));
+  // vr = union_func1(x) + BatchNorm(conv(masks)): the two bias gradients are the same column sums of dvr_in, and BatchNorm's
+  // backward has just produced them (one 256-float add instead of another pass over the 300 MB map)
+  RUN(nlv_add(G(NLV_P_UNION_B), G(NLV_P_BN6_W + 1), 256, G(NLV_P_UNION_B), st));
   {
     Scope s2(this);
     T gtap = tmp(256, 1152, NLV_F32);

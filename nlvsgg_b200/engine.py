@@ -234,6 +234,9 @@ def batch_desc(batch, plan: Plan, labels=None, dsg: bool = False) -> "_C.BatchDe
     b.union_feat, b.union_dtype = u.data_ptr(), _C.NLV_BF16 if u.dtype == BF16 else _C.NLV_F32
     b.union_rows = int(getattr(batch, "union_rows", 0) or 0)
     b.union_bitmap, b.union_off = _ptr(getattr(batch, "union_bitmap", None)), _ptr(getattr(batch, "union_off", None))
+    b.union_hx, b.union_base = _ptr(getattr(batch, "union_hx", None)), _ptr(getattr(batch, "union_base", None))
+    if b.union_rows == 3:
+        b.union_dtype = _C.NLV_BF16       # 12-bit stored values decode to bf16
     b.dist_conf, b.dist_idx = _ptr(getattr(batch, "dist_conf", None)), _ptr(getattr(batch, "dist_idx", None))
     b.dist_other = _ptr(getattr(batch, "dist_other", None))
     b.spatial_masks = _ptr(batch.spatial_masks)

@@ -13,7 +13,10 @@ buffers at running offsets — no per-frame python, no dtype or layout conversio
     pair_idx : i32 [R,2]            im_idx : i32 [R]
     union    : channels-last rows [R*49, 2048] bf16 — the operand layout of the union 1x1-conv GEMM, so the NCHW ->
                rows transposition of the fp32 entry contract disappears from the step — stored zero-suppressed
-               (res5 output is post-ReLU): occupancy u64 [R*49,32] + values bf16 [nnz], or dense when that is smaller
+               (res5 output is post-ReLU): occupancy u64 [R*49,32] + the stored values, or dense when that is smaller.
+               Stored values take 12 bits when every row's values span at most 16 consecutive HIGH bytes (sign + 7 exponent
+               bits = 32 binades; post-ReLU activations use ~13): low bytes u8 [nnz] + 4-bit codes (high byte - the row's
+               smallest one) u8 [nnz/2] + the row bases u8 [R*49] — lossless; otherwise plain bf16 [nnz]
     labels   : attention values / list lengths (CSR), spatial / contacting multi-hot u32 [R]
 
 bf16 storage: in the bf16 compute mode the device rounds both feature tensors to bf16 before their first use anyway, so
@@ -39,7 +42,7 @@ def _bf16_bits(t: torch.Tensor) -> np.ndarray:
     return t.to(torch.bfloat16).contiguous().view(torch.int16).numpy().view(np.uint16)
 
 
-def pack_union(union_feat: torch.Tensor, sparse: Optional[bool] = None):
+def pack_union(union_feat: torch.Tensor, sparse: Optional[bool] = None, pack12: bool = True):
     """[R,2048,7,7] (any float dtype) -> dict of numpy sections for the channels-last (optionally zero-suppressed) layout."""
     R = union_feat.shape[0]
     rows = _bf16_bits(union_feat.permute(0, 2, 3, 1).reshape(R * 49, 2048))          # [R*49, 2048] u16
@@ -52,7 +55,24 @@ def pack_union(union_feat: torch.Tensor, sparse: Optional[bool] = None):
         return {"union_dense": rows}, {"union": "dense", "union_nnz": nnz}
     bitmap = np.packbits(nz, axis=1, bitorder="little").view(np.uint64).reshape(R * 49, 32)
     vals = rows[nz]
-    return {"union_bitmap": bitmap, "union_vals": vals, "union_rownnz": nz.sum(1).astype(np.uint32)}, {"union": "sparse", "union_nnz": nnz}
+    rownnz = nz.sum(1).astype(np.uint32)
+    if pack12 and nnz:
+        # 12 bits per stored value: low byte + (high byte - smallest high byte of the row), when that difference fits 4 bits
+        hi, lo = (vals >> 8).astype(np.uint8), (vals & 0xFF).astype(np.uint8)
+        row_of = np.repeat(np.arange(R * 49), rownnz)
+        base = np.full(R * 49, 255, dtype=np.uint8)
+        np.minimum.at(base, row_of, hi)
+        base[rownnz == 0] = 0
+        code = hi - base[row_of]
+        if int(code.max()) <= 15:
+            if nnz & 1:                                   # the 4-bit plane of a video ends on a byte: one padding value, owned by
+                lo, code = np.append(lo, np.uint8(0)), np.append(code, np.uint8(0))    # the last row (its bitmap ignores it)
+                rownnz = rownnz.copy()
+                rownnz[-1] += 1
+            hx = (code[0::2] | (code[1::2] << 4)).astype(np.uint8)
+            return ({"union_bitmap": bitmap, "union_lo": lo, "union_hx": hx, "union_base": base, "union_rownnz": rownnz},
+                    {"union": "sparse12", "union_nnz": nnz, "union_nnz_stored": int(lo.size)})
+    return {"union_bitmap": bitmap, "union_vals": vals, "union_rownnz": rownnz}, {"union": "sparse", "union_nnz": nnz}
 
 
 def _is_create_dis(dist: torch.Tensor):
@@ -70,7 +90,7 @@ def _is_create_dis(dist: torch.Tensor):
     return (conf, other, idx) if torch.equal(rebuilt, dist) else None
 
 
-def write_video(path: str, entry: dict, sparse: Optional[bool] = None) -> dict:
+def write_video(path: str, entry: dict, sparse: Optional[bool] = None, pack12: bool = True) -> dict:
     """entry (the reference contract, lib/assign_pseudo_label.py:1368-1382, CPU tensors) -> one packed file.  Returns the header."""
     N, R = int(entry["boxes"].shape[0]), int(entry["pair_idx"].shape[0])
     sec: Dict[str, np.ndarray] = {
@@ -93,7 +113,7 @@ def write_video(path: str, entry: dict, sparse: Optional[bool] = None) -> dict:
             meta["dist"] = "full"
     else:
         meta["dist"] = "none"
-    usec, umeta = pack_union(entry["union_feat"], sparse)
+    usec, umeta = pack_union(entry["union_feat"], sparse, pack12)
     sec.update(usec)
     meta.update(umeta)
     if entry.get("attention_gt") is not None:
@@ -161,13 +181,14 @@ class Loader:
         N, R = int(nb.sum()), int(nr.sum())
         boff = np.concatenate(([0], np.cumsum(nb)))
         roff = np.concatenate(([0], np.cumsum(nr)))
-        sparse = all(m["union"] == "sparse" for m in metas)
-        if not sparse and any(m["union"] == "sparse" for m in metas):
-            raise ValueError("a batch must not mix sparse and dense union sections")
+        enc = metas[0]["union"]
+        if any(m["union"] != enc for m in metas):
+            raise ValueError("a batch must not mix union encodings (dense / sparse / sparse12)")
+        sparse, s12 = enc in ("sparse", "sparse12"), enc == "sparse12"
         dist = metas[0]["dist"]
         if any(m["dist"] != dist for m in metas):
             raise ValueError("a batch must not mix distribution encodings")
-        nnz = np.asarray([m["union_nnz"] for m in metas], dtype=np.int64)
+        nnz = np.asarray([m["union_nnz_stored"] if s12 else m["union_nnz"] for m in metas], dtype=np.int64)
         voff = np.concatenate(([0], np.cumsum(nnz)))
 
         def buf(name, nbytes, dtype, shape):
@@ -186,7 +207,12 @@ class Loader:
         if sparse:
             out["union_bitmap"] = buf("union_bitmap", R * 49 * 256, np.uint64, (R * 49, 32))
             out["union_rownnz"] = buf("union_rownnz", R * 49 * 4, np.uint32, (R * 49,))
-            out["union_vals"] = buf("union_vals", int(voff[-1]) * 2 + 32, np.uint16, (int(voff[-1]) + 16,))
+            if s12:
+                out["union_lo"] = buf("union_lo", int(voff[-1]) + 32, np.uint8, (int(voff[-1]) + 32,))
+                out["union_hx"] = buf("union_hx", int(voff[-1]) // 2 + 32, np.uint8, (int(voff[-1]) // 2 + 32,))
+                out["union_base"] = buf("union_base", R * 49, np.uint8, (R * 49,))
+            else:
+                out["union_vals"] = buf("union_vals", int(voff[-1]) * 2 + 32, np.uint16, (int(voff[-1]) + 16,))
         else:
             out["union_dense"] = buf("union_dense", R * 49 * 4096, np.uint16, (R * 49, 2048))
         has_labels = all(m.get("has_labels") for m in metas)
@@ -203,7 +229,12 @@ class Loader:
             if sparse:
                 dest["union_bitmap"] = out["union_bitmap"][r0 * 49:r1 * 49]
                 dest["union_rownnz"] = out["union_rownnz"][r0 * 49:r1 * 49]
-                dest["union_vals"] = out["union_vals"][int(voff[v]):int(voff[v + 1])]
+                if s12:
+                    dest["union_lo"] = out["union_lo"][int(voff[v]):int(voff[v + 1])]
+                    dest["union_hx"] = out["union_hx"][int(voff[v]) // 2:int(voff[v + 1]) // 2]
+                    dest["union_base"] = out["union_base"][r0 * 49:r1 * 49]
+                else:
+                    dest["union_vals"] = out["union_vals"][int(voff[v]):int(voff[v + 1])]
             else:
                 dest["union_dense"] = out["union_dense"][r0 * 49:r1 * 49]
             with open(p, "rb", buffering=0) as f:
@@ -246,11 +277,17 @@ class Loader:
             offs = buf("union_off", (R * 49 + 1) * 4, np.uint32, (R * 49 + 1,))
             offs[0] = 0
             np.cumsum(out["union_rownnz"], out=offs[1:])
-            out["union_vals"][int(voff[-1]):] = 0
-            hb.union_feat = T(out["union_vals"].view(np.int16)).view(torch.bfloat16)
             hb.union_bitmap = T(out["union_bitmap"].view(np.int64))
             hb.union_off = T(offs.view(np.int32))
-            hb.union_rows = 2
+            if s12:
+                out["union_lo"][int(voff[-1]):] = 0
+                out["union_hx"][int(voff[-1]) // 2:] = 0
+                hb.union_feat, hb.union_hx, hb.union_base = T(out["union_lo"]), T(out["union_hx"]), T(out["union_base"])
+                hb.union_rows = 3
+            else:
+                out["union_vals"][int(voff[-1]):] = 0
+                hb.union_feat = T(out["union_vals"].view(np.int16)).view(torch.bfloat16)
+                hb.union_rows = 2
         else:
             hb.union_feat = T(out["union_dense"].view(np.int16)).view(torch.bfloat16)
             hb.union_bitmap = hb.union_off = None
@@ -258,11 +295,11 @@ class Loader:
         return hb
 
 
-def write_videos(dirpath: str, entries: List[dict], sparse: Optional[bool] = None) -> List[str]:
+def write_videos(dirpath: str, entries: List[dict], sparse: Optional[bool] = None, pack12: bool = True) -> List[str]:
     os.makedirs(dirpath, exist_ok=True)
     paths = []
     for i, e in enumerate(entries):
         p = os.path.join(dirpath, f"video_{i:05d}.nlvf")
-        write_video(p, e, sparse)
+        write_video(p, e, sparse, pack12)
         paths.append(p)
     return paths

@@ -12,14 +12,25 @@ from tests.test_cpu_featfile import _entries, _unpack_numpy
 pytestmark = pytest.mark.gpu
 
 
-def test_union_unpack_kernel_matches_numpy(cuda_lib, tmp_path):
+@pytest.mark.parametrize("pack12", [True, False])
+def test_union_unpack_kernel_matches_numpy(cuda_lib, tmp_path, pack12):
     from nlvsgg_b200 import _C
-    hb = FF.Loader(pin=False).load(FF.write_videos(str(tmp_path), _entries()))
+    entries = _entries()
+    hb = FF.Loader(pin=False).load(FF.write_videos(str(tmp_path), entries, pack12=pack12))
     want = _unpack_numpy(hb)
+    ref = M.collate(entries, "sgdet").union_feat.bfloat16().permute(0, 2, 3, 1).reshape(-1, 2048).contiguous()
+    assert np.array_equal(want, ref.view(torch.int16).numpy().view(np.uint16))
     bm, off, vals = hb.union_bitmap.cuda(), hb.union_off.cuda(), hb.union_feat.cuda()
     out = torch.empty(want.shape, dtype=torch.bfloat16, device="cuda")
-    _C.check(_C.lib().nlv_union_unpack(ctypes.c_void_p(bm.data_ptr()), ctypes.c_void_p(off.data_ptr()), ctypes.c_void_p(vals.data_ptr()),
-                                       ctypes.c_longlong(want.shape[0]), ctypes.c_void_p(out.data_ptr()), None), "union_unpack")
+    vp = ctypes.c_void_p
+    if pack12:
+        assert hb.union_rows == 3
+        hx, base = hb.union_hx.cuda(), hb.union_base.cuda()
+        _C.check(_C.lib().nlv_union_unpack12(vp(bm.data_ptr()), vp(off.data_ptr()), vp(vals.data_ptr()), vp(hx.data_ptr()), vp(base.data_ptr()),
+                                             ctypes.c_longlong(want.shape[0]), vp(out.data_ptr()), None), "union_unpack12")
+    else:
+        _C.check(_C.lib().nlv_union_unpack(vp(bm.data_ptr()), vp(off.data_ptr()), vp(vals.data_ptr()),
+                                           ctypes.c_longlong(want.shape[0]), vp(out.data_ptr()), None), "union_unpack")
     torch.cuda.synchronize()
     assert np.array_equal(out.cpu().view(torch.int16).numpy().view(np.uint16), want)
 
