@@ -259,7 +259,7 @@ class SceneGraphEvaluator:
         stats = {}
         masks = recall_match(pair_off, gtd, pi[:, 0].contiguous(), pi[:, 1].contiguous(), att, cat([p["spatial_distribution"].float() for p in preds]),
                              cat([p["contacting_distribution"].float() for p in preds]), cat([p[key_s].float() for p in preds]),
-                             cat([p[key_c].to(torch.int32) for p in preds]), cat([p["boxes"][:, 1:].float() for p in preds]), stats)
+                             cat([p[key_c] for p in preds]).to(torch.int32), cat([p["boxes"] for p in preds])[:, 1:].float().contiguous(), stats)
         self.last_kernel_ms, self.last_h2d_bytes = stats["kernel_ms"], stats["h2d_bytes"]
         self.last_d2h_bytes, self.last_algorithmic_bytes = stats["d2h_bytes"], stats["algorithmic_bytes"]
         self._book(masks, gtd)
