@@ -347,6 +347,8 @@ int nlv_union_unpack(const void* bitmap, const unsigned* off, const void* vals, 
  * hx[i >> 1]; lo / hx 16-byte aligned and readable 32 bytes past their ends */
 int nlv_union_unpack12(const void* bitmap, const unsigned* off, const void* lo, const void* hx, const unsigned char* base, long long rows,
                        void* dst_bf16, void* stream);
+/* dst_bf16[pos[i]] = val[i] (bf16 bits): the exception list of the 12-bit encoding */
+int nlv_union_patch(void* dst_bf16, const unsigned* pos, const unsigned short* val, int n, void* stream);
 /* lib/assign_pseudo_label.py:934-938 create_dis on device: out f32[n,36] = conf at idx, `other` elsewhere (and at idx when
  * conf == 0); other NULL -> (1 - conf) / 35 in fp32 arithmetic */
 int nlv_create_dis(const float* conf, const float* other, const int* idx, long long n, float* out, void* stream);
@@ -450,6 +452,8 @@ typedef struct nlv_batch {
   /* union_rows == 3: zero-suppressed rows with 12-bit stored values: union_feat = low bytes u8 [nnz], union_hx = 4-bit codes
    * (two per byte; high byte = union_base[row] + code), union_base = u8 [R*49] */
   const void* union_hx; const unsigned char* union_base;
+  /* values outside their row's 16-step window: element index (row * 2048 + channel) and bf16 bits, written over the decoded rows */
+  const unsigned* union_exc_pos; const unsigned short* union_exc_val; int n_union_exc;
 } nlv_batch;
 
 typedef struct nlv_outputs {

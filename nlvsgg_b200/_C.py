@@ -104,7 +104,7 @@ class BatchDesc(ctypes.Structure):
                 ("union_bitmap", _vp), ("union_off", _vp), ("dist_conf", _vp), ("dist_other", _vp), ("dist_idx", _vp),
                 ("lab_att", _vp), ("w_att", _vp), ("spa_bits", _vp), ("w_spa", _vp), ("con_bits", _vp), ("w_con", _vp), ("w_obj", _vp),
                 ("both_w", _vp), ("work_sorted", _i), ("n_local_long", _i), ("n_glob_long", _i), ("n_cls_long", _i),
-                ("union_hx", _vp), ("union_base", _vp)]
+                ("union_hx", _vp), ("union_base", _vp), ("union_exc_pos", _vp), ("union_exc_val", _vp), ("n_union_exc", _i)]
 
 
 class Outputs(ctypes.Structure):

@@ -628,8 +628,12 @@ int nlv_session::pair_tokens_fwd(const T& feat_op) {
     T d = AD == NLV_BF16 ? ctx(R * 49, 2048, NLV_BF16) : tmp(R * 49, 2048, NLV_BF16);
     OOM_CHECK();
     g_next_units = (double)R * 49 * (256 + 4 + 4096);   // + the bytes of the stored values (added by the reader of the profile)
-    if (B.union_rows == 3) RUN(nlv_union_unpack12(B.union_bitmap, B.union_off, B.union_feat, B.union_hx, B.union_base, R * 49, d.p, st));
-    else RUN(nlv_union_unpack(B.union_bitmap, B.union_off, B.union_feat, R * 49, d.p, st));
+    if (B.union_rows == 3) {
+      RUN(nlv_union_unpack12(B.union_bitmap, B.union_off, B.union_feat, B.union_hx, B.union_base, R * 49, d.p, st));
+      if (B.n_union_exc > 0) RUN(nlv_union_patch(d.p, B.union_exc_pos, B.union_exc_val, B.n_union_exc, st));
+    } else {
+      RUN(nlv_union_unpack(B.union_bitmap, B.union_off, B.union_feat, R * 49, d.p, st));
+    }
     uf = d;
     if (AD != NLV_BF16) {
       T t = ctx(R * 49, 2048, AD);

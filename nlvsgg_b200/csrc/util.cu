@@ -270,6 +270,11 @@ union_unpack12_kernel(const unsigned long long* __restrict__ bitmap, const unsig
   }
 }
 
+__global__ void union_patch_kernel(unsigned short* __restrict__ dst, const unsigned* __restrict__ pos, const unsigned short* __restrict__ val, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[pos[i]] = val[i];
+}
+
 // lib/assign_pseudo_label.py:934-938 create_dis: d = zeros(36); d[idx] = conf; d[d == 0] = (1 - conf) / 35
 // `other`: the value of the 35 remaining entries as the producer computed it (python double or fp32 tensor arithmetic,
 // depending on the caller); NULL -> (1 - conf) / 35 in fp32
@@ -379,6 +384,15 @@ int nlv_union_unpack12(const void* bitmap, const unsigned* off, const void* lo, 
   union_unpack12_kernel<<<(unsigned)blocks, 256, 0, STREAM>>>(reinterpret_cast<const unsigned long long*>(bitmap), off,
                                                              reinterpret_cast<const unsigned char*>(lo), reinterpret_cast<const unsigned char*>(hx),
                                                              base, rows, reinterpret_cast<unsigned short*>(dst_bf16));
+  NLV_CHECK_LAUNCH();
+  return NLV_OK;
+}
+
+int nlv_union_patch(void* dst_bf16, const unsigned* pos, const unsigned short* val, int n, void* stream) {
+  NLV_CHECK_ARG(n >= 0, "union_patch: bad size");
+  if (n == 0) return NLV_OK;
+  NLV_CHECK_ARG(dst_bf16 && pos && val, "union_patch: null pointer");
+  union_patch_kernel<<<cdiv(n, 256), 256, 0, STREAM>>>(reinterpret_cast<unsigned short*>(dst_bf16), pos, val, n);
   NLV_CHECK_LAUNCH();
   return NLV_OK;
 }

@@ -235,6 +235,9 @@ def batch_desc(batch, plan: Plan, labels=None, dsg: bool = False) -> "_C.BatchDe
     b.union_rows = int(getattr(batch, "union_rows", 0) or 0)
     b.union_bitmap, b.union_off = _ptr(getattr(batch, "union_bitmap", None)), _ptr(getattr(batch, "union_off", None))
     b.union_hx, b.union_base = _ptr(getattr(batch, "union_hx", None)), _ptr(getattr(batch, "union_base", None))
+    ex = getattr(batch, "union_exc_pos", None)
+    b.union_exc_pos, b.union_exc_val = _ptr(ex), _ptr(getattr(batch, "union_exc_val", None))
+    b.n_union_exc = int(ex.numel()) if ex is not None else 0
     if b.union_rows == 3:
         b.union_dtype = _C.NLV_BF16       # 12-bit stored values decode to bf16
     b.dist_conf, b.dist_idx = _ptr(getattr(batch, "dist_conf", None)), _ptr(getattr(batch, "dist_idx", None))

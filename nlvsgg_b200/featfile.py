@@ -14,9 +14,11 @@ buffers at running offsets — no per-frame python, no dtype or layout conversio
     union    : channels-last rows [R*49, 2048] bf16 — the operand layout of the union 1x1-conv GEMM, so the NCHW ->
                rows transposition of the fp32 entry contract disappears from the step — stored zero-suppressed
                (res5 output is post-ReLU): occupancy u64 [R*49,32] + the stored values, or dense when that is smaller.
-               Stored values take 12 bits when every row's values span at most 16 consecutive HIGH bytes (sign + 7 exponent
-               bits = 32 binades; post-ReLU activations use ~13): low bytes u8 [nnz] + 4-bit codes (high byte - the row's
-               smallest one) u8 [nnz/2] + the row bases u8 [R*49] — lossless; otherwise plain bf16 [nnz]
+               Stored values take 12 bits: low bytes u8 [nnz] + 4-bit codes u8 [nnz/2] = high byte (sign + 7 exponent bits)
+               minus the row's base u8 [R*49]; a row's window of 16 high bytes = 32 binades below its largest value (post-ReLU
+               activations use ~13).  Values outside the window (vanishing magnitudes, negative values) are listed as
+               exceptions (position u32, value u16) and patched after the decode — lossless; more than 0.1 % exceptions:
+               plain bf16 [nnz]
     labels   : attention values / list lengths (CSR), spatial / contacting multi-hot u32 [R]
 
 bf16 storage: in the bf16 compute mode the device rounds both feature tensors to bf16 before their first use anyway, so
@@ -57,21 +59,32 @@ def pack_union(union_feat: torch.Tensor, sparse: Optional[bool] = None, pack12: 
     vals = rows[nz]
     rownnz = nz.sum(1).astype(np.uint32)
     if pack12 and nnz:
-        # 12 bits per stored value: low byte + (high byte - smallest high byte of the row), when that difference fits 4 bits
-        hi, lo = (vals >> 8).astype(np.uint8), (vals & 0xFF).astype(np.uint8)
-        row_of = np.repeat(np.arange(R * 49), rownnz)
-        base = np.full(R * 49, 255, dtype=np.uint8)
-        np.minimum.at(base, row_of, hi)
-        base[rownnz == 0] = 0
-        code = hi - base[row_of]
-        if int(code.max()) <= 15:
+        # 12 bits per stored value: low byte + (high byte - the row's base), the base chosen so that the row's LARGEST positive
+        # values fit the 16-step window [base, base + 15] (32 binades).  The few values outside it — magnitudes below 2^-29 of the
+        # row's maximum, negative values — keep a zero slot in the stream and are listed as exceptions (position, value) that a
+        # small kernel writes over the decoded rows.  Too many exceptions (> 0.1 % of the values): plain 16-bit values.
+        hi, lo = (vals >> 8).astype(np.int16), (vals & 0xFF).astype(np.uint8)
+        rr, cc = np.nonzero(nz)
+        top = np.zeros(R * 49, dtype=np.int16)
+        pos_mask = hi < 0x80
+        np.maximum.at(top, rr[pos_mask], hi[pos_mask])
+        base = np.maximum(top - 15, 0).astype(np.int16)
+        code = hi - base[rr]
+        exc = (code < 0) | (code > 15)
+        n_exc = int(exc.sum())
+        if n_exc <= max(16, nnz // 1000):
+            exc_pos = (rr[exc].astype(np.int64) * 2048 + cc[exc]).astype(np.uint32)      # element index inside the video's rows
+            exc_val = vals[exc].astype(np.uint16)
+            code = np.where(exc, 0, code).astype(np.uint8)
+            lo = np.where(exc, 0, lo).astype(np.uint8)
             if nnz & 1:                                   # the 4-bit plane of a video ends on a byte: one padding value, owned by
                 lo, code = np.append(lo, np.uint8(0)), np.append(code, np.uint8(0))    # the last row (its bitmap ignores it)
                 rownnz = rownnz.copy()
                 rownnz[-1] += 1
             hx = (code[0::2] | (code[1::2] << 4)).astype(np.uint8)
-            return ({"union_bitmap": bitmap, "union_lo": lo, "union_hx": hx, "union_base": base, "union_rownnz": rownnz},
-                    {"union": "sparse12", "union_nnz": nnz, "union_nnz_stored": int(lo.size)})
+            return ({"union_bitmap": bitmap, "union_lo": lo, "union_hx": hx, "union_base": base.astype(np.uint8), "union_rownnz": rownnz,
+                     "union_exc_pos": exc_pos, "union_exc_val": exc_val},
+                    {"union": "sparse12", "union_nnz": nnz, "union_nnz_stored": int(lo.size), "union_nexc": n_exc})
     return {"union_bitmap": bitmap, "union_vals": vals, "union_rownnz": rownnz}, {"union": "sparse", "union_nnz": nnz}
 
 
@@ -211,6 +224,10 @@ class Loader:
                 out["union_lo"] = buf("union_lo", int(voff[-1]) + 32, np.uint8, (int(voff[-1]) + 32,))
                 out["union_hx"] = buf("union_hx", int(voff[-1]) // 2 + 32, np.uint8, (int(voff[-1]) // 2 + 32,))
                 out["union_base"] = buf("union_base", R * 49, np.uint8, (R * 49,))
+                nexc = np.asarray([m.get("union_nexc", 0) for m in metas], dtype=np.int64)
+                eoff = np.concatenate(([0], np.cumsum(nexc)))
+                out["union_exc_pos"] = buf("union_exc_pos", int(eoff[-1]) * 4, np.uint32, (int(eoff[-1]),))
+                out["union_exc_val"] = buf("union_exc_val", int(eoff[-1]) * 2, np.uint16, (int(eoff[-1]),))
             else:
                 out["union_vals"] = buf("union_vals", int(voff[-1]) * 2 + 32, np.uint16, (int(voff[-1]) + 16,))
         else:
@@ -233,6 +250,8 @@ class Loader:
                     dest["union_lo"] = out["union_lo"][int(voff[v]):int(voff[v + 1])]
                     dest["union_hx"] = out["union_hx"][int(voff[v]) // 2:int(voff[v + 1]) // 2]
                     dest["union_base"] = out["union_base"][r0 * 49:r1 * 49]
+                    dest["union_exc_pos"] = out["union_exc_pos"][int(eoff[v]):int(eoff[v + 1])]
+                    dest["union_exc_val"] = out["union_exc_val"][int(eoff[v]):int(eoff[v + 1])]
                 else:
                     dest["union_vals"] = out["union_vals"][int(voff[v]):int(voff[v + 1])]
             else:
@@ -252,6 +271,9 @@ class Loader:
                         f.seek(m["_data0"] + o)
                         lab[name].append(np.frombuffer(f.read(nbytes), dtype=dt).reshape(shape))
             out["pair32"][r0:r1] += b0                     # pair indices become batch-global box rows
+            if s12 and eoff[v + 1] > eoff[v]:
+                assert (r1 * 49) * 2048 < 2 ** 32
+                out["union_exc_pos"][int(eoff[v]):int(eoff[v + 1])] += np.uint32(r0 * 49 * 2048)     # ... and exception positions batch-global
 
         hb = M.Batch()
         hb.n_boxes, hb.n_pairs = [int(x) for x in nb], [int(x) for x in nr]
@@ -283,6 +305,8 @@ class Loader:
                 out["union_lo"][int(voff[-1]):] = 0
                 out["union_hx"][int(voff[-1]) // 2:] = 0
                 hb.union_feat, hb.union_hx, hb.union_base = T(out["union_lo"]), T(out["union_hx"]), T(out["union_base"])
+                hb.union_exc_pos = T(out["union_exc_pos"].view(np.int32)) if eoff[-1] else None
+                hb.union_exc_val = T(out["union_exc_val"].view(np.int16)) if eoff[-1] else None
                 hb.union_rows = 3
             else:
                 out["union_vals"][int(voff[-1]):] = 0
@@ -297,9 +321,13 @@ class Loader:
 
 def write_videos(dirpath: str, entries: List[dict], sparse: Optional[bool] = None, pack12: bool = True) -> List[str]:
     os.makedirs(dirpath, exist_ok=True)
-    paths = []
+    paths, encs = [], []
     for i, e in enumerate(entries):
         p = os.path.join(dirpath, f"video_{i:05d}.nlvf")
-        write_video(p, e, sparse, pack12)
+        encs.append(write_video(p, e, sparse, pack12)["union"])
         paths.append(p)
+    if "sparse12" in encs and "sparse" in encs:      # a loader batch holds one encoding: the set falls back to 16-bit values together
+        for p, e, enc in zip(paths, entries, encs):
+            if enc == "sparse12":
+                write_video(p, e, True, False)
     return paths

@@ -23,13 +23,13 @@ class Batch:
     12-bit values (union_feat = low bytes, union_hx = 4-bit high-byte codes, union_base = the rows' smallest high bytes) — the
     layouts of the packed feature files (featfile.py)."""
     union_rows = 0
-    union_bitmap = union_off = union_hx = union_base = dist_conf = dist_other = dist_idx = None
+    union_bitmap = union_off = union_hx = union_base = union_exc_pos = union_exc_val = dist_conf = dist_other = dist_idx = None
     distribution = spatial_masks = None
     lab_csr = None
 
 
 TENSOR_KEYS = ("features", "boxes", "labels", "scores", "distribution", "union_feat", "pair_idx", "spatial_masks",
-               "union_bitmap", "union_off", "union_hx", "union_base", "dist_conf", "dist_other", "dist_idx")
+               "union_bitmap", "union_off", "union_hx", "union_base", "union_exc_pos", "union_exc_val", "dist_conf", "dist_other", "dist_idx")
 
 
 def collate(entries: List[dict], mode: str, pin: bool = False, feat_dtype: torch.dtype = F32) -> Batch:

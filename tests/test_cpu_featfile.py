@@ -23,6 +23,8 @@ def _unpack_numpy(hb):
         gi = off[rows] + k
         code = (hx[gi >> 1] >> (4 * (gi & 1))) & 15
         dense[bits] = ((base[rows].astype(np.uint16) + code) << 8) | lo[gi]
+        if hb.union_exc_pos is not None:        # values outside their row's window (union_patch_kernel)
+            dense.reshape(-1)[hb.union_exc_pos.numpy().view(np.uint32)] = hb.union_exc_val.numpy().view(np.uint16)
         return dense
     vals = hb.union_feat.view(torch.int16).numpy().view(np.uint16)
     dense[bits] = vals[:int(bits.sum())]
@@ -59,26 +61,36 @@ def test_round_trip_matches_collate(tmp_path, pack12):
     assert M.input_bytes(hb) < (0.27 if pack12 else 0.35) * M.input_bytes(ref)          # vs the fp32 NCHW entry contract
 
 
-def test_12_bit_values_fall_back_when_a_row_spans_too_many_binades(tmp_path):
-    """A row whose stored values span more than 16 high bytes (here: a negative value next to positive ones) keeps 16-bit values."""
+def test_12_bit_values_exceptions_and_fallback(tmp_path):
+    """Values outside a row's 16-step window (vanishing magnitudes, negative values) travel as exceptions; a video with too many of
+    them keeps 16-bit values, and write_videos then writes the whole set that way."""
+    def want_of(e):
+        return e["union_feat"].bfloat16().permute(0, 2, 3, 1).reshape(-1, 2048).contiguous().view(torch.int16).numpy().view(np.uint16)
     e = _entries()[0]
-    e["union_feat"][0, 5, 3, 3] = -1.5
+    e["union_feat"][0, 5, 3, 3] = -1.5                       # a negative value
+    e["union_feat"][1, 7, 0, 0] = 1e-30                      # 100 binades below the row's maximum
+    e["union_feat"][1, 8, 0, 0] = 2.0 ** -20                 # inside the window
+    e["union_feat"][2, 9, 1, 1] = -0.0
     p = str(tmp_path / "v.nlvf")
     meta = FF.write_video(p, e)
-    assert meta["union"] == "sparse"
+    assert meta["union"] == "sparse12" and meta["union_nexc"] == 3
     hb = FF.Loader(pin=False).load([p])
-    want = e["union_feat"].bfloat16().permute(0, 2, 3, 1).reshape(-1, 2048).contiguous().view(torch.int16).numpy().view(np.uint16)
-    assert hb.union_rows == 2 and np.array_equal(_unpack_numpy(hb), want)
-    # and a wide positive range inside one row
-    e = _entries()[0]
-    e["union_feat"][0, :, 0, 0] = torch.relu(e["union_feat"][0, :, 0, 0]) + 1.0
-    e["union_feat"][0, 7, 0, 0] = 1e-30
-    assert FF.write_video(p, e)["union"] == "sparse"
-    e["union_feat"][0, 7, 0, 0] = 2.0 ** -20                      # 21 binades below: still inside 16 high bytes
-    assert FF.write_video(p, e)["union"] == "sparse12"
-    hb = FF.Loader(pin=False).load([p])
-    want = e["union_feat"].bfloat16().permute(0, 2, 3, 1).reshape(-1, 2048).contiguous().view(torch.int16).numpy().view(np.uint16)
-    assert np.array_equal(_unpack_numpy(hb), want)
+    assert hb.union_rows == 3 and hb.union_exc_pos.numel() == 3 and np.array_equal(_unpack_numpy(hb), want_of(e))
+    # exceptions of the second video of a batch are re-based to batch-global rows
+    e2 = _entries()[1]
+    e2["union_feat"][3, 100, 2, 2] = -2.0
+    paths = FF.write_videos(str(tmp_path / "two"), [e, e2])
+    hb = FF.Loader(pin=False).load(paths)
+    assert hb.union_exc_pos.numel() == 4 and np.array_equal(_unpack_numpy(hb), np.concatenate([want_of(e), want_of(e2)]))
+    # mixed signs everywhere: half of the values are exceptions -> 16-bit values, for the whole set
+    g = torch.Generator().manual_seed(0)
+    e3 = _entries()[2]
+    e3["union_feat"] = torch.randn(e3["union_feat"].shape, generator=g) * (torch.rand(e3["union_feat"].shape, generator=g) > 0.5)
+    assert FF.write_video(p, e3)["union"] == "sparse"
+    paths = FF.write_videos(str(tmp_path / "three"), [e, e3])
+    assert [FF.read_header(q)["union"] for q in paths] == ["sparse", "sparse"]
+    hb = FF.Loader(pin=False).load(paths)
+    assert hb.union_rows == 2 and np.array_equal(_unpack_numpy(hb), np.concatenate([want_of(e), want_of(e3)]))
 
 
 def test_dense_union_and_full_distribution_fallbacks(tmp_path):

@@ -16,6 +16,9 @@ pytestmark = pytest.mark.gpu
 def test_union_unpack_kernel_matches_numpy(cuda_lib, tmp_path, pack12):
     from nlvsgg_b200 import _C
     entries = _entries()
+    if pack12:                                   # values outside their rows' windows: exceptions patched after the decode
+        entries[0]["union_feat"][0, 5, 3, 3] = -1.5
+        entries[1]["union_feat"][2, 7, 0, 0] = 1e-30
     hb = FF.Loader(pin=False).load(FF.write_videos(str(tmp_path), entries, pack12=pack12))
     want = _unpack_numpy(hb)
     ref = M.collate(entries, "sgdet").union_feat.bfloat16().permute(0, 2, 3, 1).reshape(-1, 2048).contiguous()
@@ -28,6 +31,9 @@ def test_union_unpack_kernel_matches_numpy(cuda_lib, tmp_path, pack12):
         hx, base = hb.union_hx.cuda(), hb.union_base.cuda()
         _C.check(_C.lib().nlv_union_unpack12(vp(bm.data_ptr()), vp(off.data_ptr()), vp(vals.data_ptr()), vp(hx.data_ptr()), vp(base.data_ptr()),
                                              ctypes.c_longlong(want.shape[0]), vp(out.data_ptr()), None), "union_unpack12")
+        ep, ev = hb.union_exc_pos.cuda(), hb.union_exc_val.cuda()
+        assert ep.numel() == 2
+        _C.check(_C.lib().nlv_union_patch(vp(out.data_ptr()), vp(ep.data_ptr()), vp(ev.data_ptr()), ep.numel(), None), "union_patch")
     else:
         _C.check(_C.lib().nlv_union_unpack(vp(bm.data_ptr()), vp(off.data_ptr()), vp(vals.data_ptr()),
                                            ctypes.c_longlong(want.shape[0]), vp(out.data_ptr()), None), "union_unpack")
