@@ -575,21 +575,39 @@ def main():
         """every step copies its own inputs from pinned host memory; the copy for step i+1 is issued on a side stream before step i
         computes, so transfers and compute overlap in steady state; every step's loss is copied back to the host behind the step
         and read there one step later (while the next step runs), the last one before the closing event"""
+        import gc
         trainer.step_from_host(hb).item()
+        # the host is on this loop's critical path (it reads a loss every step): no cyclic-GC pauses inside it, and the host may run
+        # `lag` steps ahead of the device (every step's loss is still read, `lag` steps late, from its own pinned copy)
+        gc.collect(); gc.freeze(); gc.disable()
         barrier()
         ev0.record()
-        depth = int(os.environ.get("NLV_BENCH_PREFETCH", "2"))
-        queue = [trainer.prefetch(hb) for _ in range(min(depth, a.steps))]    # copies run up to two steps ahead of the compute
-        ticket = None
+        depth = int(os.environ.get("NLV_BENCH_PREFETCH", "3"))
+        lag = int(os.environ.get("NLV_BENCH_LOSS_LAG", "2"))
+        queue = [trainer.prefetch(hb) for _ in range(min(depth, a.steps))]    # copies run up to `depth` steps ahead of the compute
+        tickets = []
+        lv = None
+        t_step, t_pref, t_wait = [], [], []      # host milliseconds per step: enqueue of the step, of the next copies, wait for a loss
         for i in range(a.steps):
+            h0 = time.perf_counter()
             loss_t, _ = trainer.step_pipelined(queue.pop(0), None)            # step i is enqueued first ...
+            h1 = time.perf_counter()
             if i + depth < a.steps:
-                queue.append(trainer.prefetch(hb))                            # ... then the copies of step i+2 (behind those of i+1)
-            if ticket is not None:
-                lv = trainer.loss_value(ticket)      # step i-1's loss (its own D2H copy), read while step i runs
-            ticket = trainer.last_ticket
-        lv = trainer.loss_value(ticket)
+                queue.append(trainer.prefetch(hb))                            # ... then the copies of step i+depth (behind the earlier ones)
+            h2 = time.perf_counter()
+            tickets.append(trainer.last_ticket)
+            if len(tickets) > lag:
+                lv = trainer.loss_value(tickets.pop(0))      # step i-lag's loss (its own D2H copy), read while later steps run
+            h3 = time.perf_counter()
+            t_step.append(1e3 * (h1 - h0)); t_pref.append(1e3 * (h2 - h1)); t_wait.append(1e3 * (h3 - h2))
+        for tk in tickets:
+            lv = trainer.loss_value(tk)
         ev1.record()
+        med = lambda v: sorted(v)[len(v) // 2]
+        e2e_loop.host = {"enqueue_step_ms_median": round(med(t_step), 3), "enqueue_copies_ms_median": round(med(t_pref), 3),
+                         "wait_loss_ms_median": round(med(t_wait), 3), "enqueue_step_ms_max": round(max(t_step), 3),
+                         "enqueue_copies_ms_max": round(max(t_pref), 3)}
+        gc.enable(); gc.unfreeze()
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1) / a.steps], device=dev)
         if world > 1:
@@ -614,18 +632,20 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t.item())
 
+    # the clock sampler covers the timed region above; it is stopped here: the end-to-end loop has the host on its critical path and
+    # the sampler's NVML queries were one suspect for runs in which every step of that loop took 2-3x longer
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
     e2e = None
     if not a.no_e2e:
         ems, lv = e2e_loop(host)
         copy_ms = h2d_alone(host)
         e2e = {"value": total_frames / (ems / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-               "ms_per_step": ems, "last_loss": lv, "input_pipelining": "H2D copies run up to two steps ahead of the compute on a side stream; each loss is read one step late from its own pinned copy",
-               "host_format": in_fmt, "cpu_binding": numa,
+               "ms_per_step": ems, "last_loss": lv, "input_pipelining": "H2D copies run up to three steps ahead of the compute on a side stream; each loss is read two steps late from its own pinned copy",
+               "host_format": in_fmt, "cpu_binding": numa, "host_side": getattr(e2e_loop, "host", None),
                "h2d_alone_ms_per_step": copy_ms, "h2d_alone_gb_per_s_per_gpu": h2d_bytes / copy_ms / 1e6,
                "h2d_gb_per_s_if_copy_bound": h2d_bytes / ems / 1e6}
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
-
     # ---- rooflines: one instrumented step (every rank runs it: it contains the gradient allreduce) ----
     step_s, step_e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     recs = []

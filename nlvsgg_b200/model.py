@@ -93,6 +93,27 @@ def upload(hb: Batch, device, rasterise: bool = True, consumer_stream=None) -> B
     return b
 
 
+def upload_from_side_stream(hb: Batch, device, copy_stream) -> Batch:
+    """Device copy of a collated batch with the copies on `copy_stream` and the MEMORY from the current (consumer) stream's pool.
+
+    Destination blocks allocated under the copy stream (and handed to the consumer with record_stream) come back to the caching
+    allocator only once a cross-stream event has completed; when the next batch is allocated before that, the allocator calls
+    cudaMalloc — a device-wide synchronisation — every step, and the pipelined loop runs 3x slower for the whole run (seen as a
+    bimodal end-to-end time).  Blocks of the consumer's own pool are reusable in stream order the moment the previous batch is
+    dropped; the copy stream only has to wait for the work already enqueued on the consumer stream before overwriting them."""
+    dev = torch.device(device)
+    main = torch.cuda.current_stream(dev)
+    dst = {k: torch.empty_like(getattr(hb, k), device=dev) for k in TENSOR_KEYS if getattr(hb, k, None) is not None}
+    b = Batch()
+    b.__dict__.update(hb.__dict__)
+    copy_stream.wait_stream(main)
+    with torch.cuda.stream(copy_stream):
+        for k, d in dst.items():
+            d.copy_(getattr(hb, k), non_blocking=True)
+            setattr(b, k, d)
+    return b
+
+
 def ensure_masks(b: Batch) -> Batch:
     if b.spatial_masks is None:
         b.spatial_masks = ops.union_mask_pairs(b.boxes, b.pair_idx, 27, -0.5)

@@ -213,9 +213,9 @@ class Trainer:
         with torch.cuda.stream(self.copy_stream):
             plan = M.make_plan(host_batch, self.dev, self.mode, self.arch == "dsg", with_labels=True, consumer_stream=main,
                                label_rng=self.label_rng, stager=self.stager)
-            b = M.upload(host_batch, self.dev, rasterise=False, consumer_stream=main)
-            ev = torch.cuda.Event()
-            ev.record(self.copy_stream)
+        b = M.upload_from_side_stream(host_batch, self.dev, self.copy_stream)     # memory from the compute stream's pool
+        ev = torch.cuda.Event()
+        ev.record(self.copy_stream)
         return b, plan, ev
 
     def step_pipelined(self, handle, next_host=None):
