@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "profiles")
 GO = os.path.join(ROOT, "gpurun_out")
 RND = os.environ.get("ROUND", "r2")     # file-name prefix of this round
-STEPS_IN_RUN = 3   # bench.py --steps 1 --warmup 1: warm-up, timed, instrumented roofline step
+STEPS_IN_RUN = 7   # bench.py --steps 1 --warmup 1: warm-up, timed, and the 5 instrumented roofline steps (bench.PROFILE_STEPS)
 os.makedirs(OUT, exist_ok=True)
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1, "nsecond": 1, "us": 1e3, "usecond": 1e3, "ms": 1e6, "msecond": 1e6,
         "s": 1e9, "second": 1e9}
@@ -145,6 +145,11 @@ if __name__ == "__main__":
         wide_table(f"attn_full_raw_{RND}.csv", f"{RND}_attn_ncu.md", f"ncu --set full, varlen attention kernels of one training step ({RND})",
                    "`ncu --set full --clock-control none --import-source on -k regex:attn_`: forward kernels, the fused single-tile backward and the "
                    "two-kernel backward (which exits at once for segments the fused kernel took).")
+    if os.path.exists(os.path.join(GO, f"fin_full_raw_{RND}.csv")):
+        wide_table(f"fin_full_raw_{RND}.csv", f"{RND}_fused_kernels_ncu.md",
+                   f"ncu --set full, attention / mask-branch / feature-decode kernels of one training step ({RND}, end of round)",
+                   "`ncu --set full --clock-control none --import-source on -k regex:'attn_|mask_conv1|bn_apply_maxpool|pool_bn_bwd|union_unpack12' -c 20` "
+                   "(tools_dev/final_ncu_r2.sh; first step of the run, cold caches).")
     if os.path.exists(os.path.join(GO, f"tail_full_raw_{RND}.csv")):
         wide_table(f"tail_full_raw_{RND}.csv", f"{RND}_tail_ncu.md", f"ncu --set full, the memory-bound kernels of one training step ({RND})",
                    "`ncu --set full --clock-control none -k regex:'bn_|colsum|layernorm|union_unpack|maxpool|im2col|col2im|gather|split3|convert'` "
