@@ -577,37 +577,47 @@ def main():
         and read there one step later (while the next step runs), the last one before the closing event"""
         import gc
         trainer.step_from_host(hb).item()
-        # the host is on this loop's critical path (it reads a loss every step): no cyclic-GC pauses inside it, and the host may run
-        # `lag` steps ahead of the device (every step's loss is still read, `lag` steps late, from its own pinned copy)
+        depth = int(os.environ.get("NLV_BENCH_PREFETCH", "3"))
+        lag = int(os.environ.get("NLV_BENCH_LOSS_LAG", "2"))
+        t_step, t_pref, t_wait = [], [], []      # host milliseconds per step: enqueue of the step, of the next copies, wait for a loss
+
+        def run(n_steps):
+            """n_steps of the pipelined loop: copies up to `depth` steps ahead, every loss read `lag` steps late"""
+            queue = [trainer.prefetch(hb) for _ in range(min(depth, n_steps))]
+            tickets, last = [], None
+            for i in range(n_steps):
+                h0 = time.perf_counter()
+                trainer.step_pipelined(queue.pop(0), None)                        # step i is enqueued first ...
+                h1 = time.perf_counter()
+                if i + depth < n_steps:
+                    queue.append(trainer.prefetch(hb))                            # ... then the copies of step i+depth (behind the earlier ones)
+                h2 = time.perf_counter()
+                tickets.append(trainer.last_ticket)
+                if len(tickets) > lag:
+                    last = trainer.loss_value(tickets.pop(0))    # step i-lag's loss (its own D2H copy), read while later steps run
+                h3 = time.perf_counter()
+                t_step.append(1e3 * (h1 - h0)); t_pref.append(1e3 * (h2 - h1)); t_wait.append(1e3 * (h3 - h2))
+            for tk in tickets:
+                last = trainer.loss_value(tk)
+            return last
+
+        # warm-up THROUGH the pipelined path (the copy stream, the device blocks of three batches in flight and the staging ring are
+        # created on first use: runs that paid for them inside the timed region showed 0.3-1.3 s of one-time stall, read as a
+        # 2-3x slower step)
+        run(max(3, a.warmup))
+        torch.cuda.synchronize()
+        del t_step[:], t_pref[:], t_wait[:]
+        # the host is on this loop's critical path (it reads a loss every step): no cyclic-GC pauses inside it
         gc.collect(); gc.freeze(); gc.disable()
         barrier()
         ev0.record()
-        depth = int(os.environ.get("NLV_BENCH_PREFETCH", "3"))
-        lag = int(os.environ.get("NLV_BENCH_LOSS_LAG", "2"))
-        queue = [trainer.prefetch(hb) for _ in range(min(depth, a.steps))]    # copies run up to `depth` steps ahead of the compute
-        tickets = []
-        lv = None
-        t_step, t_pref, t_wait = [], [], []      # host milliseconds per step: enqueue of the step, of the next copies, wait for a loss
-        for i in range(a.steps):
-            h0 = time.perf_counter()
-            loss_t, _ = trainer.step_pipelined(queue.pop(0), None)            # step i is enqueued first ...
-            h1 = time.perf_counter()
-            if i + depth < a.steps:
-                queue.append(trainer.prefetch(hb))                            # ... then the copies of step i+depth (behind the earlier ones)
-            h2 = time.perf_counter()
-            tickets.append(trainer.last_ticket)
-            if len(tickets) > lag:
-                lv = trainer.loss_value(tickets.pop(0))      # step i-lag's loss (its own D2H copy), read while later steps run
-            h3 = time.perf_counter()
-            t_step.append(1e3 * (h1 - h0)); t_pref.append(1e3 * (h2 - h1)); t_wait.append(1e3 * (h3 - h2))
-        for tk in tickets:
-            lv = trainer.loss_value(tk)
+        lv = run(a.steps)
         ev1.record()
+        gc.enable(); gc.unfreeze()
         med = lambda v: sorted(v)[len(v) // 2]
         e2e_loop.host = {"enqueue_step_ms_median": round(med(t_step), 3), "enqueue_copies_ms_median": round(med(t_pref), 3),
                          "wait_loss_ms_median": round(med(t_wait), 3), "enqueue_step_ms_max": round(max(t_step), 3),
-                         "enqueue_copies_ms_max": round(max(t_pref), 3)}
-        gc.enable(); gc.unfreeze()
+                         "enqueue_copies_ms_max": round(max(t_pref), 3), "wait_loss_ms_max": round(max(t_wait), 3)}
         barrier()
         t = torch.tensor([ev0.elapsed_time(ev1) / a.steps], device=dev)
         if world > 1:
