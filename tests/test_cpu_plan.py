@@ -94,3 +94,17 @@ def test_dsg_class_sequences_and_subject_ranks():
     assert pos.tolist() == [0, 0, 1, 2, 2, 0, 1, 2]
     assert np.array_equal(p.cls_iperm.numpy()[perm], np.arange(8))
     assert [tuple(x[:3]) for x in p.cls_work.numpy()] == [(0, 5, 0), (5, 3, 0)]
+
+
+def test_long_first_orders_items_of_long_segments_in_front():
+    """Work lists are ordered long-first (segments of more than 16 rows) so that the two-kernel attention backward is launched
+    over those items only (nlv_attn_bwd_sorted); the order inside each class is kept."""
+    import numpy as np
+    from nlvsgg_b200.plan import long_first, work_items
+    w = work_items(np.array([0, 5, 45, 50]), np.array([5, 40, 5, 17]))
+    out, n_long = long_first(w)
+    assert n_long == 3 + 2 and len(out) == len(w)
+    assert (out[:n_long, 1] > 16).all() and (out[n_long:, 1] <= 16).all()
+    assert out[:n_long].tolist() == [r for r in w.tolist() if r[1] > 16] and out[n_long:].tolist() == [r for r in w.tolist() if r[1] <= 16]
+    short_only, n0 = long_first(work_items(np.array([0, 7]), np.array([7, 9])))
+    assert n0 == 0 and short_only.tolist() == work_items(np.array([0, 7]), np.array([7, 9])).tolist()
